@@ -1,0 +1,516 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// The reference's own unit tests for the hot path, re-expressed against the oracle runtime.
+// Each case cites the test it restates; assertions are the reference's (virtual-time
+// outcomes, set cardinalities) — the reference holds no golden vectors.
+#include <cstdio>
+#include <set>
+
+#include "workloads.hpp"
+
+using namespace msim_oracle;
+
+static int g_failed = 0;
+#define CHECK(c)                                                   \
+  do {                                                             \
+    if (!(c)) {                                                    \
+      std::printf("  CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); \
+      g_failed++;                                                  \
+    }                                                              \
+  } while (0)
+#define ASSERT_PANIC(c) \
+  do {                  \
+    if (!(c)) panic(std::string("assertion failed: ") + #c); \
+  } while (0)
+
+template <class Fn>
+static void run_case(const char* name, Fn fn) {
+  int before = g_failed;
+  try {
+    fn();
+  } catch (std::exception& e) {
+    std::printf("  EXCEPTION in %s: %s\n", name, e.what());
+    g_failed++;
+  }
+  std::printf("%s %s\n", g_failed == before ? "ok  " : "FAIL", name);
+}
+
+using Flag = std::shared_ptr<u32>;
+
+static Async<Unit> tick_loop(Flag flag, u64 period) {
+  for (;;) {
+    co_await sleep(period);
+    *flag += 2;
+  }
+}
+
+// task/mod.rs:849-856
+static Async<Unit> one(int) { co_return {}; }
+static Async<Unit> spawn_in_block_on_main() {
+  (co_await spawn(one(1))).unwrap();
+  (co_await spawn(one(2))).unwrap();
+  co_return {};
+}
+
+// task/mod.rs:858-900 kill
+static Async<Unit> kill_main(Runtime* rt, u64 node1, Flag flag1, Flag flag2) {
+  u64 t0 = now();
+  co_await sleep_until(t0 + 3 * SEC);
+  ASSERT_PANIC(*flag1 == 2);
+  ASSERT_PANIC(*flag2 == 2);
+  rt->kill(node1);
+  rt->kill(node1);
+  ASSERT_PANIC(rt->is_exit(node1));
+  co_await sleep_until(t0 + 5 * SEC);
+  ASSERT_PANIC(*flag1 == 2);
+  ASSERT_PANIC(*flag2 == 4);
+  co_return {};
+}
+
+// task/mod.rs:902-937 restart
+static Async<Unit> restart_worker(Flag flag) {
+  *flag = 0;
+  for (;;) {
+    co_await sleep(2 * SEC);
+    *flag += 2;
+  }
+}
+static Async<Unit> restart_main(Runtime* rt, u64 node, Flag flag) {
+  u64 t0 = now();
+  co_await sleep_until(t0 + 3 * SEC);
+  ASSERT_PANIC(*flag == 2);
+  rt->kill(node);
+  rt->restart(node);
+  ASSERT_PANIC(!rt->is_exit(node));
+  co_await sleep_until(t0 + 6 * SEC);
+  ASSERT_PANIC(*flag == 2);
+  co_await sleep_until(t0 + 8 * SEC);
+  ASSERT_PANIC(*flag == 4);
+  co_return {};
+}
+
+// task/mod.rs:939-963 restart_on_panic
+static Async<Unit> rop_worker(Flag flag) {
+  u32 old = (*flag)++;
+  if (old < 3) panic("explicit panic");
+  co_return {};
+}
+static Async<Unit> rop_main(Flag flag) {
+  co_await sleep(60 * SEC);
+  ASSERT_PANIC(*flag == 4);
+  co_return {};
+}
+// task/mod.rs:965-983 restart_on_panic_matching (should panic with "2")
+static Async<Unit> ropm_worker(Flag flag) {
+  u32 old = (*flag)++;
+  panic(std::to_string(old));
+  co_return {};
+}
+static Async<Unit> pending_main() {
+  co_await PendingForever<Unit>{};
+  co_return {};
+}
+
+// task/mod.rs:985-1016 pause_resume
+static Async<Unit> pause_main(Runtime* rt, u64 node, Flag flag) {
+  u64 t0 = now();
+  co_await sleep_until(t0 + 3 * SEC);
+  ASSERT_PANIC(*flag == 2);
+  rt->pause(node);
+  rt->pause(node);
+  co_await sleep_until(t0 + 5 * SEC);
+  ASSERT_PANIC(*flag == 2);
+  rt->resume(node);
+  rt->resume(node);
+  co_await sleep_until(t0 + 5500 * MS);
+  ASSERT_PANIC(*flag == 4);
+  co_return {};
+}
+
+// task/mod.rs:1018-1041 random_select_from_ready_tasks
+static Async<Unit> seq_task(std::shared_ptr<std::vector<int>> out, int i) {
+  for (int j = 0; j < 5; j++) {
+    out->push_back(i * 10 + j);
+    co_await YieldNow{};
+  }
+  co_return {};
+}
+static Async<Unit> seq_main(std::shared_ptr<std::vector<int>> out) {
+  std::vector<JoinHandle<Unit>> tasks;
+  for (int i = 0; i < 3; i++) tasks.push_back(spawn(seq_task(out, i)));
+  for (auto& t : tasks) (co_await t).unwrap();  // join_all polls in order; outcome identical here
+  co_return {};
+}
+
+// task/mod.rs:1113-1139 kill_drop_futures
+struct DropProbe {
+  std::shared_ptr<int> counter;
+  ~DropProbe() {
+    if (counter) (*counter)++;
+  }
+  DropProbe(std::shared_ptr<int> c) : counter(std::move(c)) {}
+  DropProbe(DropProbe&& o) noexcept : counter(std::move(o.counter)) {}
+};
+static Async<Unit> kdf_worker(DropProbe probe) {
+  co_await PendingForever<Unit>{};
+  (void)probe;
+  co_return {};
+}
+static Async<Unit> kdf_main(Runtime* rt, u64 node, std::shared_ptr<int> dropped) {
+  co_await sleep(1 * SEC);
+  rt->kill(node);
+  ASSERT_PANIC(*dropped == 0);  // strong_count == 2
+  co_await sleep(1 * SEC);
+  ASSERT_PANIC(*dropped == 1);  // future dropped after a while
+  co_return {};
+}
+
+// task/mod.rs:1141-1155 join_cancelled
+static Async<Unit> jc_main(JoinHandle<Unit> h) {
+  h.abort();
+  auto r = co_await h;
+  ASSERT_PANIC(r.is_err() && r.err == Err::Cancelled);
+  co_return {};
+}
+
+// task/mod.rs:1157-1187 exited
+static Async<Unit> exited_init(Flag flag) {
+  spawn(tick_loop(flag, 2 * SEC));
+  co_await sleep(5 * SEC);
+  co_return {};  // exit here: the spawned task is killed
+}
+static Async<Unit> exited_main(Runtime* rt, u64 node, Flag flag) {
+  ASSERT_PANIC(!rt->is_exit(node));
+  co_await sleep(10 * SEC);
+  ASSERT_PANIC(rt->is_exit(node));
+  ASSERT_PANIC(*flag == 4);
+  co_return {};
+}
+
+// time/mod.rs:263-304
+static Async<Unit> time_main() {
+  u64 t0 = now();
+  co_await sleep(1 * SEC);
+  ASSERT_PANIC(now() - t0 >= 1 * SEC);
+  co_await sleep_until(t0 + 2 * SEC);
+  ASSERT_PANIC(now() - t0 >= 2 * SEC);
+  auto r = co_await timeout(2 * SEC, sleep(1 * SEC));
+  ASSERT_PANIC(r.is_ok());
+  auto r2 = co_await timeout(1 * SEC, sleep(2 * SEC));
+  ASSERT_PANIC(r2.is_err());
+  // advance
+  u64 t1 = now();
+  advance(1 * SEC);
+  ASSERT_PANIC(now() - t1 == 1 * SEC);
+  co_return {};
+}
+
+// net/endpoint.rs:372-408 send_recv (Barrier → both sides sleep until t=1s)
+static Async<Unit> sr_node1(SocketAddr a1, SocketAddr a2) {
+  Endpoint net = std::move((co_await Endpoint::bind(a1)).unwrap());
+  co_await sleep_until(1 * SEC);
+  Payload p1;
+  p1.v[0] = 1;
+  (co_await net.send_to(a2, 1, p1)).unwrap();
+  co_await sleep(1 * SEC);
+  Payload p2;
+  p2.v[0] = 2;
+  (co_await net.send_to(a2, 2, p2)).unwrap();
+  co_return {};
+}
+static Async<Unit> sr_node2(SocketAddr a1, SocketAddr a2) {
+  Endpoint net = std::move((co_await Endpoint::bind(a2)).unwrap());
+  co_await sleep_until(1 * SEC);
+  auto [d2, from2] = (co_await net.recv_from(2)).unwrap();
+  ASSERT_PANIC(from2 == a1 && d2.v[0] == 2);
+  auto [d1, from1] = (co_await net.recv_from(1)).unwrap();
+  ASSERT_PANIC(from1 == a1 && d1.v[0] == 1);
+  co_return {};
+}
+// net/endpoint.rs:410-443 receiver_drop
+static Async<Unit> rd_node1(SocketAddr a1, SocketAddr a2) {
+  Endpoint net = std::move((co_await Endpoint::bind(a1)).unwrap());
+  co_await sleep_until(2 * SEC);
+  Payload p1;
+  p1.v[0] = 1;
+  (co_await net.send_to(a2, 1, p1)).unwrap();
+  co_return {};
+}
+static Async<Unit> rd_node2(SocketAddr a1, SocketAddr a2) {
+  Endpoint net = std::move((co_await Endpoint::bind(a2)).unwrap());
+  auto r = co_await timeout(1 * SEC, net.recv_from(1));
+  ASSERT_PANIC(r.is_err());  // timeout and receiver dropped here
+  co_await sleep_until(2 * SEC);
+  auto [d, from] = (co_await net.recv_from(1)).unwrap();  // receive again should succeed
+  ASSERT_PANIC(from == a1 && d.v[0] == 1);
+  co_return {};
+}
+// net/endpoint.rs:469-512 bind
+static Async<Unit> bind_case() {
+  u32 ip = ip4(10, 0, 0, 1);
+  {
+    Endpoint ep = std::move((co_await Endpoint::bind(SocketAddr{IP_UNSPECIFIED, 0})).unwrap());
+    ASSERT_PANIC(ep.local_addr().ip == IP_UNSPECIFIED && ep.local_addr().port != 0);
+  }
+  {
+    Endpoint ep = std::move((co_await Endpoint::bind(SocketAddr{IP_LOCALHOST, 0})).unwrap());
+    ASSERT_PANIC(ep.local_addr().ip == IP_LOCALHOST && ep.local_addr().port != 0);
+  }
+  auto bad = co_await Endpoint::bind(SocketAddr{ip4(10, 0, 0, 2), 0});
+  ASSERT_PANIC(bad.is_err() && bad.err == Err::AddrNotAvailable);
+  {
+    Endpoint ep = std::move((co_await Endpoint::bind(SocketAddr{ip, 100})).unwrap());
+    ASSERT_PANIC(ep.local_addr() == (SocketAddr{ip, 100}));
+    auto dup = co_await Endpoint::bind(SocketAddr{ip, 100});
+    ASSERT_PANIC(dup.is_err() && dup.err == Err::AddrInUse);
+  }  // drop and reuse port
+  (co_await Endpoint::bind(SocketAddr{ip, 100})).unwrap();
+  co_return {};
+}
+// net/endpoint.rs:514-548 localhost
+static Async<Unit> lh_node1() {
+  Endpoint ep1 = std::move((co_await Endpoint::bind(SocketAddr{IP_LOCALHOST, 1})).unwrap());
+  Endpoint ep2 = std::move((co_await Endpoint::bind(SocketAddr{ip4(10, 0, 0, 1), 2})).unwrap());
+  co_await sleep_until(1 * SEC);
+  auto r = co_await timeout(1 * SEC, ep1.recv_from(1));
+  ASSERT_PANIC(r.is_err());  // localhost endpoint should not receive from other nodes
+  auto [d, from] = (co_await ep2.recv_from(1)).unwrap();
+  ASSERT_PANIC(from == (SocketAddr{ip4(10, 0, 0, 2), 1}));
+  co_return {};
+}
+static Async<Unit> lh_node2() {
+  Endpoint ep = std::move((co_await Endpoint::bind(SocketAddr{IP_LOCALHOST, 1})).unwrap());
+  co_await sleep_until(1 * SEC);
+  Payload p;
+  (co_await ep.send_to(SocketAddr{ip4(10, 0, 0, 1), 1}, 1, p)).unwrap();
+  (co_await ep.send_to(SocketAddr{ip4(10, 0, 0, 1), 2}, 1, p)).unwrap();
+  co_return {};
+}
+// net/rpc.rs doc example :15-61 — call / add_rpc_handler round trip
+static Async<Payload> echo_plus_one(Payload q) {
+  Payload r;
+  r.v[0] = q.v[0] + 1;
+  co_return r;
+}
+static Async<Unit> rpc_server(SocketAddr a) {
+  Endpoint ep = std::move((co_await Endpoint::bind(a)).unwrap());
+  ep.add_rpc_handler(77, [](Payload q) { return echo_plus_one(q); });
+  co_await PendingForever<Unit>{};
+  co_return {};
+}
+static Async<Unit> rpc_client(SocketAddr server) {
+  co_await sleep(1 * SEC);
+  Endpoint ep = std::move((co_await Endpoint::bind(SocketAddr{IP_UNSPECIFIED, 0})).unwrap());
+  for (u32 i = 0; i < 5; i++) {
+    Payload q;
+    q.v[0] = i;
+    Payload r = (co_await ep.call(server, 77, q)).unwrap();
+    ASSERT_PANIC(r.v[0] == i + 1);
+  }
+  // a call to nobody times out
+  Payload q;
+  auto r = co_await ep.call_timeout(SocketAddr{ip4(10, 0, 0, 9), 1}, 77, q, 1 * SEC);
+  ASSERT_PANIC(r.is_err() && r.err == Err::TimedOut);
+  co_return {};
+}
+
+template <class T>
+static Async<Unit> join_unwrap(JoinHandle<T> h) {
+  Result<T> r = co_await h;
+  r.unwrap();
+  co_return {};
+}
+
+int main() {
+  run_case("task::spawn_in_block_on", [] {
+    Runtime rt;
+    rt.block_on(spawn_in_block_on_main());
+  });
+  run_case("task::kill", [] {
+    Runtime rt;
+    auto n1 = rt.create_node().build();
+    auto n2 = rt.create_node().build();
+    Flag f1 = std::make_shared<u32>(0), f2 = std::make_shared<u32>(0);
+    n1.spawn(tick_loop(f1, 2 * SEC));
+    n2.spawn(tick_loop(f2, 2 * SEC));
+    rt.block_on(kill_main(&rt, n1.id(), f1, f2));
+  });
+  run_case("task::restart", [] {
+    Runtime rt;
+    Flag flag = std::make_shared<u32>(0);
+    auto n = rt.create_node().init([flag] { return restart_worker(flag); }).build();
+    rt.block_on(restart_main(&rt, n.id(), flag));
+  });
+  run_case("task::restart_on_panic", [] {
+    Runtime rt;
+    Flag flag = std::make_shared<u32>(0);
+    rt.create_node().init([flag] { return rop_worker(flag); }).restart_on_panic().build();
+    rt.block_on(rop_main(flag));
+    CHECK(*flag == 4);
+  });
+  run_case("task::restart_on_panic_matching", [] {
+    Runtime rt;
+    Flag flag = std::make_shared<u32>(0);
+    rt.create_node()
+        .init([flag] { return ropm_worker(flag); })
+        .restart_on_panic_matching("0")
+        .restart_on_panic_matching("1")
+        .build();
+    bool panicked_with_2 = false;
+    try {
+      rt.block_on(pending_main());
+    } catch (Panic& e) {
+      panicked_with_2 = std::string(e.what()) == "2";
+    }
+    CHECK(panicked_with_2);
+  });
+  run_case("task::pause_resume", [] {
+    Runtime rt;
+    auto n = rt.create_node().build();
+    Flag flag = std::make_shared<u32>(0);
+    n.spawn(tick_loop(flag, 2 * SEC));
+    rt.block_on(pause_main(&rt, n.id(), flag));
+  });
+  run_case("task::random_select_from_ready_tasks", [] {
+    std::set<std::vector<int>> seqs;
+    for (u64 seed = 0; seed < 10; seed++) {
+      Runtime rt(seed);
+      auto out = std::make_shared<std::vector<int>>();
+      rt.block_on(seq_main(out));
+      CHECK(out->size() == 15);
+      seqs.insert(*out);
+    }
+    CHECK(seqs.size() == 10);
+  });
+  run_case("task::kill_drop_futures", [] {
+    Runtime rt;
+    auto n = rt.create_node().build();
+    auto dropped = std::make_shared<int>(0);
+    n.spawn(kdf_worker(DropProbe(dropped)));
+    rt.block_on(kdf_main(&rt, n.id(), dropped));
+  });
+  run_case("task::join_cancelled", [] {
+    Runtime rt;
+    auto n = rt.create_node().build();
+    auto h = n.spawn(pending_main());
+    rt.block_on(jc_main(h));
+  });
+  run_case("task::exited", [] {
+    Runtime rt;
+    Flag flag = std::make_shared<u32>(0);
+    auto n = rt.create_node().init([flag] { return exited_init(flag); }).build();
+    rt.block_on(exited_main(&rt, n.id(), flag));
+  });
+  run_case("task::deadlock_panics (runtime/mod.rs:118-125)", [] {
+    Runtime rt;
+    bool dl = false;
+    try {
+      rt.block_on(pending_main());
+    } catch (Deadlock&) {
+      dl = true;
+    }
+    CHECK(dl);
+  });
+  run_case("time::sleep/timeout/advance", [] {
+    Runtime rt;
+    rt.block_on(time_main());
+  });
+  run_case("time::time_limit (task/mod.rs:253-258)", [] {
+    Runtime rt;
+    rt.set_time_limit(5 * SEC);
+    bool tl = false;
+    try {
+      rt.block_on(wl_sleep_main(10 * SEC));
+    } catch (TimeLimitExceeded&) {
+      tl = true;
+    }
+    CHECK(tl);
+  });
+  run_case("rand::deterministic per seed, distinct across seeds (rand.rs:312-354)", [] {
+    std::set<u64> firsts;
+    for (u64 seed = 0; seed < 3; seed++)
+      for (int rep = 0; rep < 3; rep++) {
+        Runtime rt(seed);
+        firsts.insert(rt.rand.gen_u64());
+      }
+    CHECK(firsts.size() == 3);
+  });
+  run_case("time::system_time base ~2022 (time/mod.rs:26-33)", [] {
+    Runtime rt(0);
+    u64 y2022 = 60ull * 60 * 24 * 365 * 52;
+    CHECK(rt.task.time.base_time_secs() >= y2022 && rt.task.time.base_time_secs() < y2022 + 31536000ull);
+    CHECK(rt.task.time.base_time_secs() - y2022 == 10235805ull);  // SURVEY Appendix B [DERIVED]
+  });
+  auto two_nodes = [](auto f1, auto f2, bool join_first = false) {
+    Runtime rt;
+    SocketAddr a1{ip4(10, 0, 0, 1), 1}, a2{ip4(10, 0, 0, 2), 1};
+    auto n1 = rt.create_node().ip(a1.ip).build();
+    auto n2 = rt.create_node().ip(a2.ip).build();
+    auto h1 = n1.spawn(f1(a1, a2));
+    auto h2 = n2.spawn(f2(a1, a2));
+    if (join_first) rt.block_on(join_unwrap(h1));
+    rt.block_on(join_unwrap(h2));
+  };
+  run_case("net::send_recv", [&] { two_nodes(sr_node1, sr_node2); });
+  run_case("net::receiver_drop", [&] { two_nodes(rd_node1, rd_node2); });
+  run_case("net::bind", [] {
+    Runtime rt;
+    auto n = rt.create_node().ip(ip4(10, 0, 0, 1)).build();
+    auto h = n.spawn(bind_case());
+    rt.block_on(join_unwrap(h));
+  });
+  run_case("net::localhost", [&] {
+    two_nodes([](SocketAddr, SocketAddr) { return lh_node1(); }, [](SocketAddr, SocketAddr) { return lh_node2(); },
+              true);
+  });
+  run_case("net::connect_send_recv == pingpong(1 round)", [] {
+    Runtime rt;
+    u32 done = rt.block_on(wl_pingpong_main(1, 10 * MS));
+    CHECK(done == 1);
+  });
+  run_case("rpc::call / call_timeout / add_rpc_handler", [] {
+    Runtime rt;
+    SocketAddr a1{ip4(10, 0, 0, 1), 1};
+    auto n1 = rt.create_node().ip(a1.ip).build();
+    auto n2 = rt.create_node().ip(ip4(10, 0, 0, 2)).build();
+    n1.spawn(rpc_server(a1));
+    auto h = n2.spawn(rpc_client(a1));
+    rt.block_on(join_unwrap(h));
+  });
+  run_case("check_determinism log (runtime/mod.rs:178-202)", [] {
+    std::vector<u8> log;
+    {
+      Runtime rt(7);
+      rt.rand.enable_log();
+      rt.block_on(wl_pingpong_main(3, 10 * MS));
+      log = *rt.rand.take_log();
+    }
+    CHECK(!log.empty());
+    {
+      Runtime rt(7);
+      rt.rand.enable_check(log);
+      rt.block_on(wl_pingpong_main(3, 10 * MS));  // must not panic
+    }
+    bool detected = false;
+    try {
+      Runtime rt(8);
+      rt.rand.enable_check(log);
+      rt.block_on(wl_pingpong_main(3, 10 * MS));
+    } catch (Panic&) {
+      detected = true;
+    }
+    CHECK(detected);
+  });
+  run_case("workload::raft elects exactly one leader", [] {
+    for (u64 seed = 0; seed < 20; seed++) {
+      Runtime rt(seed);
+      auto c = std::make_shared<RaftCluster>();
+      RaftOutcome out;
+      rt.block_on(wl_raft_main(c, &out));
+      CHECK(out.leader >= 1 && out.leader <= 5);
+      CHECK(out.term >= 1);
+      rt.teardown();
+    }
+  });
+  std::printf("%s (%d failed)\n", g_failed ? "SELFTEST FAILED" : "SELFTEST PASSED", g_failed);
+  return g_failed ? 1 : 0;
+}

@@ -1,0 +1,970 @@
+// msim_b200 engine — the per-seed executor step, one lane per seed.
+//
+// Replaces, for registered workloads, the reference's hot path:
+//   Executor::block_on / run_all_ready        madsim/src/sim/task/mod.rs:220-323
+//   mpsc::Receiver::try_recv_random            madsim/src/sim/utils/mpsc.rs:73-83
+//   TimeRuntime::advance_to_next_event         madsim/src/sim/time/mod.rs:45-60
+//   TimeHandle::{advance,sleep,add_timer}      madsim/src/sim/time/mod.rs:103-124,158-169
+//   naive_timer::Timer (BinaryHeap)            crate naive-timer 0.2 + std BinaryHeap sift rules
+//   GlobalRng / xoshiro256++ / gen_range       madsim/src/sim/rand.rs:42-89 + rand 0.8 / rand_xoshiro 0.6
+//   NetSim::{rand_delay,send}, Network::*      madsim/src/sim/net/mod.rs:287-333, network.rs:142-313
+//   Endpoint mailbox                           madsim/src/sim/net/endpoint.rs:298-363
+//   TaskHandle::{kill,restart,pause,resume}    madsim/src/sim/task/mod.rs:356-424
+//
+// Design (B200-first, not a translation): all per-seed state is a bounded, columnar block
+// `field[slot][seed]` that lives in shared memory while a CTA advances its seeds (staged from /
+// to HBM with bulk async copies by the kernel, see kernel.cu); the hot scalars (rng, clock,
+// trace hash, queue lengths) are cached in registers for the whole burst.  Arbitrary futures
+// become explicit poll-level state machines (workloads/*.h).  Every bounded table reports
+// overflow as MSIM_ST_FAIL_CAPACITY — never silently.
+#pragma once
+#include "defs.h"
+
+namespace msim {
+
+constexpr int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+/// Compile-time layout of one seed's state block for capacities `C`.
+template <class C>
+struct Layout {
+  static_assert(C::NT <= 128, "task bitmap is 2 x u64");
+  static_assert(C::NMSG <= 64, "message bitmap is 1 x u64");
+  static_assert(C::NT < 255 && C::NMSG < 255 && C::NSOCK < 255, "u8 indices");
+  // ---- u64 section (element offsets) ----
+  static constexpr int Q_RNG = 0;      // 4
+  static constexpr int Q_NOW = 4;
+  static constexpr int Q_HASH = 5;
+  static constexpr int Q_DRAWS = 6;
+  static constexpr int Q_TFREE = 7;    // 2: free-task bitmap
+  static constexpr int Q_MFREE = 9;    // free-message bitmap
+  static constexpr int Q_HEAP_DL = 10;                      // [TQ] timer deadlines (implicit binary heap)
+  static constexpr int Q_T_DL0 = Q_HEAP_DL + C::TQ;         // [NT] Sleep deadline of the task's current await
+  static constexpr int Q_T_DL1 = Q_T_DL0 + C::NT;           // [NT] timeout deadline / generic u64 local
+  static constexpr int Q_M_TAG = Q_T_DL1 + C::NT;           // [NMSG]
+  static constexpr int Q_M_W = Q_M_TAG + C::NMSG;           // [NMSG] payload.w (rpc response tag)
+  static constexpr int Q_RG_TAG = Q_M_W + C::NMSG;          // [NSOCK*NREG] registered receive tags
+  static constexpr int Q_WL = Q_RG_TAG + C::NSOCK * C::NREG;  // [WQ*NNODE] workload per-node u64
+  static constexpr int NQ = Q_WL + C::WQ * C::NNODE;
+  // ---- u32 section ----
+  enum : int {
+    W_EV_POP = 0, W_EV_FIRE, W_HEAP_LEN, W_RQ_LEN, W_NEXT_SPAWN, W_MSG_COUNT, W_STATUS, W_FAIL_CODE,
+    W_PEAK_TIMERS, W_LIVE_TASKS, W_PEAK_TASKS, W_USER0, W_USER1, W_USER2, W_USER3, W_CLOG_IN, W_CLOG_OUT,
+    W_PK_LEN, W_BASE_SECS, W_NEXT_NODE, W_MAIN_SLOT, W_PANIC_CODE, W_NSCALAR
+  };
+  static constexpr int W_CLOG_LINK = W_NSCALAR;                 // [NNODE] bit d set: link n→d clogged
+  static constexpr int W_HEAP_PL = W_CLOG_LINK + C::NNODE;      // [TQ]
+  static constexpr int W_T_SPAWN = W_HEAP_PL + C::TQ;           // [NT] spawn index (NONE32 = free slot)
+  static constexpr int W_T_AW = W_T_SPAWN + C::NT;              // [NT] awaiter (slot<<20|gen) or NONE32
+  static constexpr int W_T_A = W_T_AW + C::NT;                  // [NT] locals
+  static constexpr int W_T_B = W_T_A + C::NT;
+  static constexpr int W_T_C = W_T_B + C::NT;
+  static constexpr int W_M_V0 = W_T_C + C::NT;                  // [NMSG] payload v[0]
+  static constexpr int W_M_V1 = W_M_V0 + C::NMSG;
+  static constexpr int W_M_FROM = W_M_V1 + C::NMSG;             // source address
+  static constexpr int W_M_DST = W_M_FROM + C::NMSG;            // sock<<16 | gen16, captured at send
+  static constexpr int W_M_SERIAL = W_M_DST + C::NMSG;
+  static constexpr int W_RG_WAITER = W_M_SERIAL + C::NMSG;      // [NSOCK*NREG] slot<<20|gen
+  static constexpr int W_SK_PORTGEN = W_RG_WAITER + C::NSOCK * C::NREG;  // [NSOCK] port | gen<<16
+  static constexpr int W_WL = W_SK_PORTGEN + C::NSOCK;          // [WW*NNODE] workload per-node u32
+  static constexpr int W_WLS = W_WL + C::WW * C::NNODE;         // [WS] workload scalars
+  static constexpr int NW = W_WLS + C::WS;
+  // ---- u8 section ----
+  static constexpr int B_RQ = 0;                        // [NT] ready "queue": a Vec popped at a random index
+  static constexpr int B_T_KIND = B_RQ + C::NT;
+  static constexpr int B_T_PC = B_T_KIND + C::NT;
+  static constexpr int B_T_FLAGS = B_T_PC + C::NT;
+  static constexpr int B_T_NODE = B_T_FLAGS + C::NT;
+  static constexpr int B_T_EPOCH = B_T_NODE + C::NT;
+  static constexpr int B_T_SUB = B_T_EPOCH + C::NT;     // pc of the nested future (rpc call)
+  static constexpr int B_T_RX = B_T_SUB + C::NT;        // oneshot slot: delivered message or NONE8
+  static constexpr int B_T_SOCK = B_T_RX + C::NT;       // endpoint this future holds (BindGuard ref) or NONE8
+  static constexpr int B_T_SOCKGEN = B_T_SOCK + C::NT;
+  static constexpr int B_T_MSG = B_T_SOCKGEN + C::NT;   // message slot owned by the future or NONE8
+  static constexpr int B_MB = B_T_MSG + C::NT;          // [NSOCK*NMBOX] mailbox.msgs (message slots)
+  static constexpr int B_SK_NODE = B_MB + C::NSOCK * C::NMBOX;
+  static constexpr int B_SK_IPK = B_SK_NODE + C::NSOCK;
+  static constexpr int B_SK_STATE = B_SK_IPK + C::NSOCK;
+  static constexpr int B_SK_REGLEN = B_SK_STATE + C::NSOCK;
+  static constexpr int B_SK_MBLEN = B_SK_REGLEN + C::NSOCK;
+  static constexpr int B_SK_REFS = B_SK_MBLEN + C::NSOCK;
+  static constexpr int B_SK_EPOCH = B_SK_REFS + C::NSOCK;
+  static constexpr int B_N_FLAGS = B_SK_EPOCH + C::NSOCK;  // [NNODE]
+  static constexpr int B_N_EPOCH = B_N_FLAGS + C::NNODE;
+  static constexpr int B_PK = B_N_EPOCH + C::NNODE;        // [NPARK] parked runnables, park order
+  static constexpr int NB = B_PK + C::NPARK;
+
+  static constexpr int W_BASE = 8 * NQ;                 // byte offset (per seed) of the u32 section
+  static constexpr int B_BASE = W_BASE + 4 * NW;        // … of the u8 section
+  static constexpr int BYTES = round_up(B_BASE + NB, 16);  // per seed; a CTA's block is S * BYTES
+};
+
+/// One lane's view of its seed.  `WL` supplies Caps + the state machines.
+template <class WL>
+struct Engine {
+  using C = typename WL::Caps;
+  using L = Layout<C>;
+
+  unsigned char* base;  // start of the CTA's state block (shared memory on the device)
+  u32 S;                // seeds in the block
+  u32 s;                // this seed's column
+  const Params* P;
+  // register-cached hot state
+  u64 r0, r1, r2, r3, now, hash, draws;
+  u32 ev_pop, ev_fire, heap_len, rq_len, status, peak_timers;
+  // optional full trace (single-seed replay)
+  msim_trace_rec* tr;
+  u32 tr_cap, tr_n;
+
+  // ---------------- accessors ----------------
+  MSIM_HD u64& q(int off, int i = 0) const { return reinterpret_cast<u64*>(base)[(off + i) * S + s]; }
+  MSIM_HD u32& w(int off, int i = 0) const {
+    return reinterpret_cast<u32*>(base + (size_t)L::W_BASE * S)[(off + i) * S + s];
+  }
+  MSIM_HD u8& b(int off, int i = 0) const { return (base + (size_t)L::B_BASE * S)[(off + i) * S + s]; }
+
+  // task fields
+  MSIM_HD u8& t_kind(int t) const { return b(L::B_T_KIND, t); }
+  MSIM_HD u8& t_pc(int t) const { return b(L::B_T_PC, t); }
+  MSIM_HD u8& t_flags(int t) const { return b(L::B_T_FLAGS, t); }
+  MSIM_HD u8& t_node(int t) const { return b(L::B_T_NODE, t); }
+  MSIM_HD u8& t_epoch(int t) const { return b(L::B_T_EPOCH, t); }
+  MSIM_HD u8& t_sub(int t) const { return b(L::B_T_SUB, t); }
+  MSIM_HD u8& t_rx(int t) const { return b(L::B_T_RX, t); }
+  MSIM_HD u8& t_sock(int t) const { return b(L::B_T_SOCK, t); }
+  MSIM_HD u8& t_sockgen(int t) const { return b(L::B_T_SOCKGEN, t); }
+  MSIM_HD u8& t_msg(int t) const { return b(L::B_T_MSG, t); }
+  MSIM_HD u32& t_spawn(int t) const { return w(L::W_T_SPAWN, t); }
+  MSIM_HD u32& t_aw(int t) const { return w(L::W_T_AW, t); }
+  MSIM_HD u32& t_a(int t) const { return w(L::W_T_A, t); }
+  MSIM_HD u32& t_b(int t) const { return w(L::W_T_B, t); }
+  MSIM_HD u32& t_c(int t) const { return w(L::W_T_C, t); }
+  MSIM_HD u64& t_dl0(int t) const { return q(L::Q_T_DL0, t); }
+  MSIM_HD u64& t_dl1(int t) const { return q(L::Q_T_DL1, t); }
+  MSIM_HD u32 t_gen(int t) const { return t_spawn(t) & 0xfffffu; }
+  // nodes
+  MSIM_HD u8& n_flags(int n) const { return b(L::B_N_FLAGS, n); }
+  MSIM_HD u8& n_epoch(int n) const { return b(L::B_N_EPOCH, n); }
+  // workload storage
+  MSIM_HD u64& wl_q(int f, int n) const { return q(L::Q_WL, f * C::NNODE + n); }
+  MSIM_HD u32& wl_w(int f, int n) const { return w(L::W_WL, f * C::NNODE + n); }
+  MSIM_HD u32& wl_s(int i) const { return w(L::W_WLS, i); }
+
+  // ---------------- failure ----------------
+  MSIM_HD void fail(u32 st, u32 code) {
+    if (status == MSIM_ST_RUNNING) {
+      status = st;
+      w(L::W_FAIL_CODE) = code;
+    }
+  }
+  MSIM_HD void fail_cap(u32 which) { fail(MSIM_ST_FAIL_CAPACITY, which); }
+  MSIM_HD bool running() const { return status == MSIM_ST_RUNNING; }
+
+  // ---------------- trace ----------------
+  MSIM_HD static u64 mix(u64 h, u64 x) {
+    h ^= x;
+    h *= MSIM_HASH_MUL;
+    h ^= h >> 32;
+    return h;
+  }
+  MSIM_HD void trace(u64 t_now, u64 aux, u32 kind, u32 id24) {
+    u32 kind_id = (kind << 24) | (id24 & 0xffffffu);
+    u32 d = (u32)draws;
+    hash = mix(mix(mix(hash, t_now), aux), ((u64)kind_id << 32) | d);
+    if (tr) {
+      if (tr_n < tr_cap) {
+        tr[tr_n].now_ns = t_now;
+        tr[tr_n].aux = aux;
+        tr[tr_n].kind_id = kind_id;
+        tr[tr_n].draws = d;
+      }
+      tr_n++;
+    }
+  }
+
+  // ---------------- RNG (rand.rs + rand 0.8 + rand_xoshiro 0.6) ----------------
+  MSIM_HD u64 next_u64() {
+    draws++;
+    u64 result = rotl64(r0 + r3, 23) + r0;
+    u64 t = r1 << 17;
+    r2 ^= r0;
+    r3 ^= r1;
+    r1 ^= r2;
+    r0 ^= r3;
+    r2 ^= t;
+    r3 = rotl64(r3, 45);
+    return result;
+  }
+  /// Rng::gen_range(lo..hi) for u64/usize: UniformInt::sample_single (widening multiply + zone)
+  MSIM_HD u64 gen_range_u64(u64 lo, u64 hi) {
+    u64 range = hi - lo;
+    u64 zone = (range << clz64(range)) - 1;
+    for (;;) {
+      u64 v = next_u64();
+      u64 l = v * range;
+      if (l <= zone) return lo + mulhi64(v, range);
+    }
+  }
+  /// Uniform::<u64>::new_inclusive(lo, hi).sample — modulo zone (UniformDuration Medium)
+  MSIM_HD u64 sample_inclusive_u64(u64 lo, u64 hi) {
+    u64 range = hi - lo + 1;
+    u64 zone = ~0ull - ((~0ull - range + 1) % range);
+    for (;;) {
+      u64 v = next_u64();
+      u64 l = v * range;
+      if (l <= zone) return lo + mulhi64(v, range);
+    }
+  }
+  /// gen_range(config.send_latency): sampler pre-digested on the host (Params.lat_*)
+  MSIM_HD u64 sample_latency() {
+    if (P->lat_mode == 0) {  // Small: Uniform<u32> over sub-second nanos; next_u32 = next_u64 >> 32
+      u32 range = (u32)P->lat_range, zone = (u32)P->lat_zone;
+      for (;;) {
+        u32 v = (u32)(next_u64() >> 32);
+        u64 m = (u64)v * range;
+        if ((u32)m <= zone) return P->lat_base + (u32)P->lat_lo + (u32)(m >> 32);
+      }
+    } else {
+      u64 range = P->lat_range, zone = P->lat_zone;
+      for (;;) {
+        u64 v = next_u64();
+        u64 l = v * range;
+        if (l <= zone) return P->lat_lo + mulhi64(v, range);
+      }
+    }
+  }
+
+  // ---------------- timer heap (naive_timer over Rust's BinaryHeap) ----------------
+  MSIM_HD u64& h_dl(int i) const { return q(L::Q_HEAP_DL, i); }
+  MSIM_HD u32& h_pl(int i) const { return w(L::W_HEAP_PL, i); }
+  /// Timer::add = BinaryHeap::push: append, sift_up while STRICTLY earlier than the parent
+  MSIM_HD void timer_push(u64 dl, u32 pl) {
+    u32 pos = heap_len;
+    if (pos >= (u32)C::TQ) {
+      fail_cap(MSIM_CAP_TIMERS);
+      return;
+    }
+    heap_len = pos + 1;
+    if (heap_len > peak_timers) peak_timers = heap_len;
+    while (pos > 0) {
+      u32 parent = (pos - 1) >> 1;
+      u64 pd = h_dl(parent);
+      if (dl >= pd) break;
+      h_dl(pos) = pd;
+      h_pl(pos) = h_pl(parent);
+      pos = parent;
+    }
+    h_dl(pos) = dl;
+    h_pl(pos) = pl;
+  }
+  /// BinaryHeap::pop: move the last element to the root, sift_down_to_bottom (on equal
+  /// deadlines the RIGHT child is promoted), then sift_up from the leaf.
+  MSIM_HD void timer_pop(u64& dl, u32& pl) {
+    dl = h_dl(0);
+    pl = h_pl(0);
+    u32 end = --heap_len;
+    if (end == 0) return;
+    u64 edl = h_dl(end);
+    u32 epl = h_pl(end);
+    u32 pos = 0, child = 1;
+    while (end >= 2 && child <= end - 2) {
+      u64 dl_l = h_dl(child), dl_r = h_dl(child + 1);
+      if (dl_l >= dl_r) {
+        child++;
+        dl_l = dl_r;
+      }
+      h_dl(pos) = dl_l;
+      h_pl(pos) = h_pl(child);
+      pos = child;
+      child = 2 * pos + 1;
+    }
+    if (child == end - 1) {
+      h_dl(pos) = h_dl(child);
+      h_pl(pos) = h_pl(child);
+      pos = child;
+    }
+    while (pos > 0) {
+      u32 parent = (pos - 1) >> 1;
+      u64 pd = h_dl(parent);
+      if (edl >= pd) break;
+      h_dl(pos) = pd;
+      h_pl(pos) = h_pl(parent);
+      pos = parent;
+    }
+    h_dl(pos) = edl;
+    h_pl(pos) = epl;
+  }
+  /// Timer::expire(limit): fire every timer with deadline <= limit, in heap order.
+  /// `now` is NOT touched: advance_to_next_event fires callbacks under the old clock.
+  MSIM_HD void expire(u64 limit) {
+    while (heap_len > 0 && h_dl(0) <= limit && running()) {
+      u64 dl;
+      u32 pl;
+      timer_pop(dl, pl);
+      ev_fire++;
+      u32 kind = pl >> 28, a = (pl >> 20) & 0xff, g = pl & 0xfffffu;
+      if (kind == TK_WAKE) {
+        trace(now, dl, MSIM_EV_WAKE, g);
+        wake(a, g);
+      } else if (kind == TK_DELIVER) {
+        trace(now, dl, MSIM_EV_DELIVER, w(L::W_M_SERIAL, a));
+        deliver(a);
+      } else {
+        trace(now, dl, MSIM_EV_RESTART, a);
+        restart(a);
+      }
+    }
+  }
+  /// TimeHandle::advance (time/mod.rs:103-106) — also the clock-jump fault `time::advance`
+  MSIM_HD void time_advance(u64 dur) {
+    now += dur;
+    expire(now);
+  }
+  /// sleep()/sleep_until(): deadline = max(deadline, now + 1 ms)  (time/mod.rs:111-124)
+  MSIM_HD u64 sleep_deadline(u64 deadline) const {
+    u64 m = now + NS_PER_MS;
+    return deadline > m ? deadline : m;
+  }
+  /// Sleep::poll (time/sleep.rs:47-54): EVERY pending poll registers another timer
+  MSIM_HD bool sleep_poll(int t, u64 deadline) {
+    if (now >= deadline) return true;
+    timer_push(deadline, timer_payload(TK_WAKE, t, t_gen(t)));
+    return false;
+  }
+
+  // ---------------- tasks (async-task state machine) ----------------
+  MSIM_HD void rq_push(int t) {
+    if (rq_len >= (u32)C::NT) {
+      fail_cap(MSIM_CAP_READY);
+      return;
+    }
+    b(L::B_RQ, rq_len++) = (u8)t;
+  }
+  /// Waker::wake for the task that lived in slot `t` with generation `gen`
+  MSIM_HD void wake(int t, u32 gen) {
+    if ((t_spawn(t) & 0xfffffu) != gen || t_spawn(t) == NONE32) return;
+    u8 f = t_flags(t);
+    if (f & (TF_COMPLETED | TF_CLOSED)) return;
+    if (f & TF_SCHEDULED) return;
+    t_flags(t) = f | TF_SCHEDULED;
+    if (!(f & TF_RUNNING)) rq_push(t);
+  }
+  MSIM_HD void wake_task(int t) { wake(t, t_gen(t)); }
+  MSIM_HD void notify_awaiter(int t) {
+    u32 aw = t_aw(t);
+    if (aw != NONE32) {
+      t_aw(t) = NONE32;
+      wake(aw >> 20, aw & 0xfffffu);
+    }
+  }
+  MSIM_HD void maybe_free(int t) {
+    u8 f = t_flags(t);
+    if ((f & (TF_ALIVE | TF_JOINABLE | TF_SCHEDULED | TF_RUNNING)) == 0 && (f & (TF_COMPLETED | TF_CLOSED))) {
+      t_flags(t) = 0;
+      t_spawn(t) = NONE32;
+      q(L::Q_TFREE, t >> 6) |= 1ull << (t & 63);
+    }
+  }
+  /// Dropping the task's future (and the TaskInfo inside it)
+  MSIM_HD void drop_future(int t) {
+    u8 f = t_flags(t);
+    if (f & TF_ALIVE) {
+      WL::on_drop(*this, t);
+      t_flags(t) = t_flags(t) & ~TF_ALIVE;
+      w(L::W_LIVE_TASKS)--;
+    }
+  }
+  /// impl Drop for Runnable: the kill / cancel path (task/mod.rs:273)
+  MSIM_HD void drop_runnable(int t) {
+    u8 f = t_flags(t);
+    if (!(f & (TF_COMPLETED | TF_CLOSED))) t_flags(t) = f | TF_CLOSED;
+    drop_future(t);
+    t_flags(t) = t_flags(t) & ~TF_SCHEDULED;
+    notify_awaiter(t);
+    maybe_free(t);
+  }
+  /// Spawner::spawn_inner (task/mod.rs:627-654): returns the slot or -1
+  MSIM_HD int spawn(u32 kind, u32 node, u8 extra_flags = 0) {
+    int t = -1;
+    for (int wd = 0; wd < (C::NT + 63) / 64; wd++) {
+      u64 m = q(L::Q_TFREE, wd);
+      if (m) {
+        int bit = ffs64(m);
+        q(L::Q_TFREE, wd) = m & (m - 1);
+        t = wd * 64 + bit;
+        break;
+      }
+    }
+    u32 idx = w(L::W_NEXT_SPAWN);
+    if (t < 0 || t >= C::NT || idx >= 0xfffffu) {
+      fail_cap(MSIM_CAP_TASKS);
+      return -1;
+    }
+    w(L::W_NEXT_SPAWN) = idx + 1;
+    t_kind(t) = (u8)kind;
+    t_pc(t) = 0;
+    t_sub(t) = 0;
+    t_flags(t) = TF_SCHEDULED | TF_ALIVE | extra_flags;
+    t_node(t) = (u8)node;
+    t_epoch(t) = n_epoch(node);
+    t_rx(t) = NONE8;
+    t_sock(t) = NONE8;
+    t_msg(t) = NONE8;
+    t_spawn(t) = idx;
+    t_aw(t) = NONE32;
+    u32 live = ++w(L::W_LIVE_TASKS);
+    if (live > w(L::W_PEAK_TASKS)) w(L::W_PEAK_TASKS) = live;
+    rq_push(t);
+    return t;
+  }
+  /// JoinHandle::poll (async_task::Task::poll_task).  1 = Ok (output = t_a(target)), 2 = cancelled
+  MSIM_HD int join_poll(int self, int target) {
+    u8 f = t_flags(target);
+    if (f & TF_CLOSED) {
+      if (f & (TF_SCHEDULED | TF_RUNNING)) {
+        t_aw(target) = ((u32)self << 20) | t_gen(self);
+        return 0;
+      }
+      t_flags(target) = f & ~TF_JOINABLE;
+      maybe_free(target);
+      return 2;
+    }
+    if (!(f & TF_COMPLETED)) {
+      t_aw(target) = ((u32)self << 20) | t_gen(self);
+      return 0;
+    }
+    t_flags(target) = (f | TF_CLOSED) & ~TF_JOINABLE;
+    return 1;  // caller reads t_a(target) then calls join_release(target)
+  }
+  MSIM_HD void join_release(int target) { maybe_free(target); }
+  /// Dropping a JoinHandle = detach
+  MSIM_HD void join_detach(int target) {
+    t_flags(target) = t_flags(target) & ~TF_JOINABLE;
+    maybe_free(target);
+  }
+  /// AbortHandle::abort (task/join.rs:158-163)
+  MSIM_HD void abort_task(int t) {
+    if (t_flags(t) & TF_ALIVE) {
+      t_flags(t) = t_flags(t) | TF_CANCELLED;
+      wake_task(t);
+    }
+  }
+
+  // ---------------- nodes: kill / restart / pause / resume (task/mod.rs:356-424) ----------------
+  MSIM_HD bool task_node_killed(int t) const {
+    int n = t_node(t);
+    return t_epoch(t) != n_epoch(n) || (n_flags(n) & NF_KILLED);
+  }
+  /// NodeInfo::kill for the CURRENT info of node n: wake every live task in spawn order
+  MSIM_HD void info_kill(int n, u8 epoch) {
+    // spawn order = ascending spawn index among this incarnation's live tasks
+    u32 last = 0;
+    bool first = true;
+    for (;;) {
+      u32 best = NONE32;
+      int bt = -1;
+      for (int t = 0; t < C::NT; t++) {
+        u32 sp = t_spawn(t);
+        if (sp == NONE32 || !(t_flags(t) & TF_ALIVE)) continue;
+        if (t_node(t) != n || t_epoch(t) != epoch) continue;
+        if (!first && sp <= last) continue;
+        if (sp < best) {
+          best = sp;
+          bt = t;
+        }
+      }
+      if (bt < 0) break;
+      wake_task(bt);
+      last = best;
+      first = false;
+    }
+  }
+  MSIM_HD void drop_parked(int n) {
+    u32 len = w(L::W_PK_LEN), keep = 0;
+    for (u32 i = 0; i < len; i++) {
+      int t = b(L::B_PK, i);
+      if (t_node(t) == n) {
+        drop_runnable(t);
+      } else {
+        b(L::B_PK, keep++) = (u8)t;
+      }
+    }
+    w(L::W_PK_LEN) = keep;
+  }
+  MSIM_HD void kill(int n) {
+    drop_parked(n);
+    n_flags(n) = n_flags(n) | NF_KILLED;
+    info_kill(n, n_epoch(n));
+    reset_node_sockets(n);  // NetSim::reset_node: all sockets of the node closed (network.rs:142-147)
+  }
+  /// Spawner::exit (task/mod.rs:656-661): info.kill() only — no reset_node, paused list kept
+  MSIM_HD void node_exit(int n, u8 epoch) {
+    if (n_epoch(n) == epoch) n_flags(n) = n_flags(n) | NF_KILLED;
+    info_kill(n, epoch);
+  }
+  MSIM_HD void restart(int n) {
+    drop_parked(n);
+    info_kill(n, n_epoch(n));  // old_info.kill()
+    n_epoch(n) = n_epoch(n) + 1;
+    n_flags(n) = n_flags(n) & ~(NF_KILLED | NF_PAUSED);
+    WL::node_init(*this, n);
+  }
+  MSIM_HD void pause(int n) { n_flags(n) = n_flags(n) | NF_PAUSED; }
+  MSIM_HD void resume(int n) {
+    n_flags(n) = n_flags(n) & ~NF_PAUSED;
+    u32 len = w(L::W_PK_LEN), keep = 0;
+    for (u32 i = 0; i < len; i++) {
+      int t = b(L::B_PK, i);
+      if (t_node(t) == n)
+        rq_push(t);
+      else
+        b(L::B_PK, keep++) = (u8)t;
+    }
+    w(L::W_PK_LEN) = keep;
+  }
+  MSIM_HD bool is_exit(int n) const { return n_flags(n) & NF_KILLED; }
+  /// Handle::create_node + NodeBuilder::build (runtime/mod.rs:405-418): ids start at 1
+  MSIM_HD int create_node(bool has_ip, bool with_init, bool restart_on_panic = false) {
+    u32 n = w(L::W_NEXT_NODE);
+    if (n >= (u32)C::NNODE) {
+      fail_cap(MSIM_CAP_TASKS);
+      return 0;
+    }
+    w(L::W_NEXT_NODE) = n + 1;
+    n_flags(n) = NF_EXISTS | (has_ip ? NF_HAS_IP : 0) | (restart_on_panic ? NF_RESTART_ON_PANIC : 0);
+    n_epoch(n) = 0;
+    if (with_init) WL::node_init(*this, n);
+    return (int)n;
+  }
+
+  // ---------------- network (net/network.rs, net/mod.rs, net/endpoint.rs) ----------------
+  MSIM_HD u8& sk_state(int k) const { return b(L::B_SK_STATE, k); }
+  MSIM_HD u32 sk_gen(int k) const { return w(L::W_SK_PORTGEN, k) >> 16; }
+  MSIM_HD u32 sk_port(int k) const { return w(L::W_SK_PORTGEN, k) & 0xffff; }
+  MSIM_HD int msg_alloc() {
+    u64 m = q(L::Q_MFREE);
+    if (!m) {
+      fail_cap(MSIM_CAP_MSGS);
+      return -1;
+    }
+    int i = ffs64(m);
+    q(L::Q_MFREE) = m & (m - 1);
+    return i;
+  }
+  MSIM_HD void msg_free(int m) { q(L::Q_MFREE) |= 1ull << m; }
+  MSIM_HD int sock_find(int node, u32 ipk, u32 port) const {
+    for (int k = 0; k < C::NSOCK; k++)
+      if (sk_state(k) && b(L::B_SK_NODE, k) == node && b(L::B_SK_IPK, k) == ipk && sk_port(k) == port) return k;
+    return -1;
+  }
+  /// Network::bind (network.rs:206-251).  >= 0 socket slot; -1 AddrNotAvailable; -2 AddrInUse
+  MSIM_HD int sock_bind(int node, u32 addr) {
+    u32 ipk = addr_ipk(addr), port = addr_port(addr);
+    if (ipk == IPK_NODE && (int)addr_node(addr) != node) return -1;
+    if (port == 0) {
+      port = 1;
+      while (port <= 0xffff && sock_find(node, ipk, port) >= 0) port++;
+      if (port > 0xffff) return -2;
+    }
+    if (sock_find(node, ipk, port) >= 0) return -2;
+    int k = 0;
+    while (k < C::NSOCK && sk_state(k)) k++;
+    if (k >= C::NSOCK) {
+      fail_cap(MSIM_CAP_SOCKETS);
+      return -2;
+    }
+    sk_state(k) = 1;
+    b(L::B_SK_NODE, k) = (u8)node;
+    b(L::B_SK_IPK, k) = (u8)ipk;
+    b(L::B_SK_REGLEN, k) = 0;
+    b(L::B_SK_MBLEN, k) = 0;
+    b(L::B_SK_REFS, k) = 1;
+    b(L::B_SK_EPOCH, k) = n_epoch(node);
+    w(L::W_SK_PORTGEN, k) = port | ((sk_gen(k) + 1) << 16);
+    return k;
+  }
+  MSIM_HD void sock_release_storage(int k) {
+    u32 ml = b(L::B_SK_MBLEN, k);
+    for (u32 i = 0; i < ml; i++) msg_free(b(L::B_MB, k * C::NMBOX + i));
+    b(L::B_SK_MBLEN, k) = 0;
+    b(L::B_SK_REGLEN, k) = 0;
+    sk_state(k) = 0;
+    w(L::W_SK_PORTGEN, k) = (w(L::W_SK_PORTGEN, k) & 0xffff0000u) + 0x10000u;  // gen++ : stale refs miss
+  }
+  MSIM_HD void reset_node_sockets(int n) {
+    for (int k = 0; k < C::NSOCK; k++)
+      if (sk_state(k) && b(L::B_SK_NODE, k) == n) sock_release_storage(k);
+  }
+  /// A future takes / drops a clone of the Endpoint (Arc<BindGuard>)
+  MSIM_HD void sock_ref(int t, int k) {
+    t_sock(t) = (u8)k;
+    t_sockgen(t) = (u8)sk_gen(k);
+    b(L::B_SK_REFS, k)++;
+  }
+  MSIM_HD void sock_adopt(int t, int k) {  // the binder: REFS already 1
+    t_sock(t) = (u8)k;
+    t_sockgen(t) = (u8)sk_gen(k);
+  }
+  /// BindGuard::drop (net/mod.rs:483-493): close unless the binding incarnation was killed
+  MSIM_HD void sock_unref(int t) {
+    int k = t_sock(t);
+    if (k == NONE8) return;
+    t_sock(t) = NONE8;
+    if (!sk_state(k) || (u8)sk_gen(k) != t_sockgen(t)) return;
+    if (--b(L::B_SK_REFS, k) != 0) return;
+    int n = b(L::B_SK_NODE, k);
+    bool killed = b(L::B_SK_EPOCH, k) != n_epoch(n) || (n_flags(n) & NF_KILLED);
+    if (!killed) sock_release_storage(k);
+  }
+  MSIM_HD bool link_clogged(int src, int dst) const {
+    return ((w(L::W_CLOG_OUT) >> src) & 1) || ((w(L::W_CLOG_IN) >> dst) & 1) || ((w(L::W_CLOG_LINK, src) >> dst) & 1);
+  }
+  MSIM_HD void clog_node(int n) {
+    w(L::W_CLOG_IN) |= 1u << n;
+    w(L::W_CLOG_OUT) |= 1u << n;
+  }
+  MSIM_HD void unclog_node(int n) {
+    w(L::W_CLOG_IN) &= ~(1u << n);
+    w(L::W_CLOG_OUT) &= ~(1u << n);
+  }
+  MSIM_HD void clog_link(int sN, int d) { w(L::W_CLOG_LINK, sN) |= 1u << d; }
+  MSIM_HD void unclog_link(int sN, int d) { w(L::W_CLOG_LINK, sN) &= ~(1u << d); }
+
+  /// NetSim::rand_delay (net/mod.rs:287-295): returns the Sleep deadline (always >= now + 1 ms)
+  MSIM_HD u64 rand_delay_deadline() {
+    u64 delay = gen_range_u64(0, 5) * 1000ull;
+    if (P->buggify) {
+      if (next_u64() < P->buggify_p10_int) delay = gen_range_u64(1, 5) * NS_PER_SEC;
+    }
+    return sleep_deadline(now + delay);
+  }
+  /// The part of NetSim::send after rand_delay (net/mod.rs:304-332) + Network::try_send
+  /// (network.rs:296-313).  `m` is a prepared message slot (tag, w, v0, v1); consumed.
+  MSIM_HD void net_send(int src_node, u32 src_port, u32 dst, int m) {
+    // resolve_dest_node (network.rs:273-291)
+    int dst_node;
+    u32 ipk = addr_ipk(dst);
+    if (ipk == IPK_LOOPBACK || (ipk != IPK_NODE ? sock_find(src_node, ipk, addr_port(dst)) >= 0
+                                                : ((int)addr_node(dst) == src_node &&
+                                                   sock_find(src_node, IPK_NODE, addr_port(dst)) >= 0))) {
+      dst_node = src_node;
+    } else if (!(n_flags(src_node) & NF_HAS_IP)) {
+      msg_free(m);
+      return;  // "ip not set": before any draw
+    } else if (ipk == IPK_NODE && addr_node(dst) < (u32)C::NNODE && (n_flags(addr_node(dst)) & NF_HAS_IP)) {
+      dst_node = (int)addr_node(dst);
+    } else {
+      msg_free(m);
+      return;  // destination not found
+    }
+    // test_link (network.rs:261-270): `clogged || gen_bool(loss)` — no draw when clogged
+    if (link_clogged(src_node, dst_node)) {
+      msg_free(m);
+      return;
+    }
+    if (P->loss_always || next_u64() < P->loss_p_int) {
+      msg_free(m);
+      return;
+    }
+    u32 serial = ++w(L::W_MSG_COUNT);
+    u64 latency = sample_latency();
+    // socket lookup AFTER the draws: exact address, then (UNSPECIFIED, port)
+    int k = sock_find(dst_node, ipk, addr_port(dst));
+    if (k < 0) k = sock_find(dst_node, IPK_UNSPEC, addr_port(dst));
+    if (k < 0) {
+      msg_free(m);
+      return;
+    }
+    w(L::W_M_FROM, m) = mk_addr(ipk == IPK_LOOPBACK ? IPK_LOOPBACK : IPK_NODE, src_node, src_port);
+    w(L::W_M_DST, m) = ((u32)k << 16) | (sk_gen(k) & 0xffff);
+    w(L::W_M_SERIAL, m) = serial & 0xffffffu;
+    timer_push(now + latency, timer_payload(TK_DELIVER, m, 0));
+  }
+  /// Timer callback of NetSim::send → EndpointSocket::deliver → Mailbox::deliver
+  /// (endpoint.rs:310-351).  The target socket OBJECT was captured at send time: if it has
+  /// been closed/reset since, the message lands in a mailbox nobody can read (dropped here).
+  MSIM_HD void deliver(int m) {
+    u32 d = w(L::W_M_DST, m);
+    int k = d >> 16;
+    if (!sk_state(k) || (sk_gen(k) & 0xffff) != (d & 0xffff)) {
+      msg_free(m);
+      return;
+    }
+    u64 tag = q(L::Q_M_TAG, m);
+    u32 rl = b(L::B_SK_REGLEN, k);
+    for (u32 i = 0; i < rl; i++) {
+      if (q(L::Q_RG_TAG, k * C::NREG + i) == tag) {
+        u32 waiter = w(L::W_RG_WAITER, k * C::NREG + i);
+        // swap_remove(i)
+        rl--;
+        q(L::Q_RG_TAG, k * C::NREG + i) = q(L::Q_RG_TAG, k * C::NREG + rl);
+        w(L::W_RG_WAITER, k * C::NREG + i) = w(L::W_RG_WAITER, k * C::NREG + rl);
+        b(L::B_SK_REGLEN, k) = (u8)rl;
+        // oneshot::Sender::send: registrations of dropped receivers are removed eagerly
+        // (mbox_unregister), so the receiver is alive: store the value, wake its task
+        int t = waiter >> 20;
+        t_rx(t) = (u8)m;
+        wake(t, waiter & 0xfffffu);
+        return;
+      }
+    }
+    u32 ml = b(L::B_SK_MBLEN, k);
+    if (ml >= (u32)C::NMBOX) {
+      fail_cap(MSIM_CAP_MAILBOX);
+      msg_free(m);
+      return;
+    }
+    b(L::B_MB, k * C::NMBOX + ml) = (u8)m;
+    b(L::B_SK_MBLEN, k) = (u8)(ml + 1);
+  }
+  /// Mailbox::recv(tag) (endpoint.rs:353-362) on the endpoint the task holds: either fills the
+  /// task's oneshot at once (t_rx) or registers (tag, oneshot sender)
+  MSIM_HD void mbox_recv(int t, int k, u64 tag) {
+    u32 ml = b(L::B_SK_MBLEN, k);
+    for (u32 i = 0; i < ml; i++) {
+      int m = b(L::B_MB, k * C::NMBOX + i);
+      if (q(L::Q_M_TAG, m) == tag) {
+        ml--;
+        b(L::B_MB, k * C::NMBOX + i) = b(L::B_MB, k * C::NMBOX + ml);  // swap_remove
+        b(L::B_SK_MBLEN, k) = (u8)ml;
+        t_rx(t) = (u8)m;
+        return;
+      }
+    }
+    u32 rl = b(L::B_SK_REGLEN, k);
+    if (rl >= (u32)C::NREG) {
+      fail_cap(MSIM_CAP_REGISTERED);
+      return;
+    }
+    q(L::Q_RG_TAG, k * C::NREG + rl) = tag;
+    w(L::W_RG_WAITER, k * C::NREG + rl) = ((u32)t << 20) | t_gen(t);
+    b(L::B_SK_REGLEN, k) = (u8)(rl + 1);
+    t_rx(t) = NONE8;
+  }
+  /// Dropping a oneshot::Receiver that is still registered.  The reference leaves the dead
+  /// sender in `registered` until a message with its tag arrives; removing it eagerly is
+  /// unobservable as long as no two LIVE registrations of a mailbox share a tag (the shipped
+  /// workloads guarantee it; the oracle checks it) — DESIGN.md "eager registration GC".
+  MSIM_HD void mbox_unregister(int t) {
+    int k = t_sock(t);
+    if (k == NONE8 || !sk_state(k) || (u8)sk_gen(k) != t_sockgen(t)) return;
+    u32 me = ((u32)t << 20) | t_gen(t);
+    u32 rl = b(L::B_SK_REGLEN, k);
+    for (u32 i = 0; i < rl; i++)
+      if (w(L::W_RG_WAITER, k * C::NREG + i) == me) {
+        rl--;
+        q(L::Q_RG_TAG, k * C::NREG + i) = q(L::Q_RG_TAG, k * C::NREG + rl);
+        w(L::W_RG_WAITER, k * C::NREG + i) = w(L::W_RG_WAITER, k * C::NREG + rl);
+        b(L::B_SK_REGLEN, k) = (u8)rl;
+        return;
+      }
+  }
+  /// Generic cleanup of what a future may hold (oneshot value, prepared message, registration,
+  /// endpoint clone).  Workload on_drop hooks call this.
+  MSIM_HD void drop_task_resources(int t, bool registered) {
+    if (registered) mbox_unregister(t);
+    if (t_rx(t) != NONE8) {
+      msg_free(t_rx(t));
+      t_rx(t) = NONE8;
+    }
+    if (t_msg(t) != NONE8) {
+      msg_free(t_msg(t));
+      t_msg(t) = NONE8;
+    }
+    sock_unref(t);
+  }
+
+  // ---------------- lifecycle ----------------
+  /// Runtime::with_seed_and_config (runtime/mod.rs:53-69) for this seed + block_on's spawn of main
+  MSIM_HD void init(u64 seed) {
+    // zero this seed's columns
+    for (int i = 0; i < L::NQ; i++) q(i) = 0;
+    for (int i = 0; i < L::NW; i++) w(i) = 0;
+    for (int i = 0; i < L::NB; i++) b(i) = 0;
+    // seed_from_u64: SplitMix64 x4
+    u64 x = seed;
+    u64 st[4];
+    for (int i = 0; i < 4; i++) {
+      x += 0x9e3779b97f4a7c15ull;
+      u64 z = x;
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+      st[i] = z ^ (z >> 31);
+    }
+    r0 = st[0], r1 = st[1], r2 = st[2], r3 = st[3];
+    now = 0;
+    hash = MSIM_HASH_INIT;
+    draws = 0;
+    ev_pop = ev_fire = heap_len = rq_len = peak_timers = 0;
+    status = MSIM_ST_RUNNING;
+    for (int t = 0; t < C::NT; t++) t_spawn(t) = NONE32;
+    for (int wd = 0; wd < (C::NT + 63) / 64; wd++) {
+      int n = C::NT - wd * 64;
+      q(L::Q_TFREE, wd) = n >= 64 ? ~0ull : ((1ull << n) - 1);
+    }
+    q(L::Q_MFREE) = C::NMSG >= 64 ? ~0ull : ((1ull << C::NMSG) - 1);
+    // TimeRuntime::new (time/mod.rs:26-38): draw #1 of every runtime
+    w(L::W_BASE_SECS) = (u32)gen_range_u64(0, 60ull * 60 * 24 * 365);
+    // node 0 = "madsim-main" (task/mod.rs:187-198)
+    n_flags(0) = NF_EXISTS;
+    w(L::W_NEXT_NODE) = 1;
+    int m = spawn(WL::MAIN_KIND, 0, TF_JOINABLE);
+    w(L::W_MAIN_SLOT) = (u32)m;
+  }
+  /// registers ← state block
+  MSIM_HD void load() {
+    r0 = q(L::Q_RNG, 0), r1 = q(L::Q_RNG, 1), r2 = q(L::Q_RNG, 2), r3 = q(L::Q_RNG, 3);
+    now = q(L::Q_NOW);
+    hash = q(L::Q_HASH);
+    draws = q(L::Q_DRAWS);
+    ev_pop = w(L::W_EV_POP), ev_fire = w(L::W_EV_FIRE);
+    heap_len = w(L::W_HEAP_LEN), rq_len = w(L::W_RQ_LEN);
+    status = w(L::W_STATUS);
+    peak_timers = w(L::W_PEAK_TIMERS);
+  }
+  /// registers → state block
+  MSIM_HD void store() {
+    q(L::Q_RNG, 0) = r0, q(L::Q_RNG, 1) = r1, q(L::Q_RNG, 2) = r2, q(L::Q_RNG, 3) = r3;
+    q(L::Q_NOW) = now;
+    q(L::Q_HASH) = hash;
+    q(L::Q_DRAWS) = draws;
+    w(L::W_EV_POP) = ev_pop, w(L::W_EV_FIRE) = ev_fire;
+    w(L::W_HEAP_LEN) = heap_len, w(L::W_RQ_LEN) = rq_len;
+    w(L::W_STATUS) = status;
+    w(L::W_PEAK_TIMERS) = peak_timers;
+  }
+  MSIM_HD void result(SeedResult& r) {
+    r.trace_hash = hash;
+    r.elapsed_ns = now;
+    r.draws = draws;
+    r.ev_pop = ev_pop;
+    r.ev_fire = ev_fire;
+    r.status = status;
+    r.fail_code = w(L::W_FAIL_CODE);
+    r.user[0] = w(L::W_USER0), r.user[1] = w(L::W_USER1), r.user[2] = w(L::W_USER2), r.user[3] = w(L::W_USER3);
+    r.peak_timers = peak_timers;
+    r.peak_tasks = w(L::W_PEAK_TASKS);
+  }
+
+  /// Runnable::run (async-task) + the panic policy of run_all_ready (task/mod.rs:285-317)
+  MSIM_HD void run_task(int t) {
+    u8 f = t_flags(t);
+    if (f & TF_CLOSED) {
+      drop_future(t);
+      t_flags(t) = t_flags(t) & ~TF_SCHEDULED;
+      notify_awaiter(t);
+      maybe_free(t);
+      return;
+    }
+    t_flags(t) = (f & ~TF_SCHEDULED) | TF_RUNNING;
+    int r = WL::poll(*this, t);
+    if (r == POLL_READY) {
+      if (t_flags(t) & TF_INIT) node_exit(t_node(t), t_epoch(t));  // `future.await; h.exit()`
+      drop_future(t);
+      t_flags(t) = (t_flags(t) & ~(TF_RUNNING | TF_SCHEDULED)) | TF_COMPLETED;
+      notify_awaiter(t);
+      maybe_free(t);
+    } else if (r == POLL_PANIC) {
+      // async-task's guard: close, drop the future, notify the awaiter
+      t_flags(t) = (t_flags(t) & ~(TF_RUNNING | TF_SCHEDULED)) | TF_CLOSED;
+      drop_future(t);
+      notify_awaiter(t);
+      int n = t_node(t);
+      bool rop = (n_flags(n) & NF_RESTART_ON_PANIC) && t_epoch(t) == n_epoch(n);
+      maybe_free(t);
+      if (rop) {
+        u64 delay = sample_inclusive_u64(NS_PER_SEC, 10 * NS_PER_SEC - 1);  // gen_range(1s..10s): Medium
+        kill(n);
+        timer_push(now + delay, timer_payload(TK_RESTART, n, 0));
+      } else {
+        fail(MSIM_ST_FAIL_ASSERT, w(L::W_PANIC_CODE));
+      }
+    } else {
+      f = t_flags(t) & ~TF_RUNNING;
+      t_flags(t) = f;
+      if (f & TF_CLOSED) {
+        t_flags(t) = f & ~TF_SCHEDULED;
+        drop_future(t);
+        notify_awaiter(t);
+        maybe_free(t);
+      } else if (f & TF_SCHEDULED) {
+        rq_push(t);  // woken while running
+      }
+    }
+  }
+  MSIM_HD int panic(u32 code) {
+    w(L::W_PANIC_CODE) = code;
+    return POLL_PANIC;
+  }
+
+  /// ONE EVENT STEP of Executor::block_on (task/mod.rs:239-259): if the ready Vec is not empty,
+  /// pop a random runnable, dispatch it and advance the clock 50-100 ns; otherwise finish, or
+  /// jump to the next timer.  Returns false when the seed has stopped.
+  MSIM_HD bool step() {
+    if (rq_len > 0) {
+      // try_recv_random (utils/mpsc.rs:73-83)
+      u32 len = rq_len;
+      u32 idx = (u32)gen_range_u64(0, len);
+      int t = b(L::B_RQ, idx);
+      b(L::B_RQ, idx) = b(L::B_RQ, len - 1);  // swap_remove
+      rq_len = len - 1;
+      ev_pop++;
+      u64 aux = ((u64)len << 32) | idx;
+      u8 f = t_flags(t);
+      u32 id = t_spawn(t);
+      if (!(f & TF_ALIVE)) {  // metadata().upgrade() failed: future already dropped
+        trace(now, aux, MSIM_EV_SKIP, id);
+        t_flags(t) = f & ~TF_SCHEDULED;
+        maybe_free(t);
+        return true;
+      }
+      bool do_drop = (f & TF_CANCELLED) || task_node_killed(t);
+      if (!do_drop && (n_flags(t_node(t)) & NF_PAUSED)) {
+        trace(now, aux, MSIM_EV_PARK, id);
+        u32 pl = w(L::W_PK_LEN);
+        if (pl >= (u32)C::NPARK) {
+          fail_cap(MSIM_CAP_PARKED);
+          return false;
+        }
+        b(L::B_PK, pl) = (u8)t;
+        w(L::W_PK_LEN) = pl + 1;
+        return true;
+      }
+      trace(now, aux, do_drop ? MSIM_EV_DROP : MSIM_EV_POLL, id);
+      if (do_drop)
+        drop_runnable(t);
+      else
+        run_task(t);
+      if (!running()) return false;
+      // advance time: 50-100ns (task/mod.rs:319-321)
+      u64 dur = gen_range_u64(50, 100);
+      time_advance(dur);
+      return running();
+    }
+    // ready Vec drained: task.is_finished()?
+    int m = (int)w(L::W_MAIN_SLOT);
+    if (t_flags(m) & (TF_COMPLETED | TF_CLOSED)) {
+      if (t_flags(m) & TF_COMPLETED) {
+        status = MSIM_ST_PASS;
+        WL::finish(*this);
+      } else {
+        fail(MSIM_ST_FAIL_ASSERT, 0xdead);  // main task cancelled
+      }
+      return false;
+    }
+    // advance_to_next_event (time/mod.rs:45-60)
+    if (heap_len == 0) {
+      fail(MSIM_ST_FAIL_DEADLOCK, 0);
+      return false;
+    }
+    u64 t_next = h_dl(0) + 50;
+    expire(t_next);
+    now = t_next;
+    if (P->time_limit_ns && now >= P->time_limit_ns) {
+      fail(MSIM_ST_FAIL_TIME_LIMIT, 0);
+      return false;
+    }
+    return running();
+  }
+};
+
+}  // namespace msim

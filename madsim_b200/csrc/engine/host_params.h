@@ -1,0 +1,132 @@
+// Host-side digest of (msim_config, msim_workload_desc) → engine Params.
+// Mirrors how rand 0.8 builds its samplers so the device only does integer work:
+//   Bernoulli::new(p)            p_int = (p * 2^64) as u64, p == 1.0 → always true
+//   UniformDuration::new(lo,hi)  Small / Medium mode, Uniform::new_inclusive zone
+// (reference call sites network.rs:262,267).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "defs.h"
+
+namespace msim {
+
+inline int workload_defaults(uint32_t workload, msim_workload_desc* d) {
+  std::memset(d, 0, sizeof(*d));
+  d->workload = workload;
+  switch (workload) {
+    case MSIM_WL_SLEEP:
+      d->p[0] = NS_PER_SEC;
+      return 0;
+    case MSIM_WL_PINGPONG:
+      d->n_nodes = 2;
+      d->p[0] = 1000;
+      d->p[1] = 10 * NS_PER_MS;
+      return 0;
+    case MSIM_WL_RAFT:
+      d->n_nodes = 5;
+      d->p[0] = 10000;
+      d->p[3] = 40;
+      d->p[4] = 50;
+      d->p[5] = 150;
+      d->p[6] = 300;
+      return 0;
+    case MSIM_WL_CHAOS:
+      d->n_nodes = 1;
+      d->p[0] = 8;
+      d->p[1] = 2000;
+      return 0;
+  }
+  return MSIM_EINVAL;
+}
+
+inline void config_defaults(msim_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->packet_loss_rate = 0.0;
+  c->send_latency_lo_ns = 1 * NS_PER_MS;
+  c->send_latency_hi_ns = 10 * NS_PER_MS;
+}
+
+/// Returns 0 or MSIM_EINVAL (+ message).
+inline int make_params(const msim_config& c, const msim_workload_desc& wl, Params* out, std::string* err) {
+  Params P;
+  std::memset(&P, 0, sizeof(P));
+  P.workload = wl.workload;
+  P.n_nodes = wl.n_nodes;
+  for (int i = 0; i < 8; i++) P.p[i] = wl.p[i];
+  double p = c.packet_loss_rate;
+  if (!(p >= 0.0 && p <= 1.0)) {
+    if (err) *err = "packet_loss_rate outside [0, 1]";
+    return MSIM_EINVAL;
+  }
+  if (p == 1.0) {
+    P.loss_always = 1;
+  } else {
+    P.loss_p_int = (u64)(p * 18446744073709551616.0);
+  }
+  u64 lo = c.send_latency_lo_ns, hi = c.send_latency_hi_ns;
+  if (!(lo < hi)) {
+    if (err) *err = "send_latency: low >= high";
+    return MSIM_EINVAL;
+  }
+  u64 hi_incl = hi - 1;
+  u64 low_s = lo / NS_PER_SEC, high_s = hi_incl / NS_PER_SEC;
+  u64 low_n = lo % NS_PER_SEC, high_n = hi_incl % NS_PER_SEC;
+  if (high_n < low_n) {
+    high_s -= 1;
+    high_n += NS_PER_SEC;
+  }
+  if (low_s == high_s) {
+    P.lat_mode = 0;
+    P.lat_base = low_s * NS_PER_SEC;
+    P.lat_lo = low_n;
+    u32 range = (u32)(high_n - low_n + 1);
+    u32 reject = range ? (u32)((0xffffffffu - range + 1) % range) : 0;
+    P.lat_range = range;
+    P.lat_zone = 0xffffffffu - reject;
+    if (range == 0) {
+      if (err) *err = "send_latency: full u32 range unsupported";
+      return MSIM_EINVAL;
+    }
+  } else {
+    P.lat_mode = 1;
+    u64 l = low_s * NS_PER_SEC + low_n, h = high_s * NS_PER_SEC + high_n;
+    u64 range = h - l + 1;
+    P.lat_lo = l;
+    P.lat_range = range;
+    P.lat_zone = ~0ull - ((~0ull - range + 1) % range);
+  }
+  P.time_limit_ns = c.time_limit_ns;
+  P.buggify = c.buggify ? 1 : 0;
+  P.buggify_p10_int = (u64)(0.1 * 18446744073709551616.0);
+  // workload parameter validation
+  switch (wl.workload) {
+    case MSIM_WL_SLEEP:
+      break;
+    case MSIM_WL_PINGPONG:
+      break;
+    case MSIM_WL_RAFT:
+      if (P.n_nodes == 0) P.n_nodes = 5;
+      if (P.n_nodes > 5 || ((wl.p[1] & MSIM_RAFT_FAULT_CLOG_LINK) && P.n_nodes < 2)) {
+        if (err) *err = "raft: n_nodes must be 1..5 (>= 2 with link faults)";
+        return MSIM_EINVAL;
+      }
+      if (!(wl.p[5] < wl.p[6]) || wl.p[3] == 0 || wl.p[4] == 0) {
+        if (err) *err = "raft: need el_lo < el_hi, rpc timeout > 0, heartbeat > 0";
+        return MSIM_EINVAL;
+      }
+      if (wl.p[1] > 7) {
+        if (err) *err = "raft: unknown fault mask bits";
+        return MSIM_EINVAL;
+      }
+      break;
+    default:
+      if (err) *err = "unknown workload";
+      return MSIM_EINVAL;
+  }
+  *out = P;
+  return 0;
+}
+
+}  // namespace msim

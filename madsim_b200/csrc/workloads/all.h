@@ -1,0 +1,5 @@
+#pragma once
+#include "pingpong.h"
+#include "raft.h"
+#include "sleep.h"
+#define MSIM_HAVE_RAFT 1

@@ -31,8 +31,13 @@ struct Extra {
   uint32_t peak_ready, peak_registered, peak_msgs, tasks_spawned;
 };
 
+thread_local size_t g_peak_registered = 0, g_peak_msgs = 0;
+
 int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_seed_result* out,
             std::vector<msim_trace_rec>* full, std::string* msg, Extra* extra) {
+  g_peak_registered = g_peak_msgs = 0;
+  tls_peak_registered = &g_peak_registered;
+  tls_peak_msgs = &g_peak_msgs;
   Runtime rt(seed, to_config(c));
   if (c && c->time_limit_ns) rt.set_time_limit(c->time_limit_ns);
   if (c && c->buggify) rt.rand.enable_buggify();
@@ -94,7 +99,8 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
   if (extra) {
     extra->peak_ready = u32(rt.task.peak_ready);
     extra->tasks_spawned = rt.task.handle.sh.next_task_id;
-    extra->peak_registered = extra->peak_msgs = 0;
+    extra->peak_registered = u32(g_peak_registered);
+    extra->peak_msgs = u32(g_peak_msgs);
   }
   rt.tracer.full = nullptr;
   *out = r;

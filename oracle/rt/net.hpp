@@ -264,10 +264,16 @@ struct Message {  // endpoint.rs:290-294
 };
 
 /// endpoint.rs:298-363
+inline thread_local size_t* tls_peak_registered = nullptr;  // capacity statistics only
+inline thread_local size_t* tls_peak_msgs = nullptr;
 struct Mailbox {
   std::vector<std::pair<u64, OneshotSender<Message>>> registered;
   std::vector<Message> msgs;
   size_t peak_registered = 0, peak_msgs = 0;
+  ~Mailbox() {
+    if (tls_peak_registered) *tls_peak_registered = std::max(*tls_peak_registered, peak_registered);
+    if (tls_peak_msgs) *tls_peak_msgs = std::max(*tls_peak_msgs, peak_msgs);
+  }
   void deliver(Message m) {
     size_t i = 0;
     std::optional<Message> msg = std::move(m);

@@ -415,6 +415,7 @@ struct Executor {
     // NOTE: block_on does not set info.waker (stays a noop waker, :127)
     task->scheduled = true;
     task->schedule();
+    ti.reset();  // `info` was moved into the future (task/mod.rs:229-231)
     for (;;) {
       run_all_ready();
       if (task->is_finished()) {

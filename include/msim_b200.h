@@ -185,6 +185,13 @@ int msim_batch_sync(msim_batch* b);
 int msim_batch_results(msim_batch* b, msim_seed_result* out /*n_seeds*/, uint32_t* fail_bitmap /*ceil(n/32) words*/,
                        msim_stats* stats);
 int msim_batch_trace_hash(msim_batch* b, uint64_t* hash /*n_seeds*/);
+/* Device-side summary into caller-provided DEVICE memory (e.g. a torch tensor that is then
+ * all-reduced over NCCL — the only cross-GPU step): u64 counters[8] =
+ * {ev_pop, ev_fire, draws, n_pass, n_fail, n_unfinished, first_fail_seed, n_seeds} followed by
+ * u32 fail_bitmap[ceil(n/32)].  Enqueued on the batch's stream.                              */
+int msim_batch_summarize_device(msim_batch* b, void* d_out, size_t bytes);
+/* bytes of per-seed device state of a workload (capacity table in DESIGN.md)                */
+int msim_workload_state_bytes(uint32_t workload);
 /* device pointer of the result array (msim_seed_result[n_seeds]) for zero-copy consumers (torch / NCCL) */
 int msim_batch_results_device(msim_batch* b, void** dptr, size_t* bytes);
 /* Full canonical trace of ONE seed: replays that seed on the device with the

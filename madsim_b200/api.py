@@ -1,0 +1,275 @@
+"""Host-side mirror of the reference's runtime interface for the hot path.
+
+Reference (Rust)                                   here
+-------------------------------------------------  ------------------------------------------
+madsim::Config{net{packet_loss_rate,send_latency}}  Config            (config.rs:11-35, network.rs:66-89)
+Runtime::with_seed_and_config / block_on            Batch.run         (runtime/mod.rs:53-130) — many seeds at once
+Builder::from_env().run(f)                          Builder.from_env().run(workload)  (runtime/builder.rs:64-162)
+panic "note: run with `MADSIM_TEST_SEED=..`"        SimulationFailure (runtime/mod.rs:205-210)
+`f` (the async test body)                           Workload          (a registered program, see include/msim_b200.h)
+
+Everything executes on the GPU through the C-ABI (libmsim_b200.so); nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _native as N
+
+SEED_RESULT_DTYPE = np.dtype(
+    [
+        ("trace_hash", "<u8"),
+        ("elapsed_ns", "<u8"),
+        ("draws", "<u8"),
+        ("ev_pop", "<u4"),
+        ("ev_fire", "<u4"),
+        ("status", "<u4"),
+        ("fail_code", "<u4"),
+        ("user", "<u4", (4,)),
+        ("peak_timers", "<u4"),
+        ("peak_tasks", "<u4"),
+    ]
+)
+TRACE_DTYPE = np.dtype([("now_ns", "<u8"), ("aux", "<u8"), ("kind_id", "<u4"), ("draws", "<u4")])
+assert SEED_RESULT_DTYPE.itemsize == 64 and TRACE_DTYPE.itemsize == 24
+MS = 1_000_000
+SEC = 1_000_000_000
+
+
+@dataclass
+class Config:
+    """madsim::Config (config.rs:11-21) + Runtime knobs (builder.rs:26-63)."""
+
+    packet_loss_rate: float = 0.0
+    send_latency_ns: tuple = (1 * MS, 10 * MS)
+    time_limit_ns: int = 0
+    buggify: bool = False
+
+    def to_c(self) -> N.MsimConfig:
+        return N.MsimConfig(
+            float(self.packet_loss_rate),
+            int(self.send_latency_ns[0]),
+            int(self.send_latency_ns[1]),
+            int(self.time_limit_ns),
+            1 if self.buggify else 0,
+            0,
+        )
+
+
+@dataclass
+class Workload:
+    """A registered program: what `f` is in `Builder::run(f)`."""
+
+    workload: int
+    n_nodes: int = 0
+    p: list = field(default_factory=lambda: [0] * 8)
+
+    @staticmethod
+    def sleep(duration_ns: int = SEC) -> "Workload":
+        return Workload(N.WL_SLEEP, 0, [duration_ns, 0, 0, 0, 0, 0, 0, 0])
+
+    @staticmethod
+    def pingpong(rounds: int = 1000, think_ns: int = 10 * MS) -> "Workload":
+        return Workload(N.WL_PINGPONG, 2, [rounds, think_ns, 0, 0, 0, 0, 0, 0])
+
+    @staticmethod
+    def raft(
+        n_nodes: int = 5,
+        duration_ms: int = 10_000,
+        faults: int = 0,
+        bug: int = 0,
+        rpc_timeout_ms: int = 40,
+        heartbeat_ms: int = 50,
+        election_ms: tuple = (150, 300),
+    ) -> "Workload":
+        return Workload(
+            N.WL_RAFT,
+            n_nodes,
+            [duration_ms, faults, bug, rpc_timeout_ms, heartbeat_ms, election_ms[0], election_ms[1], 0],
+        )
+
+    def to_c(self) -> N.MsimWorkloadDesc:
+        return N.MsimWorkloadDesc(self.workload, self.n_nodes, (C.c_uint64 * 8)(*[int(x) for x in self.p]))
+
+    def name(self) -> str:
+        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos"}.get(self.workload, "?")
+
+
+class SimulationFailure(AssertionError):
+    """What a panicking seed is in the reference (runtime/mod.rs:205-210)."""
+
+    def __init__(self, seed: int, status: int, fail_code: int):
+        self.seed, self.status, self.fail_code = seed, status, fail_code
+        super().__init__(
+            f"seed {seed}: {N.STATUS_NAMES.get(status, status)} (code {fail_code})\n"
+            f"note: run with `MADSIM_TEST_SEED={seed}` environment variable to reproduce this error"
+        )
+
+
+class Batch:
+    """Many `Runtime`s that share a Config, advanced together on one GPU."""
+
+    def __init__(self, config: Config | None = None, device: int = 0):
+        self._lib = N.load()
+        self._h = C.c_void_p()
+        self.config = config or Config()
+        cfg = self.config.to_c()
+        N.check(self._lib.msim_batch_create(C.byref(cfg), device, C.byref(self._h)))
+        self.device = device
+        self.n_seeds = 0
+        self.seed_base = 0
+        self.workload: Workload | None = None
+
+    def close(self):
+        if self._h:
+            self._lib.msim_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def load(self, workload: Workload) -> "Batch":
+        d = workload.to_c()
+        N.check(self._lib.msim_workload_load(self._h, C.byref(d)))
+        self.workload = workload
+        return self
+
+    def set_geometry(self, seeds_per_cta: int = 0, lanes_per_warp: int = 0) -> "Batch":
+        N.check(self._lib.msim_batch_set_geometry(self._h, seeds_per_cta, lanes_per_warp))
+        return self
+
+    def set_stream(self, cuda_stream: int) -> "Batch":
+        N.check(self._lib.msim_batch_set_stream(self._h, C.c_void_p(cuda_stream)))
+        return self
+
+    def run(self, seed_base: int, n_seeds: int, max_events_per_seed: int = 0, sync: bool = True) -> "Batch":
+        fn = self._lib.msim_batch_run if sync else self._lib.msim_batch_run_async
+        N.check(fn(self._h, seed_base, n_seeds, max_events_per_seed))
+        self.seed_base, self.n_seeds = seed_base, n_seeds
+        return self
+
+    def resume(self, max_events_per_seed: int = 0) -> "Batch":
+        N.check(self._lib.msim_batch_resume(self._h, max_events_per_seed))
+        return self
+
+    def sync(self) -> "Batch":
+        N.check(self._lib.msim_batch_sync(self._h))
+        return self
+
+    def results(self, want_results: bool = True):
+        """→ (results ndarray[n] of SEED_RESULT_DTYPE or None, fail_bitmap uint32[ceil(n/32)], stats dict)"""
+        n = self.n_seeds
+        res = np.empty(n, dtype=SEED_RESULT_DTYPE) if want_results else None
+        bitmap = np.zeros((n + 31) // 32, dtype=np.uint32)
+        st = N.MsimStats()
+        N.check(
+            self._lib.msim_batch_results(
+                self._h,
+                res.ctypes.data_as(C.c_void_p) if want_results else None,
+                bitmap.ctypes.data_as(C.c_void_p),
+                C.byref(st),
+            )
+        )
+        stats = {k: getattr(st, k) for k, _ in N.MsimStats._fields_ if k != "reserved"}
+        return res, bitmap, stats
+
+    def trace_hash(self) -> np.ndarray:
+        h = np.empty(self.n_seeds, dtype=np.uint64)
+        N.check(self._lib.msim_batch_trace_hash(self._h, h.ctypes.data_as(C.c_void_p)))
+        return h
+
+    def trace(self, seed: int, cap: int = 1 << 20):
+        """Full canonical trace of one seed (device replay).  → (records ndarray, result record)"""
+        buf = np.empty(cap, dtype=TRACE_DTYPE)
+        n = C.c_size_t(0)
+        r = N.MsimSeedResult()
+        N.check(self._lib.msim_batch_trace(self._h, seed, buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(r)))
+        rec = np.frombuffer(bytes(r), dtype=SEED_RESULT_DTYPE)[0]
+        return buf[: min(n.value, cap)].copy(), rec, n.value
+
+    def summarize_into(self, device_ptr: int, nbytes: int):
+        """Device-side summary (counters + fail bitmap) into caller-owned device memory."""
+        N.check(self._lib.msim_batch_summarize_device(self._h, C.c_void_p(device_ptr), nbytes))
+
+    def results_device(self):
+        p, b = C.c_void_p(), C.c_size_t()
+        N.check(self._lib.msim_batch_results_device(self._h, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    @staticmethod
+    def summary_nbytes(n_seeds: int) -> int:
+        return 64 + 4 * ((n_seeds + 31) // 32)
+
+
+def state_bytes(workload: int) -> int:
+    return N.load().msim_workload_state_bytes(workload)
+
+
+def device_count() -> int:
+    n = N.load().msim_device_count()
+    if n < 0:
+        raise N.MsimError(n, N.load().msim_last_error().decode())
+    return n
+
+
+@dataclass
+class Builder:
+    """runtime/builder.rs:7-162: the many-seed test driver (`#[madsim::test]`)."""
+
+    seed: int = 0
+    count: int = 1
+    jobs: int = 1  # MADSIM_TEST_JOBS: here the number of GPUs a sweep may use (informational)
+    config: Config = field(default_factory=Config)
+    time_limit_s: float | None = None
+    check: bool = False
+
+    @staticmethod
+    def from_env() -> "Builder":
+        """Same environment variables as builder.rs:64-118."""
+        b = Builder()
+        env = os.environ
+        if "MADSIM_TEST_SEED" in env:
+            b.seed = int(env["MADSIM_TEST_SEED"])
+        if "MADSIM_TEST_NUM" in env:
+            b.count = int(env["MADSIM_TEST_NUM"])
+        if "MADSIM_TEST_JOBS" in env:
+            b.jobs = int(env["MADSIM_TEST_JOBS"])
+        if "MADSIM_TEST_TIME_LIMIT" in env:
+            b.time_limit_s = float(env["MADSIM_TEST_TIME_LIMIT"])
+        b.check = "MADSIM_TEST_CHECK_DETERMINISM" in env
+        return b
+
+    def run(self, workload: Workload, device: int = 0):
+        """Run seeds seed..seed+count; raise SimulationFailure for the first failing seed
+        (builder.rs:129-159).  With `check`, every seed is run twice and the traces compared
+        (Runtime::check_determinism, runtime/mod.rs:178-202)."""
+        cfg = self.config
+        if self.time_limit_s is not None:
+            cfg = Config(cfg.packet_loss_rate, cfg.send_latency_ns, int(self.time_limit_s * 1e9), cfg.buggify)
+        with Batch(cfg, device) as b:
+            b.load(workload)
+            b.run(self.seed, self.count)
+            res, bitmap, stats = b.results()
+            if self.check:
+                b.run(self.seed, self.count)
+                res2, _, _ = b.results()
+                if not np.array_equal(res["trace_hash"], res2["trace_hash"]):
+                    bad = int(np.nonzero(res["trace_hash"] != res2["trace_hash"])[0][0])
+                    raise AssertionError(f"non-determinism detected (seed {self.seed + bad})")
+        if stats["n_fail"]:
+            i = int(stats["first_fail_seed"] - self.seed)
+            raise SimulationFailure(self.seed + i, int(res["status"][i]), int(res["fail_code"][i]))
+        return res, stats

@@ -18,6 +18,13 @@
 #define MSIM_HD inline
 #define MSIM_HD_NOINLINE inline
 #endif
+// Heavy helpers that are called from many state-machine sites: one shared copy keeps the
+// hot code inside the instruction cache (round-1 ncu: 57 % icc hit rate when all inlined).
+#if defined(MSIM_INLINE_ALL)
+#define MSIM_FN MSIM_HD
+#else
+#define MSIM_FN MSIM_HD_NOINLINE
+#endif
 
 namespace msim {
 

@@ -195,7 +195,7 @@ struct Engine {
     return result;
   }
   /// Rng::gen_range(lo..hi) for u64/usize: UniformInt::sample_single (widening multiply + zone)
-  MSIM_HD u64 gen_range_u64(u64 lo, u64 hi) {
+  MSIM_FN u64 gen_range_u64(u64 lo, u64 hi) {
     u64 range = hi - lo;
     u64 zone = (range << clz64(range)) - 1;
     for (;;) {
@@ -205,7 +205,7 @@ struct Engine {
     }
   }
   /// Uniform::<u64>::new_inclusive(lo, hi).sample — modulo zone (UniformDuration Medium)
-  MSIM_HD u64 sample_inclusive_u64(u64 lo, u64 hi) {
+  MSIM_FN u64 sample_inclusive_u64(u64 lo, u64 hi) {
     u64 range = hi - lo + 1;
     u64 zone = ~0ull - ((~0ull - range + 1) % range);
     for (;;) {
@@ -215,7 +215,7 @@ struct Engine {
     }
   }
   /// gen_range(config.send_latency): sampler pre-digested on the host (Params.lat_*)
-  MSIM_HD u64 sample_latency() {
+  MSIM_FN u64 sample_latency() {
     if (P->lat_mode == 0) {  // Small: Uniform<u32> over sub-second nanos; next_u32 = next_u64 >> 32
       u32 range = (u32)P->lat_range, zone = (u32)P->lat_zone;
       for (;;) {
@@ -237,7 +237,7 @@ struct Engine {
   MSIM_HD u64& h_dl(int i) const { return q(L::Q_HEAP_DL, i); }
   MSIM_HD u32& h_pl(int i) const { return w(L::W_HEAP_PL, i); }
   /// Timer::add = BinaryHeap::push: append, sift_up while STRICTLY earlier than the parent
-  MSIM_HD void timer_push(u64 dl, u32 pl) {
+  MSIM_FN void timer_push(u64 dl, u32 pl) {
     u32 pos = heap_len;
     if (pos >= (u32)C::TQ) {
       fail_cap(MSIM_CAP_TIMERS);
@@ -258,7 +258,7 @@ struct Engine {
   }
   /// BinaryHeap::pop: move the last element to the root, sift_down_to_bottom (on equal
   /// deadlines the RIGHT child is promoted), then sift_up from the leaf.
-  MSIM_HD void timer_pop(u64& dl, u32& pl) {
+  MSIM_FN void timer_pop(u64& dl, u32& pl) {
     dl = h_dl(0);
     pl = h_pl(0);
     u32 end = --heap_len;
@@ -340,7 +340,7 @@ struct Engine {
     b(L::B_RQ, rq_len++) = (u8)t;
   }
   /// Waker::wake for the task that lived in slot `t` with generation `gen`
-  MSIM_HD void wake(int t, u32 gen) {
+  MSIM_FN void wake(int t, u32 gen) {
     if ((t_spawn(t) & 0xfffffu) != gen || t_spawn(t) == NONE32) return;
     u8 f = t_flags(t);
     if (f & (TF_COMPLETED | TF_CLOSED)) return;
@@ -383,7 +383,7 @@ struct Engine {
     maybe_free(t);
   }
   /// Spawner::spawn_inner (task/mod.rs:627-654): returns the slot or -1
-  MSIM_HD int spawn(u32 kind, u32 node, u8 extra_flags = 0) {
+  MSIM_FN int spawn(u32 kind, u32 node, u8 extra_flags = 0) {
     int t = -1;
     for (int wd = 0; wd < (C::NT + 63) / 64; wd++) {
       u64 m = q(L::Q_TFREE, wd);
@@ -455,7 +455,7 @@ struct Engine {
     return t_epoch(t) != n_epoch(n) || (n_flags(n) & NF_KILLED);
   }
   /// NodeInfo::kill for the CURRENT info of node n: wake every live task in spawn order
-  MSIM_HD void info_kill(int n, u8 epoch) {
+  MSIM_FN void info_kill(int n, u8 epoch) {
     // spawn order = ascending spawn index among this incarnation's live tasks
     u32 last = 0;
     bool first = true;
@@ -478,7 +478,7 @@ struct Engine {
       first = false;
     }
   }
-  MSIM_HD void drop_parked(int n) {
+  MSIM_FN void drop_parked(int n) {
     u32 len = w(L::W_PK_LEN), keep = 0;
     for (u32 i = 0; i < len; i++) {
       int t = b(L::B_PK, i);
@@ -490,7 +490,7 @@ struct Engine {
     }
     w(L::W_PK_LEN) = keep;
   }
-  MSIM_HD void kill(int n) {
+  MSIM_FN void kill(int n) {
     drop_parked(n);
     n_flags(n) = n_flags(n) | NF_KILLED;
     info_kill(n, n_epoch(n));
@@ -501,7 +501,7 @@ struct Engine {
     if (n_epoch(n) == epoch) n_flags(n) = n_flags(n) | NF_KILLED;
     info_kill(n, epoch);
   }
-  MSIM_HD void restart(int n) {
+  MSIM_FN void restart(int n) {
     drop_parked(n);
     info_kill(n, n_epoch(n));  // old_info.kill()
     n_epoch(n) = n_epoch(n) + 1;
@@ -557,7 +557,7 @@ struct Engine {
     return -1;
   }
   /// Network::bind (network.rs:206-251).  >= 0 socket slot; -1 AddrNotAvailable; -2 AddrInUse
-  MSIM_HD int sock_bind(int node, u32 addr) {
+  MSIM_FN int sock_bind(int node, u32 addr) {
     u32 ipk = addr_ipk(addr), port = addr_port(addr);
     if (ipk == IPK_NODE && (int)addr_node(addr) != node) return -1;
     if (port == 0) {
@@ -630,7 +630,7 @@ struct Engine {
   MSIM_HD void unclog_link(int sN, int d) { w(L::W_CLOG_LINK, sN) &= ~(1u << d); }
 
   /// NetSim::rand_delay (net/mod.rs:287-295): returns the Sleep deadline (always >= now + 1 ms)
-  MSIM_HD u64 rand_delay_deadline() {
+  MSIM_FN u64 rand_delay_deadline() {
     u64 delay = gen_range_u64(0, 5) * 1000ull;
     if (P->buggify) {
       if (next_u64() < P->buggify_p10_int) delay = gen_range_u64(1, 5) * NS_PER_SEC;
@@ -639,7 +639,7 @@ struct Engine {
   }
   /// The part of NetSim::send after rand_delay (net/mod.rs:304-332) + Network::try_send
   /// (network.rs:296-313).  `m` is a prepared message slot (tag, w, v0, v1); consumed.
-  MSIM_HD void net_send(int src_node, u32 src_port, u32 dst, int m) {
+  MSIM_FN void net_send(int src_node, u32 src_port, u32 dst, int m) {
     // resolve_dest_node (network.rs:273-291)
     int dst_node;
     u32 ipk = addr_ipk(dst);
@@ -682,7 +682,7 @@ struct Engine {
   /// Timer callback of NetSim::send → EndpointSocket::deliver → Mailbox::deliver
   /// (endpoint.rs:310-351).  The target socket OBJECT was captured at send time: if it has
   /// been closed/reset since, the message lands in a mailbox nobody can read (dropped here).
-  MSIM_HD void deliver(int m) {
+  MSIM_FN void deliver(int m) {
     u32 d = w(L::W_M_DST, m);
     int k = d >> 16;
     if (!sk_state(k) || (sk_gen(k) & 0xffff) != (d & 0xffff)) {
@@ -718,7 +718,7 @@ struct Engine {
   }
   /// Mailbox::recv(tag) (endpoint.rs:353-362) on the endpoint the task holds: either fills the
   /// task's oneshot at once (t_rx) or registers (tag, oneshot sender)
-  MSIM_HD void mbox_recv(int t, int k, u64 tag) {
+  MSIM_FN void mbox_recv(int t, int k, u64 tag) {
     u32 ml = b(L::B_SK_MBLEN, k);
     for (u32 i = 0; i < ml; i++) {
       int m = b(L::B_MB, k * C::NMBOX + i);
@@ -744,7 +744,7 @@ struct Engine {
   /// sender in `registered` until a message with its tag arrives; removing it eagerly is
   /// unobservable as long as no two LIVE registrations of a mailbox share a tag (the shipped
   /// workloads guarantee it; the oracle checks it) — DESIGN.md "eager registration GC".
-  MSIM_HD void mbox_unregister(int t) {
+  MSIM_FN void mbox_unregister(int t) {
     int k = t_sock(t);
     if (k == NONE8 || !sk_state(k) || (u8)sk_gen(k) != t_sockgen(t)) return;
     u32 me = ((u32)t << 20) | t_gen(t);
@@ -760,7 +760,7 @@ struct Engine {
   }
   /// Generic cleanup of what a future may hold (oneshot value, prepared message, registration,
   /// endpoint clone).  Workload on_drop hooks call this.
-  MSIM_HD void drop_task_resources(int t, bool registered) {
+  MSIM_FN void drop_task_resources(int t, bool registered) {
     if (registered) mbox_unregister(t);
     if (t_rx(t) != NONE8) {
       msg_free(t_rx(t));
@@ -775,7 +775,7 @@ struct Engine {
 
   // ---------------- lifecycle ----------------
   /// Runtime::with_seed_and_config (runtime/mod.rs:53-69) for this seed + block_on's spawn of main
-  MSIM_HD void init(u64 seed) {
+  MSIM_FN void init(u64 seed) {
     // zero this seed's columns
     for (int i = 0; i < L::NQ; i++) q(i) = 0;
     for (int i = 0; i < L::NW; i++) w(i) = 0;

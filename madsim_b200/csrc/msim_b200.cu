@@ -1,0 +1,690 @@
+// libmsim_b200.so — CUDA kernels (sm_100a) + the C-ABI of include/msim_b200.h.
+//
+// Kernel shape (B200-first):
+//   * one CTA owns S consecutive seeds; their whole state is a columnar block
+//     `field[slot][seed]` of S * Layout::BYTES bytes that lives in SHARED MEMORY for the
+//     duration of the launch (up to 227 KB per CTA → grid sized to one CTA per SM);
+//   * the block is staged HBM→smem / smem→HBM with 1-D bulk async copies (TMA, UBLKCP in SASS)
+//     completed through an mbarrier — only when a run is split into bursts; a run-to-completion
+//     launch initialises the block in place from the seed and writes back 64 B per seed;
+//   * lane = seed, but only `lanes_per_warp` lanes of each warp are populated (default 1): seeds
+//     follow different branches of the event loop, so co-resident lanes serialise (measured:
+//     1.01 active threads per instruction) while separate warps overlap on the 4 schedulers; the
+//     seed count per SM is bounded by shared memory, not by threads;
+//   * integer-only, no tensor cores: xoshiro256++, widening multiplies, heap sifts.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine/host_params.h"
+#include "workloads/all.h"
+
+using namespace msim;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// device side
+// ------------------------------------------------------------------------------------------
+constexpr int SMEM_HDR = 128;            // mbarrier lives here; the state block follows (128 B aligned)
+constexpr unsigned BULK_CHUNK = 32768;   // bytes per cp.async.bulk
+#ifndef MSIM_MAX_THREADS
+#define MSIM_MAX_THREADS 896
+#endif
+constexpr int MAX_THREADS = MSIM_MAX_THREADS;  // warps per CTA x 32; bounds registers per thread
+
+struct KernelArgs {
+  Params P;
+  uint64_t seed_base;
+  uint64_t n_seeds;
+  uint64_t max_events;      // per seed per launch; 0 = unlimited
+  unsigned char* blob;      // [n_blocks][S * BYTES] checkpoint in HBM (may be null if never needed)
+  SeedResult* results;      // [n_seeds]
+  msim_trace_rec* trace;    // optional (single-seed replay)
+  uint32_t* trace_n;
+  uint32_t trace_cap;
+  uint32_t S;               // seeds per CTA
+  uint32_t L;               // populated lanes per warp
+  uint32_t resume;          // 0: init from seed, 1: load checkpoint
+  uint32_t* unfinished;     // device counter: seeds still RUNNING after this launch
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+/// TMA 1-D bulk copy global → shared, completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+/// TMA 1-D bulk copy shared → global (bulk async-group)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <class WL>
+__global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_constant__ KernelArgs a) {
+  using E = Engine<WL>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  unsigned char* block = smem + SMEM_HDR;
+
+  const uint32_t S = a.S;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t col = warp * a.L + lane;  // this thread's seed column
+  const uint64_t first = (uint64_t)blockIdx.x * S;
+  const bool active = lane < a.L && col < S && first + col < a.n_seeds;
+  const uint32_t block_bytes = S * (uint32_t)E::L::BYTES;
+  unsigned char* gblob = a.blob ? a.blob + (size_t)blockIdx.x * block_bytes : nullptr;
+
+  // ---- stage in: TMA bulk copy of the checkpoint (resume) ----
+  if (a.resume) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_proxy_async();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, block_bytes);
+      for (uint32_t off = 0; off < block_bytes; off += BULK_CHUNK) {
+        uint32_t nb = block_bytes - off < BULK_CHUNK ? block_bytes - off : BULK_CHUNK;
+        bulk_g2s(block + off, gblob + off, nb, bar);
+      }
+    }
+    mbar_wait(bar, 0);
+  }
+
+  E e;
+  e.base = block;
+  e.S = S;
+  e.s = col;
+  e.P = &a.P;
+  e.tr = nullptr;
+  e.tr_cap = 0;
+  e.tr_n = 0;
+  e.status = MSIM_ST_PASS;
+  if (active) {
+    if (a.trace) {
+      e.tr = a.trace;
+      e.tr_cap = a.trace_cap;
+    }
+    if (a.resume) {
+      e.load();
+      if (a.trace) e.tr_n = *a.trace_n;
+    } else {
+      e.init(a.seed_base + first + col);
+    }
+    // ---- the event loop: up to max_events steps out of shared memory / registers ----
+    if (e.status == MSIM_ST_RUNNING) {
+      uint64_t budget = a.max_events ? a.max_events : ~0ull;
+      while (budget-- && e.step()) {
+      }
+    }
+    e.store();
+    SeedResult r;
+    e.result(r);
+    a.results[first + col] = r;
+    if (a.trace) *a.trace_n = e.tr_n;
+  }
+  // ---- stage out: checkpoint only if some seed of this CTA has not finished ----
+  int still = __syncthreads_or(active && e.status == MSIM_ST_RUNNING);
+  if (still) {
+    if (active && e.status == MSIM_ST_RUNNING) atomicAdd(a.unfinished, 1u);
+    if (gblob) {
+      fence_proxy_async();  // generic-proxy smem writes → visible to the async proxy
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (uint32_t off = 0; off < block_bytes; off += BULK_CHUNK) {
+          uint32_t nb = block_bytes - off < BULK_CHUNK ? block_bytes - off : BULK_CHUNK;
+          bulk_s2g(gblob + off, block + off, nb);
+        }
+        bulk_commit_wait();
+      }
+    }
+  }
+}
+
+/// Batch summary on the device: counters + pass/fail bitmap (what the N-GPU run all-reduces).
+/// out: u64 counters[8] = {ev_pop, ev_fire, draws, n_pass, n_fail, n_unfinished, first_fail_seed, n_seeds}
+///      followed by u32 bitmap[ceil(n/32)] (bit set = seed failed)
+__global__ void msim_summary_kernel(const SeedResult* __restrict__ res, uint64_t n, uint64_t seed_base,
+                                    unsigned long long* __restrict__ counters, uint32_t* __restrict__ bitmap) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long pop = 0, fire = 0, draws = 0, pass = 0, failn = 0, unf = 0, first = ~0ull;
+  bool failed = false;
+  if (i < n) {
+    SeedResult r = res[i];
+    pop = r.ev_pop;
+    fire = r.ev_fire;
+    draws = r.draws;
+    if (r.status == MSIM_ST_PASS)
+      pass = 1;
+    else if (r.status == MSIM_ST_RUNNING)
+      unf = 1;
+    else {
+      failn = 1;
+      failed = true;
+      first = seed_base + i;
+    }
+  }
+  uint32_t bits = __ballot_sync(0xffffffffu, failed);
+  if ((threadIdx.x & 31) == 0 && i < n) bitmap[i >> 5] = bits;
+  for (int o = 16; o > 0; o >>= 1) {
+    pop += __shfl_xor_sync(0xffffffffu, pop, o);
+    fire += __shfl_xor_sync(0xffffffffu, fire, o);
+    draws += __shfl_xor_sync(0xffffffffu, draws, o);
+    pass += __shfl_xor_sync(0xffffffffu, pass, o);
+    failn += __shfl_xor_sync(0xffffffffu, failn, o);
+    unf += __shfl_xor_sync(0xffffffffu, unf, o);
+    unsigned long long f2 = __shfl_xor_sync(0xffffffffu, first, o);
+    first = f2 < first ? f2 : first;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&counters[0], pop);
+    atomicAdd(&counters[1], fire);
+    atomicAdd(&counters[2], draws);
+    atomicAdd(&counters[3], pass);
+    atomicAdd(&counters[4], failn);
+    atomicAdd(&counters[5], unf);
+    atomicMin(&counters[6], first);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+thread_local std::string g_err;
+int set_err(int code, const std::string& m) {
+  g_err = m;
+  return code;
+}
+#define CUDA_TRY(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t _e = (x);                                                                        \
+    if (_e != cudaSuccess)                                                                       \
+      return set_err(MSIM_ECUDA, std::string(#x) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+template <class WL>
+cudaError_t launch_wl(const KernelArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  auto k = msim_step_kernel<WL>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<grid, block, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+int state_bytes_of(uint32_t workload) {
+  switch (workload) {
+    case MSIM_WL_SLEEP: return Layout<WL_Sleep::Caps>::BYTES;
+    case MSIM_WL_PINGPONG: return Layout<WL_PingPong::Caps>::BYTES;
+    case MSIM_WL_RAFT: return Layout<WL_Raft::Caps>::BYTES;
+  }
+  return -1;
+}
+
+}  // namespace
+
+struct msim_batch {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem = 0;
+  msim_config cfg{};
+  msim_workload_desc wl{};
+  bool has_wl = false;
+  Params P{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint32_t user_S = 0, user_L = 0;
+  // current run
+  uint64_t seed_base = 0, n_seeds = 0;
+  uint32_t S = 0, L = 0, n_blocks = 0, threads = 0;
+  size_t smem = 0;
+  bool ran = false, pending = false;
+  SeedResult* d_results = nullptr;
+  size_t d_results_cap = 0;
+  unsigned char* d_blob = nullptr;
+  size_t d_blob_cap = 0;
+  uint32_t* d_unfinished = nullptr;
+  uint32_t* h_unfinished = nullptr;  // pinned
+  SeedResult* h_results = nullptr;   // pinned staging
+  size_t h_results_cap = 0;
+  unsigned long long* d_summary = nullptr;
+  size_t d_summary_cap = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double kernel_ms = 0;
+  uint32_t launches = 0;
+};
+
+namespace {
+
+int choose_geometry(msim_batch* b, uint64_t n) {
+  int bytes = state_bytes_of(b->wl.workload);
+  if (bytes <= 0) return set_err(MSIM_EINVAL, "unknown workload");
+  uint32_t s_max = (uint32_t)((b->max_smem - SMEM_HDR) / bytes);
+  if (s_max == 0) return set_err(MSIM_EINVAL, "state block of one seed exceeds shared memory");
+  uint32_t S = b->user_S;
+  if (S == 0) {
+    // one CTA per SM when the batch fits in one wave; otherwise the largest block
+    uint64_t per_sm = (n + b->sm_count - 1) / b->sm_count;
+    S = (uint32_t)(per_sm < s_max ? per_sm : s_max);
+    if (S == 0) S = 1;
+    if (S > (uint32_t)MAX_THREADS) S = MAX_THREADS;
+  }
+  if (S > s_max) return set_err(MSIM_EINVAL, "seeds_per_cta exceeds shared memory (" + std::to_string(s_max) + " max)");
+  uint32_t L = b->user_L ? b->user_L : 1;  // one seed per warp: lanes never run converged (profiles/), warps do overlap
+  if (L > 32) L = 32;
+  const uint32_t max_warps = MAX_THREADS / 32;
+  if (S > max_warps * 32) return set_err(MSIM_EINVAL, "seeds_per_cta too large for the CTA");
+  uint32_t warps = (S + L - 1) / L;
+  if (warps > max_warps) {  // populate more lanes per warp instead of more warps
+    L = (S + max_warps - 1) / max_warps;
+    warps = (S + L - 1) / L;
+  }
+  b->S = S;
+  b->L = L;
+  b->threads = warps * 32;
+  b->n_blocks = (uint32_t)((n + S - 1) / S);
+  b->smem = SMEM_HDR + (size_t)S * bytes;
+  return MSIM_OK;
+}
+
+int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_trace, uint32_t* d_trace_n,
+           uint32_t trace_cap) {
+  KernelArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.P = b->P;
+  a.seed_base = b->seed_base;
+  a.n_seeds = b->n_seeds;
+  a.max_events = max_events;
+  a.blob = b->d_blob;
+  a.results = b->d_results;
+  a.trace = d_trace;
+  a.trace_n = d_trace_n;
+  a.trace_cap = trace_cap;
+  a.S = b->S;
+  a.L = b->L;
+  a.resume = resume ? 1 : 0;
+  a.unfinished = b->d_unfinished;
+  CUDA_TRY(cudaMemsetAsync(b->d_unfinished, 0, sizeof(uint32_t), b->stream));
+  dim3 grid(b->n_blocks), block(b->threads);
+  cudaError_t e;
+  switch (b->wl.workload) {
+    case MSIM_WL_SLEEP: e = launch_wl<WL_Sleep>(a, grid, block, b->smem, b->stream); break;
+    case MSIM_WL_PINGPONG: e = launch_wl<WL_PingPong>(a, grid, block, b->smem, b->stream); break;
+    case MSIM_WL_RAFT: e = launch_wl<WL_Raft>(a, grid, block, b->smem, b->stream); break;
+    default: return set_err(MSIM_EINVAL, "unknown workload");
+  }
+  if (e != cudaSuccess) return set_err(MSIM_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  b->launches++;
+  return MSIM_OK;
+}
+
+int ensure_buffers(msim_batch* b, uint64_t n, bool need_blob) {
+  if (n > b->d_results_cap) {
+    if (b->d_results) cudaFree(b->d_results);
+    b->d_results = nullptr;
+    CUDA_TRY(cudaMalloc(&b->d_results, n * sizeof(SeedResult)));
+    b->d_results_cap = n;
+  }
+  if (n > b->h_results_cap) {
+    if (b->h_results) cudaFreeHost(b->h_results);
+    b->h_results = nullptr;
+    CUDA_TRY(cudaMallocHost(&b->h_results, n * sizeof(SeedResult)));
+    b->h_results_cap = n;
+  }
+  size_t words = (n + 31) / 32;
+  size_t sb = 8 * sizeof(unsigned long long) + words * sizeof(uint32_t);
+  if (sb > b->d_summary_cap) {
+    if (b->d_summary) cudaFree(b->d_summary);
+    b->d_summary = nullptr;
+    CUDA_TRY(cudaMalloc(&b->d_summary, sb));
+    b->d_summary_cap = sb;
+  }
+  if (need_blob) {
+    size_t bb = (size_t)b->n_blocks * (b->smem - SMEM_HDR);
+    if (bb > b->d_blob_cap) {
+      if (b->d_blob) cudaFree(b->d_blob);
+      b->d_blob = nullptr;
+      CUDA_TRY(cudaMalloc(&b->d_blob, bb));
+      b->d_blob_cap = bb;
+    }
+  }
+  return MSIM_OK;
+}
+
+int run_impl(msim_batch* b, uint64_t seed_base, uint64_t n, uint64_t max_events, bool sync) {
+  if (!b) return set_err(MSIM_EINVAL, "null batch");
+  if (!b->has_wl) return set_err(MSIM_ESTATE, "msim_workload_load must be called before msim_batch_run");
+  if (n == 0) return set_err(MSIM_EINVAL, "n_seeds must be > 0");
+  CUDA_TRY(cudaSetDevice(b->device));
+  b->seed_base = seed_base;
+  b->n_seeds = n;
+  int rc = choose_geometry(b, n);
+  if (rc) return rc;
+  rc = ensure_buffers(b, n, max_events != 0);
+  if (rc) return rc;
+  if (max_events == 0) {
+    // run to completion: no checkpoint needed
+  }
+  b->launches = 0;
+  CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+  rc = launch(b, max_events, false, nullptr, nullptr, 0);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+  b->ran = true;
+  b->pending = true;
+  if (sync) return msim_batch_sync(b);
+  return MSIM_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int msim_version(void) { return MSIM_VERSION; }
+const char* msim_last_error(void) { return g_err.c_str(); }
+
+int msim_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) return set_err(MSIM_ENODEV, "no CUDA device: libmsim_b200 has no CPU fallback");
+  return n;
+}
+
+int msim_config_default(msim_config* cfg) {
+  if (!cfg) return set_err(MSIM_EINVAL, "null config");
+  config_defaults(cfg);
+  return MSIM_OK;
+}
+
+int msim_workload_default(uint32_t workload, msim_workload_desc* out) {
+  if (!out) return set_err(MSIM_EINVAL, "null descriptor");
+  if (workload_defaults(workload, out)) return set_err(MSIM_EINVAL, "unknown workload");
+  if (workload == MSIM_WL_CHAOS) return set_err(MSIM_EINVAL, "MSIM_WL_CHAOS is not available on the device yet");
+  return MSIM_OK;
+}
+
+int msim_batch_create(const msim_config* cfg, int device, msim_batch** out) {
+  if (!out) return set_err(MSIM_EINVAL, "null out pointer");
+  *out = nullptr;
+  int n = msim_device_count();
+  if (n < 0) return n;
+  if (device < 0 || device >= n) return set_err(MSIM_EINVAL, "bad device ordinal");
+  CUDA_TRY(cudaSetDevice(device));
+  auto* b = new msim_batch();
+  b->device = device;
+  if (cfg)
+    b->cfg = *cfg;
+  else
+    config_defaults(&b->cfg);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  b->sm_count = prop.multiProcessorCount;
+  b->max_smem = (int)prop.sharedMemPerBlockOptin;
+  CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  b->own_stream = true;
+  CUDA_TRY(cudaEventCreate(&b->ev0));
+  CUDA_TRY(cudaEventCreate(&b->ev1));
+  CUDA_TRY(cudaMalloc(&b->d_unfinished, sizeof(uint32_t)));
+  CUDA_TRY(cudaMallocHost(&b->h_unfinished, sizeof(uint32_t)));
+  *out = b;
+  return MSIM_OK;
+}
+
+void msim_batch_destroy(msim_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  if (b->d_results) cudaFree(b->d_results);
+  if (b->d_blob) cudaFree(b->d_blob);
+  if (b->d_unfinished) cudaFree(b->d_unfinished);
+  if (b->d_summary) cudaFree(b->d_summary);
+  if (b->h_unfinished) cudaFreeHost(b->h_unfinished);
+  if (b->h_results) cudaFreeHost(b->h_results);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int msim_workload_load(msim_batch* b, const msim_workload_desc* w) {
+  if (!b || !w) return set_err(MSIM_EINVAL, "null argument");
+  Params P;
+  std::string err;
+  int rc = make_params(b->cfg, *w, &P, &err);
+  if (rc) return set_err(rc, err);
+  if (state_bytes_of(w->workload) <= 0) return set_err(MSIM_EINVAL, "workload not available on the device");
+  b->wl = *w;
+  b->wl.n_nodes = P.n_nodes;
+  b->P = P;
+  b->has_wl = true;
+  b->ran = false;
+  return MSIM_OK;
+}
+
+int msim_batch_set_geometry(msim_batch* b, uint32_t seeds_per_cta, uint32_t lanes_per_warp) {
+  if (!b) return set_err(MSIM_EINVAL, "null batch");
+  if (lanes_per_warp > 32) return set_err(MSIM_EINVAL, "lanes_per_warp must be 0..32");
+  b->user_S = seeds_per_cta;
+  b->user_L = lanes_per_warp;
+  return MSIM_OK;
+}
+
+int msim_batch_set_stream(msim_batch* b, void* cuda_stream) {
+  if (!b) return set_err(MSIM_EINVAL, "null batch");
+  if (b->own_stream && b->stream) {
+    cudaStreamSynchronize(b->stream);
+    cudaStreamDestroy(b->stream);
+  }
+  b->stream = (cudaStream_t)cuda_stream;
+  b->own_stream = false;
+  return MSIM_OK;
+}
+
+int msim_batch_sync(msim_batch* b) {
+  if (!b) return set_err(MSIM_EINVAL, "null batch");
+  if (!b->pending) return MSIM_OK;
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  b->kernel_ms = ms;
+  b->pending = false;
+  return MSIM_OK;
+}
+
+int msim_batch_run(msim_batch* b, uint64_t seed_base, uint64_t n_seeds, uint64_t max_events_per_seed) {
+  return run_impl(b, seed_base, n_seeds, max_events_per_seed, true);
+}
+int msim_batch_run_async(msim_batch* b, uint64_t seed_base, uint64_t n_seeds, uint64_t max_events_per_seed) {
+  return run_impl(b, seed_base, n_seeds, max_events_per_seed, false);
+}
+
+int msim_batch_resume(msim_batch* b, uint64_t max_events_per_seed) {
+  if (!b || !b->ran) return set_err(MSIM_ESTATE, "nothing to resume");
+  if (!b->d_blob) return set_err(MSIM_ESTATE, "the previous run kept no checkpoint (max_events_per_seed was 0)");
+  CUDA_TRY(cudaSetDevice(b->device));
+  int rc = msim_batch_sync(b);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+  rc = launch(b, max_events_per_seed, true, nullptr, nullptr, 0);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+  b->pending = true;
+  double before = b->kernel_ms;
+  rc = msim_batch_sync(b);
+  b->kernel_ms += before;
+  return rc;
+}
+
+int msim_batch_results_device(msim_batch* b, void** dptr, size_t* bytes) {
+  if (!b || !b->ran) return set_err(MSIM_ESTATE, "no run yet");
+  if (dptr) *dptr = b->d_results;
+  if (bytes) *bytes = b->n_seeds * sizeof(SeedResult);
+  return MSIM_OK;
+}
+
+/// Device-side summary into caller-provided DEVICE memory (e.g. a torch tensor that is then
+/// all-reduced over NCCL): u64 counters[8] + u32 bitmap[ceil(n/32)].
+int msim_batch_summarize_device(msim_batch* b, void* d_out, size_t bytes) {
+  if (!b || !b->ran) return set_err(MSIM_ESTATE, "no run yet");
+  size_t words = (b->n_seeds + 31) / 32;
+  size_t need = 8 * sizeof(unsigned long long) + words * sizeof(uint32_t);
+  if (!d_out || bytes < need) return set_err(MSIM_ERANGE, "summary buffer too small");
+  CUDA_TRY(cudaSetDevice(b->device));
+  unsigned long long init[8] = {0, 0, 0, 0, 0, 0, ~0ull, (unsigned long long)b->n_seeds};
+  CUDA_TRY(cudaMemcpyAsync(d_out, init, sizeof(init), cudaMemcpyHostToDevice, b->stream));
+  auto* counters = (unsigned long long*)d_out;
+  auto* bitmap = (uint32_t*)((unsigned char*)d_out + sizeof(init));
+  unsigned threads = 256, blocks = (unsigned)((b->n_seeds + threads - 1) / threads);
+  msim_summary_kernel<<<blocks, threads, 0, b->stream>>>(b->d_results, b->n_seeds, b->seed_base, counters, bitmap);
+  CUDA_TRY(cudaGetLastError());
+  b->launches++;
+  return MSIM_OK;
+}
+
+int msim_batch_results(msim_batch* b, msim_seed_result* out, uint32_t* fail_bitmap, msim_stats* stats) {
+  if (!b || !b->ran) return set_err(MSIM_ESTATE, "no run yet");
+  CUDA_TRY(cudaSetDevice(b->device));
+  int rc = msim_batch_sync(b);
+  if (rc) return rc;
+  uint64_t n = b->n_seeds;
+  size_t words = (n + 31) / 32;
+  std::vector<unsigned long long> h(8 + (words + 1) / 2 + 1);
+  if (fail_bitmap || stats) {
+    rc = msim_batch_summarize_device(b, b->d_summary, b->d_summary_cap);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h.data(), b->d_summary, 8 * sizeof(unsigned long long) + words * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, b->stream));
+  }
+  if (out) {
+    CUDA_TRY(cudaMemcpyAsync(b->h_results, b->d_results, n * sizeof(SeedResult), cudaMemcpyDeviceToHost, b->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  if (out) std::memcpy(out, b->h_results, n * sizeof(SeedResult));
+  if (fail_bitmap) std::memcpy(fail_bitmap, h.data() + 8, words * sizeof(uint32_t));
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->n_seeds = n;
+    stats->ev_pop = h[0];
+    stats->ev_fire = h[1];
+    stats->draws = h[2];
+    stats->n_pass = h[3];
+    stats->n_fail = h[4];
+    stats->n_unfinished = h[5];
+    stats->first_fail_seed = h[6];
+    stats->kernel_ms = b->kernel_ms;
+    stats->launches = b->launches;
+    stats->seeds_per_cta = b->S;
+    stats->lanes_per_warp = b->L;
+    stats->ctas = b->n_blocks;
+    stats->smem_bytes = (uint32_t)b->smem;
+  }
+  return MSIM_OK;
+}
+
+int msim_batch_trace_hash(msim_batch* b, uint64_t* hash) {
+  if (!b || !b->ran) return set_err(MSIM_ESTATE, "no run yet");
+  if (!hash) return set_err(MSIM_EINVAL, "null output");
+  int rc = msim_batch_sync(b);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaMemcpyAsync(b->h_results, b->d_results, b->n_seeds * sizeof(SeedResult), cudaMemcpyDeviceToHost,
+                           b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  for (uint64_t i = 0; i < b->n_seeds; i++) hash[i] = b->h_results[i].trace_hash;
+  return MSIM_OK;
+}
+
+int msim_batch_trace(msim_batch* b, uint64_t seed, msim_trace_rec* out, size_t cap, size_t* n, msim_seed_result* result) {
+  if (!b || !b->has_wl) return set_err(MSIM_ESTATE, "msim_workload_load must be called first");
+  if (cap > 0xffffffffull) return set_err(MSIM_ERANGE, "trace capacity too large");
+  CUDA_TRY(cudaSetDevice(b->device));
+  int rc = msim_batch_sync(b);
+  if (rc) return rc;
+  // replay this one seed in a scratch batch that shares config + workload
+  msim_batch* r = nullptr;
+  rc = msim_batch_create(&b->cfg, b->device, &r);
+  if (rc) return rc;
+  struct Guard {
+    msim_batch* p;
+    ~Guard() { msim_batch_destroy(p); }
+  } guard{r};
+  rc = msim_workload_load(r, &b->wl);
+  if (rc) return rc;
+  r->user_S = 1;
+  r->user_L = 1;
+  r->seed_base = seed;
+  r->n_seeds = 1;
+  rc = choose_geometry(r, 1);
+  if (rc) return rc;
+  rc = ensure_buffers(r, 1, false);
+  if (rc) return rc;
+  msim_trace_rec* d_tr = nullptr;
+  uint32_t* d_n = nullptr;
+  size_t dcap = cap ? cap : 1;
+  CUDA_TRY(cudaMalloc(&d_tr, dcap * sizeof(msim_trace_rec)));
+  CUDA_TRY(cudaMalloc(&d_n, sizeof(uint32_t)));
+  CUDA_TRY(cudaMemsetAsync(d_n, 0, sizeof(uint32_t), r->stream));
+  rc = launch(r, 0, false, d_tr, d_n, (uint32_t)cap);
+  if (rc == MSIM_OK) {
+    uint32_t hn = 0;
+    cudaError_t e = cudaStreamSynchronize(r->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(&hn, d_n, sizeof(hn), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out && cap)
+      e = cudaMemcpy(out, d_tr, (hn < cap ? hn : cap) * sizeof(msim_trace_rec), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && result) e = cudaMemcpy(result, r->d_results, sizeof(SeedResult), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess)
+      rc = set_err(MSIM_ECUDA, std::string("trace replay: ") + cudaGetErrorString(e));
+    else if (n)
+      *n = hn;
+  }
+  cudaFree(d_tr);
+  cudaFree(d_n);
+  return rc;
+}
+
+/// Bytes of per-seed state for a workload (DESIGN.md capacity table; bench roofline accounting)
+int msim_workload_state_bytes(uint32_t workload) {
+  int b = state_bytes_of(workload);
+  return b > 0 ? b : set_err(MSIM_EINVAL, "unknown workload");
+}
+
+}  // extern "C"

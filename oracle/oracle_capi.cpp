@@ -29,6 +29,7 @@ Config to_config(const msim_config* c) {
 
 struct Extra {
   uint32_t peak_ready, peak_registered, peak_msgs, tasks_spawned;
+  uint64_t sum_log2_heap;
 };
 
 thread_local size_t g_peak_registered = 0, g_peak_msgs = 0;
@@ -99,6 +100,7 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
   if (extra) {
     extra->peak_ready = u32(rt.task.peak_ready);
     extra->tasks_spawned = rt.task.handle.sh.next_task_id;
+    extra->sum_log2_heap = rt.tracer.sum_log2_heap;
     extra->peak_registered = u32(g_peak_registered);
     extra->peak_msgs = u32(g_peak_msgs);
   }
@@ -116,7 +118,7 @@ int oracle_version(void) { return MSIM_VERSION; }
 /// One seed; optionally the full canonical trace.
 int oracle_run_seed(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed, msim_seed_result* out,
                     msim_trace_rec* trace, size_t cap, size_t* n_trace, char* msg, size_t msg_cap,
-                    uint32_t* extra4) {
+                    uint32_t* extra4 /* [6] or NULL */) {
   std::vector<msim_trace_rec> full;
   std::string m;
   Extra ex{};
@@ -133,6 +135,8 @@ int oracle_run_seed(const msim_config* cfg, const msim_workload_desc* wl, uint64
     extra4[1] = ex.peak_registered;
     extra4[2] = ex.peak_msgs;
     extra4[3] = ex.tasks_spawned;
+    extra4[4] = uint32_t(ex.sum_log2_heap);
+    extra4[5] = uint32_t(ex.sum_log2_heap >> 32);
   }
   return MSIM_OK;
 }

@@ -20,6 +20,7 @@ namespace msim_oracle {
 struct Tracer {
   u64 hash = MSIM_HASH_INIT;
   u64 n_pop = 0, n_fire = 0;
+  u64 sum_log2_heap = 0;  // Σ floor(log2(heap length)) over timer fires: roofline byte model
   std::vector<msim_trace_rec>* full = nullptr;  // optional full trace
   static u64 mix(u64 h, u64 w) {
     h ^= w;
@@ -70,6 +71,7 @@ class Timer {
     assert(!expiring_ && "timer callbacks never re-enter the timer (spin lock held, time/mod.rs:46,105)");
     expiring_ = true;
     while (!ev_.empty() && ev_[0].deadline <= now) {
+      len_at_fire_ = ev_.size();
       Event e = pop();
       on_fire(e);
       e.callback();
@@ -78,6 +80,7 @@ class Timer {
   }
   size_t len() const { return ev_.size(); }
   size_t peak() const { return peak_; }
+  size_t len_at_fire() const { return len_at_fire_; }
   bool expiring() const { return expiring_; }
 
  private:
@@ -122,7 +125,7 @@ class Timer {
     return item;
   }
   std::vector<Event> ev_;
-  size_t peak_ = 0;
+  size_t peak_ = 0, len_at_fire_ = 1;
   bool expiring_ = false;
 };
 
@@ -194,6 +197,7 @@ class TimeHandle {
   void expire(u64 now) {
     timer_.expire(now, [&](const Timer::Event& e) {
       tracer_.record(clock_.elapsed(), e.deadline, e.meta.kind, e.meta.id, rand_.draws());
+      tracer_.sum_log2_heap += 63 - __builtin_clzll(u64(timer_.len_at_fire()));
     });
   }
   GlobalRng& rand_;

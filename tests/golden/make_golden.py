@@ -1,0 +1,52 @@
+"""Generates tests/golden/golden_v1.json from the ORACLE (oracle/liboracle.so).
+
+The reference holds no golden vectors for this path and cannot be built here (no Rust toolchain,
+SURVEY.md §8c), so these vectors pin the oracle + engine against regressions; they are NOT outputs
+of the reference itself (parity vs the reference stays "unpinned").
+Run:  python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import oracle_py as o
+
+import madsim_b200 as m
+
+CASES = {
+    "sleep_1s": (dict(), dict(kind="sleep", duration_ns=10**9), [0, 1, 2, 2333]),
+    "pingpong_r1000": (dict(), dict(kind="pingpong", rounds=1000), [0, 1, 2333]),  # BASELINE config 1
+    "pingpong_r50_loss10": (dict(packet_loss_rate=0.1), dict(kind="pingpong", rounds=50), list(range(8))),
+    "raft_cfg2": (dict(), dict(kind="raft"), list(range(16)) + [4095, 65535]),  # BASELINE config 2
+    "raft_cfg3": (dict(), dict(kind="raft", faults=7), list(range(16)) + [4095, 65535]),  # config 3
+    "raft_cfg2_bug": (dict(), dict(kind="raft", bug=1), [88, 89, 90]),
+    "raft_cfg3_loss5": (dict(packet_loss_rate=0.05), dict(kind="raft", faults=7), list(range(4))),
+}
+
+
+def make_wl(d):
+    d = dict(d)
+    kind = d.pop("kind")
+    return getattr(m.Workload, kind)(**d)
+
+
+def main():
+    out = {"format": 1, "fields": ["trace_hash", "elapsed_ns", "draws", "ev_pop", "ev_fire", "status", "fail_code",
+                                   "user"], "cases": {}}
+    for name, (cfg, wl, seeds) in CASES.items():
+        rows = []
+        for s in seeds:
+            r, _, _, _ = o.run_seed(m.Config(**cfg), make_wl(wl), s)
+            rows.append([s, str(int(r["trace_hash"])), int(r["elapsed_ns"]), int(r["draws"]), int(r["ev_pop"]),
+                         int(r["ev_fire"]), int(r["status"]), int(r["fail_code"]), [int(x) for x in r["user"]]])
+        out["cases"][name] = {"config": cfg, "workload": wl, "rows": rows}
+    with open(os.path.join(HERE, "golden_v1.json"), "w") as f:
+        json.dump(out, f, indent=0, separators=(",", ":"))
+    print("wrote", len(out["cases"]), "cases")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,101 @@
+"""Host logic: the device engine's state machines, compiled for the host by tests/enginecheck
+(TEST-ONLY — the product runs them on the GPU exclusively), diffed against the oracle.  This is
+what lets the state machines be developed and regression-tested where there is no GPU."""
+import numpy as np
+import pytest
+
+import madsim_b200 as m
+
+FIELDS = ("trace_hash", "elapsed_ns", "draws", "ev_pop", "ev_fire", "status", "fail_code", "user", "peak_timers",
+          "peak_tasks")
+
+
+def _assert_same(oracle, cfg, wl, seed_base, n, **kw):
+    ref = oracle.run_many(cfg, wl, seed_base, n)
+    got, _ = oracle.engine_host(cfg, wl, seed_base, n, **kw)
+    for f in FIELDS:
+        if not np.array_equal(ref[f], got[f]):
+            bad = int(np.nonzero((ref[f] != got[f]).reshape(n, -1).any(axis=1))[0][0])
+            _, tr_o, _, _ = oracle.run_seed(cfg, wl, seed_base + bad, trace=True)
+            _, tr_e = oracle.engine_host(cfg, wl, seed_base + bad, 1, trace_seed=seed_base + bad)
+            d = oracle.first_trace_diff(tr_o, tr_e)
+            pytest.fail(f"{f} differs at seed {seed_base + bad}: oracle {ref[f][bad]} engine {got[f][bad]}; "
+                        f"first trace divergence at record {d}")
+
+
+CASES = [
+    ("sleep", m.Config(), m.Workload.sleep(10**9), 0, 64),
+    ("pingpong", m.Config(), m.Workload.pingpong(rounds=40), 0, 64),
+    ("pingpong-loss", m.Config(packet_loss_rate=0.1), m.Workload.pingpong(rounds=40), 100, 64),  # deadlocks
+    ("pingpong-lossall", m.Config(packet_loss_rate=1.0), m.Workload.pingpong(rounds=3), 0, 8),
+    ("pingpong-buggify-medium", m.Config(send_latency_ns=(500 * m.MS, 2500 * m.MS), buggify=True),
+     m.Workload.pingpong(rounds=20), 0, 32),
+    ("pingpong-small-carry", m.Config(send_latency_ns=(1500 * m.MS, 2200 * m.MS)), m.Workload.pingpong(rounds=20), 0, 16),
+    ("pingpong-timelimit", m.Config(time_limit_ns=2 * m.SEC), m.Workload.pingpong(rounds=1000), 0, 8),
+    ("pingpong-zero-rounds", m.Config(), m.Workload.pingpong(rounds=0), 0, 8),
+    ("raft", m.Config(), m.Workload.raft(duration_ms=3000), 0, 48),
+    ("raft-faults", m.Config(), m.Workload.raft(duration_ms=4000, faults=7), 1000, 48),
+    ("raft-bug", m.Config(), m.Workload.raft(duration_ms=4000, bug=1), 0, 120),
+    ("raft-faults-bug-loss", m.Config(packet_loss_rate=0.05), m.Workload.raft(duration_ms=4000, faults=7, bug=1), 7, 48),
+    ("raft-3node", m.Config(), m.Workload.raft(n_nodes=3, duration_ms=3000, faults=5), 0, 32),
+    ("raft-1node", m.Config(), m.Workload.raft(n_nodes=1, duration_ms=1500), 0, 8),
+    ("raft-fast-timeouts", m.Config(), m.Workload.raft(duration_ms=1500, rpc_timeout_ms=25, heartbeat_ms=30,
+                                                        election_ms=(80, 160), faults=4), 0, 32),
+    ("raft-zero-duration", m.Config(), m.Workload.raft(duration_ms=0), 0, 4),
+]
+
+
+@pytest.mark.parametrize("name,cfg,wl,base,n", CASES, ids=[c[0] for c in CASES])
+def test_engine_matches_oracle(oracle, name, cfg, wl, base, n):
+    _assert_same(oracle, cfg, wl, base, n, seeds_per_block=5)
+
+
+def test_burst_checkpoint_equals_run_to_completion(oracle):
+    # registers ↔ state-block spill every k events must not change anything
+    cfg, wl = m.Config(), m.Workload.raft(duration_ms=2000, faults=7)
+    a, _ = oracle.engine_host(cfg, wl, 0, 16, seeds_per_block=4)
+    for k in (1, 7, 1000):
+        b, _ = oracle.engine_host(cfg, wl, 0, 16, seeds_per_block=3, max_events=k)
+        assert np.array_equal(a, b)
+
+
+def test_full_trace_equal(oracle):
+    cfg, wl = m.Config(), m.Workload.raft(duration_ms=2500, faults=7)
+    for seed in (0, 5, 123456789012345):
+        _, tr_o, _, _ = oracle.run_seed(cfg, wl, seed, trace=True)
+        _, tr_e = oracle.engine_host(cfg, wl, seed, 1, trace_seed=seed)
+        assert len(tr_o) == len(tr_e) and oracle.first_trace_diff(tr_o, tr_e) is None
+
+
+def test_capacity_overflow_is_reported_not_silent(oracle):
+    # 20 virtual minutes of clock-jump faults accumulate stale responses / timers until a bounded
+    # table overflows on SOME seed; such seeds must say FAIL_CAPACITY, everything else must match
+    cfg, wl = m.Config(), m.Workload.raft(duration_ms=120_000, faults=7)
+    got, _ = oracle.engine_host(cfg, wl, 0, 12, seeds_per_block=4)
+    ref = oracle.run_many(cfg, wl, 0, 12)
+    ok = got["status"] != m.ST_FAIL_CAPACITY
+    assert np.array_equal(got["trace_hash"][ok], ref["trace_hash"][ok])
+    assert set(np.unique(got["status"])) <= {m.ST_PASS, m.ST_FAIL_CAPACITY}
+    assert (got["fail_code"][~ok] > 0).all()
+
+
+def test_leaky_config_overflows_loudly(oracle):
+    # rpc timeout (3 ms) below the round trip: EVERY response arrives after its caller gave up and
+    # stays in the mailbox forever (the reference leaks them too, endpoint.rs:335-350) → the bounded
+    # device mailbox must report MSIM_CAP_MAILBOX, and the trace must agree up to that point
+    cfg = m.Config()
+    wl = m.Workload.raft(duration_ms=3000, rpc_timeout_ms=3, heartbeat_ms=20, election_ms=(40, 80), faults=4)
+    got, tr_e = oracle.engine_host(cfg, wl, 0, 1, trace_seed=0)
+    assert got["status"][0] == m.ST_FAIL_CAPACITY and got["fail_code"][0] == 5
+    _, tr_o, _, _ = oracle.run_seed(cfg, wl, 0, trace=True)
+    assert len(tr_e) < len(tr_o) and np.array_equal(tr_o[: len(tr_e)], tr_e)
+
+
+def test_bug_mode_finds_a_failing_seed(oracle):
+    # seeds-to-first-bug: the injected double-vote bug must be caught as "two leaders in one term"
+    cfg, wl = m.Config(), m.Workload.raft(bug=1)
+    got, _ = oracle.engine_host(cfg, wl, 0, 128, seeds_per_block=8)
+    fails = np.nonzero(got["status"] == m.ST_FAIL_ASSERT)[0]
+    assert len(fails) > 0 and (got["fail_code"][fails] == 1).all()
+    ref = oracle.run_many(cfg, wl, 0, 128)
+    assert np.array_equal(got["status"], ref["status"]) and int(fails[0]) == int(np.nonzero(ref["status"] == 2)[0][0])

@@ -159,20 +159,18 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
     a.results[first + col] = r;
     if (a.trace) *a.trace_n = e.tr_n;
   }
-  // ---- stage out: checkpoint only if some seed of this CTA has not finished ----
-  int still = __syncthreads_or(active && e.status == MSIM_ST_RUNNING);
-  if (still) {
-    if (active && e.status == MSIM_ST_RUNNING) atomicAdd(a.unfinished, 1u);
-    if (gblob) {
-      fence_proxy_async();  // generic-proxy smem writes → visible to the async proxy
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        for (uint32_t off = 0; off < block_bytes; off += BULK_CHUNK) {
-          uint32_t nb = block_bytes - off < BULK_CHUNK ? block_bytes - off : BULK_CHUNK;
-          bulk_s2g(gblob + off, block + off, nb);
-        }
-        bulk_commit_wait();
+  // ---- stage out: in burst mode (a checkpoint buffer exists) the block always goes back to HBM,
+  // finished seeds included, so that a later resume reloads a consistent image ----
+  if (active && e.status == MSIM_ST_RUNNING) atomicAdd(a.unfinished, 1u);
+  if (gblob) {
+    fence_proxy_async();  // generic-proxy smem writes → visible to the async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (uint32_t off = 0; off < block_bytes; off += BULK_CHUNK) {
+        uint32_t nb = block_bytes - off < BULK_CHUNK ? block_bytes - off : BULK_CHUNK;
+        bulk_s2g(gblob + off, block + off, nb);
       }
+      bulk_commit_wait();
     }
   }
 }

@@ -7,8 +7,11 @@
 // vectors for this path and cannot be compiled here (no Rust toolchain).
 // The oracle is pinned instead by public KATs of the third-party arithmetic and by the
 // reference's outcome assertions (tests/test_oracle_*.py).
+#include <malloc.h>
+
 #include <atomic>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 #include "workloads.hpp"
@@ -111,6 +114,19 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
 
 }  // namespace
 
+// The CPU baseline must not be handicapped by allocator artefacts: with the default glibc
+// thresholds every Runtime teardown trims/unmaps memory, which serialises 100+ worker threads on
+// the kernel's mmap lock (measured: 128 threads reached only ~9x one thread).  Keep freed memory
+// in the per-thread arenas instead.
+static void tune_malloc_once() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TOP_PAD, 64 << 20);
+  });
+}
+
 extern "C" {
 
 int oracle_version(void) { return MSIM_VERSION; }
@@ -144,6 +160,7 @@ int oracle_run_seed(const msim_config* cfg, const msim_workload_desc* wl, uint64
 /// Builder::run seed sweep (runtime/builder.rs:129-150): seeds seed_base..+n on `jobs` threads.
 int oracle_run_many(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed_base, uint64_t n,
                     uint32_t jobs, msim_seed_result* out) {
+  tune_malloc_once();
   if (jobs == 0) jobs = std::max(1u, std::thread::hardware_concurrency());
   std::atomic<uint64_t> next{0};
   std::atomic<int> rc{0};

@@ -18,6 +18,11 @@
 #define MSIM_HD inline
 #define MSIM_HD_NOINLINE inline
 #endif
+#if defined(__CUDACC__)
+#define MSIM_NOUNROLL _Pragma("unroll 1")
+#else
+#define MSIM_NOUNROLL
+#endif
 // Heavy helpers that are called from many state-machine sites: one shared copy keeps the
 // hot code inside the instruction cache (round-1 ncu: 57 % icc hit rate when all inlined).
 #if defined(MSIM_INLINE_ALL)

@@ -8,15 +8,24 @@
 //   naive_timer::Timer (BinaryHeap)            crate naive-timer 0.2 + std BinaryHeap sift rules
 //   GlobalRng / xoshiro256++ / gen_range       madsim/src/sim/rand.rs:42-89 + rand 0.8 / rand_xoshiro 0.6
 //   NetSim::{rand_delay,send}, Network::*      madsim/src/sim/net/mod.rs:287-333, network.rs:142-313
-//   Endpoint mailbox                           madsim/src/sim/net/endpoint.rs:298-363
+//   Endpoint mailbox, rpc call/call_timeout    madsim/src/sim/net/endpoint.rs:298-363, net/rpc.rs:96-131
 //   TaskHandle::{kill,restart,pause,resume}    madsim/src/sim/task/mod.rs:356-424
 //
-// Design (B200-first, not a translation): all per-seed state is a bounded, columnar block
-// `field[slot][seed]` that lives in shared memory while a CTA advances its seeds (staged from /
-// to HBM with bulk async copies by the kernel, see kernel.cu); the hot scalars (rng, clock,
-// trace hash, queue lengths) are cached in registers for the whole burst.  Arbitrary futures
-// become explicit poll-level state machines (workloads/*.h).  Every bounded table reports
-// overflow as MSIM_ST_FAIL_CAPACITY — never silently.
+// Design (B200-first, not a translation).
+//  * All per-seed state is ONE bounded block (Layout::BYTES) that lives in shared memory while a
+//    CTA advances its seeds; the hot scalars (rng, clock, trace hash, queue lengths) are cached
+//    in registers for the whole burst.  The block is seed-major (one base register + immediate
+//    offsets per access): HBM<->smem staging is a bulk TMA copy of whole blocks, so the HBM image
+//    needs no columnar interleave for coalescing, and address arithmetic is what the instruction
+//    -issue-bound kernel cannot afford (profiles/: 0.42 IPC, 57 % I-cache hit rate when every
+//    primitive was inlined at every await site).
+//  * REQUEST / DISPATCH: a task's future is an explicit state machine (`WL::fsm`) that contains
+//    only workload logic.  Whenever it needs a runtime primitive — sleep, rand_delay, bind, send,
+//    recv, call_timeout, spawn, gen_range, join, time::advance — it RETURNS a request; the engine
+//    executes it in one shared place (`poll_task`) and re-enters the state machine.  Each
+//    primitive's poll-level behaviour therefore exists exactly once in the
+//    instruction stream, and lanes of a warp that wait in the same primitive execute it together.
+//  * Every bounded table reports overflow as MSIM_ST_FAIL_CAPACITY — never silently.
 #pragma once
 #include "defs.h"
 
@@ -24,13 +33,51 @@ namespace msim {
 
 constexpr int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-/// Compile-time layout of one seed's state block for capacities `C`.
+// ---- what a suspended future is waiting for (t_wait): state[3:0] | WF_* ----
+enum : u8 {
+  W_NONE = 0,
+  W_SLEEP = 1,       // Sleep on dl0                                   -> resume the state machine
+  W_BIND = 2,        // Endpoint::bind: rand_delay, then Network::bind -> ret = socket
+  W_SEND = 3,        // send_to_raw: rand_delay, then NetSim::send of the prepared message
+  W_RECV_RX = 4,     // recv_from_raw: oneshot not filled yet
+  W_RECV_DELAY = 5,  // recv_from_raw: rand_delay AFTER the receipt   -> rv0/rv1/rfrom/rw
+  W_CALL_SEND = 6,   // call_timeout: inside call's send_to_raw
+  W_CALL_RX = 7,     // call_timeout: inside call's recv_from_raw (oneshot)
+  W_CALL_DELAY = 8,  // call_timeout: inside call's post-receipt rand_delay
+  W_JOIN = 9,        // JoinHandle.await
+  WF_RD = 0x10,      // rand_delay not drawn yet: draw it now, then sleep on dl0
+  WF_SLEEP = 0x20,   // sleeping on dl0
+};
+
+// ---- requests a state machine returns to the engine ----
+enum : int {
+  RQ_PENDING = 0,   // Poll::Pending with nothing registered (woken by someone else)
+  RQ_READY,         // Poll::Ready
+  RQ_PANIC,         // ya = code
+  RQ_SLEEP_FOR,     // time::sleep(xa ns)
+  RQ_SLEEP_UNTIL,   // time::sleep_until(xa)
+  RQ_RAND_DELAY,    // NetSim::rand_delay
+  RQ_BIND,          // Endpoint::bind(ya = addr)                          -> ret = socket or <0
+  RQ_SEND,          // ep.send_to_raw(ya = dst, tag xa, payload {w: xb, v: [yb, yc]})
+  RQ_RECV,          // ep.recv_from_raw(tag xa)                           -> rv0, rv1, rfrom, rw
+  RQ_CALL,          // ep.call_timeout(ya = dst, req tag xa, {yb, yc}, timeout xb ns) -> ret, rv0, rv1
+  RQ_SPAWN,         // task::spawn: ya = kind | SPAWN_*; yb = node; locals a = yc, b = yd, c = lo32(xa), dl1 = xb -> ret
+  RQ_CREATE_NODE,   // Handle::create_node().ip().init().build(): ya = NODE_* flags     -> ret = node id
+  RQ_GEN_RANGE,     // thread_rng().gen_range(xa..xb) (u64)                -> ret64
+  RQ_JOIN,          // JoinHandle(ya = task slot).await                   -> ret (1 ok / 2 cancelled), rv0 = output
+  RQ_ADVANCE,       // time::advance(xa ns)
+};
+enum : u32 { SPAWN_EP = 0x100, SPAWN_JOINABLE = 0x200 };  // clone the caller's Endpoint / keep a JoinHandle
+enum : u32 { NODE_IP = 1, NODE_INIT = 2, NODE_RESTART_ON_PANIC = 4 };
+enum : int { CALL_OK = 1, CALL_TIMEOUT = 2 };
+
+/// Compile-time layout of one seed's state block for capacities `C` (element offsets per section).
 template <class C>
 struct Layout {
   static_assert(C::NT <= 128, "task bitmap is 2 x u64");
   static_assert(C::NMSG <= 64, "message bitmap is 1 x u64");
   static_assert(C::NT < 255 && C::NMSG < 255 && C::NSOCK < 255, "u8 indices");
-  // ---- u64 section (element offsets) ----
+  // ---- u64 section ----
   static constexpr int Q_RNG = 0;      // 4
   static constexpr int Q_NOW = 4;
   static constexpr int Q_HASH = 5;
@@ -51,7 +98,7 @@ struct Layout {
     W_PEAK_TIMERS, W_LIVE_TASKS, W_PEAK_TASKS, W_USER0, W_USER1, W_USER2, W_USER3, W_CLOG_IN, W_CLOG_OUT,
     W_PK_LEN, W_BASE_SECS, W_NEXT_NODE, W_MAIN_SLOT, W_PANIC_CODE, W_NSCALAR
   };
-  static constexpr int W_CLOG_LINK = W_NSCALAR;                 // [NNODE] bit d set: link n→d clogged
+  static constexpr int W_CLOG_LINK = W_NSCALAR;                 // [NNODE] bit d set: link n->d clogged
   static constexpr int W_HEAP_PL = W_CLOG_LINK + C::NNODE;      // [TQ]
   static constexpr int W_T_SPAWN = W_HEAP_PL + C::TQ;           // [NT] spawn index (NONE32 = free slot)
   static constexpr int W_T_AW = W_T_SPAWN + C::NT;              // [NT] awaiter (slot<<20|gen) or NONE32
@@ -60,7 +107,7 @@ struct Layout {
   static constexpr int W_T_C = W_T_B + C::NT;
   static constexpr int W_M_V0 = W_T_C + C::NT;                  // [NMSG] payload v[0]
   static constexpr int W_M_V1 = W_M_V0 + C::NMSG;
-  static constexpr int W_M_FROM = W_M_V1 + C::NMSG;             // source address
+  static constexpr int W_M_FROM = W_M_V1 + C::NMSG;             // source address (before the send: the destination)
   static constexpr int W_M_DST = W_M_FROM + C::NMSG;            // sock<<16 | gen16, captured at send
   static constexpr int W_M_SERIAL = W_M_DST + C::NMSG;
   static constexpr int W_RG_WAITER = W_M_SERIAL + C::NMSG;      // [NSOCK*NREG] slot<<20|gen
@@ -75,8 +122,8 @@ struct Layout {
   static constexpr int B_T_FLAGS = B_T_PC + C::NT;
   static constexpr int B_T_NODE = B_T_FLAGS + C::NT;
   static constexpr int B_T_EPOCH = B_T_NODE + C::NT;
-  static constexpr int B_T_SUB = B_T_EPOCH + C::NT;     // pc of the nested future (rpc call)
-  static constexpr int B_T_RX = B_T_SUB + C::NT;        // oneshot slot: delivered message or NONE8
+  static constexpr int B_T_WAIT = B_T_EPOCH + C::NT;    // W_* | WF_*: what the suspended future awaits
+  static constexpr int B_T_RX = B_T_WAIT + C::NT;       // oneshot slot: delivered message or NONE8
   static constexpr int B_T_SOCK = B_T_RX + C::NT;       // endpoint this future holds (BindGuard ref) or NONE8
   static constexpr int B_T_SOCKGEN = B_T_SOCK + C::NT;
   static constexpr int B_T_MSG = B_T_SOCKGEN + C::NT;   // message slot owned by the future or NONE8
@@ -93,9 +140,9 @@ struct Layout {
   static constexpr int B_PK = B_N_EPOCH + C::NNODE;        // [NPARK] parked runnables, park order
   static constexpr int NB = B_PK + C::NPARK;
 
-  static constexpr int W_BASE = 8 * NQ;                 // byte offset (per seed) of the u32 section
-  static constexpr int B_BASE = W_BASE + 4 * NW;        // … of the u8 section
-  static constexpr int BYTES = round_up(B_BASE + NB, 16);  // per seed; a CTA's block is S * BYTES
+  static constexpr int W_BASE = 8 * NQ;                 // byte offset of the u32 section
+  static constexpr int B_BASE = W_BASE + 4 * NW;        // ... of the u8 section
+  static constexpr int BYTES = round_up(B_BASE + NB, 16);  // one seed; a CTA's block is S * BYTES
 };
 
 /// One lane's view of its seed.  `WL` supplies Caps + the state machines.
@@ -104,31 +151,30 @@ struct Engine {
   using C = typename WL::Caps;
   using L = Layout<C>;
 
-  unsigned char* base;  // start of the CTA's state block (shared memory on the device)
-  u32 S;                // seeds in the block
-  u32 s;                // this seed's column
+  unsigned char* sb;  // this seed's state block (shared memory on the device)
   const Params* P;
   // register-cached hot state
   u64 r0, r1, r2, r3, now, hash, draws;
   u32 ev_pop, ev_fire, heap_len, rq_len, status, peak_timers;
+  // request (state machine -> engine) and result (engine -> state machine) registers
+  u64 xa, xb, ret64, rw;
+  u32 ya, yb, yc, yd, rv0, rv1, rfrom;
+  int ret;
   // optional full trace (single-seed replay)
   msim_trace_rec* tr;
   u32 tr_cap, tr_n;
 
   // ---------------- accessors ----------------
-  MSIM_HD u64& q(int off, int i = 0) const { return reinterpret_cast<u64*>(base)[(off + i) * S + s]; }
-  MSIM_HD u32& w(int off, int i = 0) const {
-    return reinterpret_cast<u32*>(base + (size_t)L::W_BASE * S)[(off + i) * S + s];
-  }
-  MSIM_HD u8& b(int off, int i = 0) const { return (base + (size_t)L::B_BASE * S)[(off + i) * S + s]; }
+  MSIM_HD u64& q(int off, int i = 0) const { return reinterpret_cast<u64*>(sb)[off + i]; }
+  MSIM_HD u32& w(int off, int i = 0) const { return reinterpret_cast<u32*>(sb + L::W_BASE)[off + i]; }
+  MSIM_HD u8& b(int off, int i = 0) const { return (sb + L::B_BASE)[off + i]; }
 
-  // task fields
   MSIM_HD u8& t_kind(int t) const { return b(L::B_T_KIND, t); }
   MSIM_HD u8& t_pc(int t) const { return b(L::B_T_PC, t); }
   MSIM_HD u8& t_flags(int t) const { return b(L::B_T_FLAGS, t); }
   MSIM_HD u8& t_node(int t) const { return b(L::B_T_NODE, t); }
   MSIM_HD u8& t_epoch(int t) const { return b(L::B_T_EPOCH, t); }
-  MSIM_HD u8& t_sub(int t) const { return b(L::B_T_SUB, t); }
+  MSIM_HD u8& t_wait(int t) const { return b(L::B_T_WAIT, t); }
   MSIM_HD u8& t_rx(int t) const { return b(L::B_T_RX, t); }
   MSIM_HD u8& t_sock(int t) const { return b(L::B_T_SOCK, t); }
   MSIM_HD u8& t_sockgen(int t) const { return b(L::B_T_SOCKGEN, t); }
@@ -141,10 +187,8 @@ struct Engine {
   MSIM_HD u64& t_dl0(int t) const { return q(L::Q_T_DL0, t); }
   MSIM_HD u64& t_dl1(int t) const { return q(L::Q_T_DL1, t); }
   MSIM_HD u32 t_gen(int t) const { return t_spawn(t) & 0xfffffu; }
-  // nodes
   MSIM_HD u8& n_flags(int n) const { return b(L::B_N_FLAGS, n); }
   MSIM_HD u8& n_epoch(int n) const { return b(L::B_N_EPOCH, n); }
-  // workload storage
   MSIM_HD u64& wl_q(int f, int n) const { return q(L::Q_WL, f * C::NNODE + n); }
   MSIM_HD u32& wl_w(int f, int n) const { return w(L::W_WL, f * C::NNODE + n); }
   MSIM_HD u32& wl_s(int i) const { return w(L::W_WLS, i); }
@@ -195,7 +239,7 @@ struct Engine {
     return result;
   }
   /// Rng::gen_range(lo..hi) for u64/usize: UniformInt::sample_single (widening multiply + zone)
-  MSIM_FN u64 gen_range_u64(u64 lo, u64 hi) {
+  MSIM_HD u64 gen_range_u64(u64 lo, u64 hi) {
     u64 range = hi - lo;
     u64 zone = (range << clz64(range)) - 1;
     for (;;) {
@@ -204,8 +248,22 @@ struct Engine {
       if (l <= zone) return lo + mulhi64(v, range);
     }
   }
+  /// the same sampler for ranges that fit 32 bits (ready-queue index, 50..100 ns, 0..5 us): the
+  /// 64 x 64 widening multiply degenerates to two 32 x 32 products
+  MSIM_HD u32 gen_range_small(u32 lo, u32 hi) {
+    u32 range = hi - lo;
+    u64 zone = ((u64)range << (32 + clz32(range))) - 1;
+    for (;;) {
+      u64 v = next_u64();
+      u64 p_lo = (u64)(u32)v * range;
+      u64 p_hi = (v >> 32) * range;
+      u64 l = p_lo + (p_hi << 32);            // low 64 bits of v * range
+      u64 h = (p_hi + (p_lo >> 32)) >> 32;    // high 64 bits (fits 32)
+      if (l <= zone) return lo + (u32)h;
+    }
+  }
   /// Uniform::<u64>::new_inclusive(lo, hi).sample — modulo zone (UniformDuration Medium)
-  MSIM_FN u64 sample_inclusive_u64(u64 lo, u64 hi) {
+  MSIM_HD u64 sample_inclusive_u64(u64 lo, u64 hi) {
     u64 range = hi - lo + 1;
     u64 zone = ~0ull - ((~0ull - range + 1) % range);
     for (;;) {
@@ -215,7 +273,7 @@ struct Engine {
     }
   }
   /// gen_range(config.send_latency): sampler pre-digested on the host (Params.lat_*)
-  MSIM_FN u64 sample_latency() {
+  MSIM_HD u64 sample_latency() {
     if (P->lat_mode == 0) {  // Small: Uniform<u32> over sub-second nanos; next_u32 = next_u64 >> 32
       u32 range = (u32)P->lat_range, zone = (u32)P->lat_zone;
       for (;;) {
@@ -237,7 +295,7 @@ struct Engine {
   MSIM_HD u64& h_dl(int i) const { return q(L::Q_HEAP_DL, i); }
   MSIM_HD u32& h_pl(int i) const { return w(L::W_HEAP_PL, i); }
   /// Timer::add = BinaryHeap::push: append, sift_up while STRICTLY earlier than the parent
-  MSIM_FN void timer_push(u64 dl, u32 pl) {
+  MSIM_HD void timer_push(u64 dl, u32 pl) {
     u32 pos = heap_len;
     if (pos >= (u32)C::TQ) {
       fail_cap(MSIM_CAP_TIMERS);
@@ -258,7 +316,7 @@ struct Engine {
   }
   /// BinaryHeap::pop: move the last element to the root, sift_down_to_bottom (on equal
   /// deadlines the RIGHT child is promoted), then sift_up from the leaf.
-  MSIM_FN void timer_pop(u64& dl, u32& pl) {
+  MSIM_HD void timer_pop(u64& dl, u32& pl) {
     dl = h_dl(0);
     pl = h_pl(0);
     u32 end = --heap_len;
@@ -314,21 +372,10 @@ struct Engine {
       }
     }
   }
-  /// TimeHandle::advance (time/mod.rs:103-106) — also the clock-jump fault `time::advance`
-  MSIM_HD void time_advance(u64 dur) {
-    now += dur;
-    expire(now);
-  }
   /// sleep()/sleep_until(): deadline = max(deadline, now + 1 ms)  (time/mod.rs:111-124)
   MSIM_HD u64 sleep_deadline(u64 deadline) const {
     u64 m = now + NS_PER_MS;
     return deadline > m ? deadline : m;
-  }
-  /// Sleep::poll (time/sleep.rs:47-54): EVERY pending poll registers another timer
-  MSIM_HD bool sleep_poll(int t, u64 deadline) {
-    if (now >= deadline) return true;
-    timer_push(deadline, timer_payload(TK_WAKE, t, t_gen(t)));
-    return false;
   }
 
   // ---------------- tasks (async-task state machine) ----------------
@@ -340,11 +387,11 @@ struct Engine {
     b(L::B_RQ, rq_len++) = (u8)t;
   }
   /// Waker::wake for the task that lived in slot `t` with generation `gen`
-  MSIM_FN void wake(int t, u32 gen) {
-    if ((t_spawn(t) & 0xfffffu) != gen || t_spawn(t) == NONE32) return;
+  MSIM_HD void wake(int t, u32 gen) {
+    u32 sp = t_spawn(t);
+    if ((sp & 0xfffffu) != gen || sp == NONE32) return;
     u8 f = t_flags(t);
-    if (f & (TF_COMPLETED | TF_CLOSED)) return;
-    if (f & TF_SCHEDULED) return;
+    if (f & (TF_COMPLETED | TF_CLOSED | TF_SCHEDULED)) return;
     t_flags(t) = f | TF_SCHEDULED;
     if (!(f & TF_RUNNING)) rq_push(t);
   }
@@ -364,12 +411,25 @@ struct Engine {
       q(L::Q_TFREE, t >> 6) |= 1ull << (t & 63);
     }
   }
-  /// Dropping the task's future (and the TaskInfo inside it)
+  /// Dropping the task's future (and the TaskInfo inside it): whatever the suspended future holds
+  /// goes with it — oneshot receiver (registered or filled), prepared message, Endpoint clone.
   MSIM_HD void drop_future(int t) {
     u8 f = t_flags(t);
     if (f & TF_ALIVE) {
-      WL::on_drop(*this, t);
-      t_flags(t) = t_flags(t) & ~TF_ALIVE;
+      u8 st = t_wait(t) & 0x0f;
+      if (st == W_RECV_RX || st == W_CALL_RX) mbox_unregister(t);
+      if (t_rx(t) != NONE8) {
+        msg_free(t_rx(t));
+        t_rx(t) = NONE8;
+      }
+      if (t_msg(t) != NONE8) {
+        msg_free(t_msg(t));
+        t_msg(t) = NONE8;
+      }
+      if (st == W_JOIN) join_detach((int)t_c(t));
+      sock_unref(t);
+      t_wait(t) = W_NONE;
+      t_flags(t) = f & ~TF_ALIVE;
       w(L::W_LIVE_TASKS)--;
     }
   }
@@ -383,8 +443,9 @@ struct Engine {
     maybe_free(t);
   }
   /// Spawner::spawn_inner (task/mod.rs:627-654): returns the slot or -1
-  MSIM_FN int spawn(u32 kind, u32 node, u8 extra_flags = 0) {
+  MSIM_HD int spawn(u32 kind, u32 node, u8 extra_flags) {
     int t = -1;
+MSIM_NOUNROLL
     for (int wd = 0; wd < (C::NT + 63) / 64; wd++) {
       u64 m = q(L::Q_TFREE, wd);
       if (m) {
@@ -402,7 +463,7 @@ struct Engine {
     w(L::W_NEXT_SPAWN) = idx + 1;
     t_kind(t) = (u8)kind;
     t_pc(t) = 0;
-    t_sub(t) = 0;
+    t_wait(t) = W_NONE;
     t_flags(t) = TF_SCHEDULED | TF_ALIVE | extra_flags;
     t_node(t) = (u8)node;
     t_epoch(t) = n_epoch(node);
@@ -416,7 +477,7 @@ struct Engine {
     rq_push(t);
     return t;
   }
-  /// JoinHandle::poll (async_task::Task::poll_task).  1 = Ok (output = t_a(target)), 2 = cancelled
+  /// JoinHandle::poll (async_task::Task::poll_task).  0 pending, 1 Ok (output = t_a(target)), 2 cancelled
   MSIM_HD int join_poll(int self, int target) {
     u8 f = t_flags(target);
     if (f & TF_CLOSED) {
@@ -425,7 +486,6 @@ struct Engine {
         return 0;
       }
       t_flags(target) = f & ~TF_JOINABLE;
-      maybe_free(target);
       return 2;
     }
     if (!(f & TF_COMPLETED)) {
@@ -433,12 +493,12 @@ struct Engine {
       return 0;
     }
     t_flags(target) = (f | TF_CLOSED) & ~TF_JOINABLE;
-    return 1;  // caller reads t_a(target) then calls join_release(target)
+    return 1;  // caller reads t_a(target) then maybe_free(target)
   }
-  MSIM_HD void join_release(int target) { maybe_free(target); }
   /// Dropping a JoinHandle = detach
   MSIM_HD void join_detach(int target) {
     t_flags(target) = t_flags(target) & ~TF_JOINABLE;
+    t_aw(target) = NONE32;
     maybe_free(target);
   }
   /// AbortHandle::abort (task/join.rs:158-163)
@@ -454,14 +514,14 @@ struct Engine {
     int n = t_node(t);
     return t_epoch(t) != n_epoch(n) || (n_flags(n) & NF_KILLED);
   }
-  /// NodeInfo::kill for the CURRENT info of node n: wake every live task in spawn order
-  MSIM_FN void info_kill(int n, u8 epoch) {
-    // spawn order = ascending spawn index among this incarnation's live tasks
+  /// NodeInfo::kill for the incarnation (n, epoch): wake every live task in spawn order
+  MSIM_HD void info_kill(int n, u8 epoch) {
     u32 last = 0;
     bool first = true;
     for (;;) {
       u32 best = NONE32;
       int bt = -1;
+MSIM_NOUNROLL
       for (int t = 0; t < C::NT; t++) {
         u32 sp = t_spawn(t);
         if (sp == NONE32 || !(t_flags(t) & TF_ALIVE)) continue;
@@ -478,8 +538,9 @@ struct Engine {
       first = false;
     }
   }
-  MSIM_FN void drop_parked(int n) {
+  MSIM_HD void drop_parked(int n) {
     u32 len = w(L::W_PK_LEN), keep = 0;
+MSIM_NOUNROLL
     for (u32 i = 0; i < len; i++) {
       int t = b(L::B_PK, i);
       if (t_node(t) == n) {
@@ -490,7 +551,7 @@ struct Engine {
     }
     w(L::W_PK_LEN) = keep;
   }
-  MSIM_FN void kill(int n) {
+  MSIM_HD void kill(int n) {
     drop_parked(n);
     n_flags(n) = n_flags(n) | NF_KILLED;
     info_kill(n, n_epoch(n));
@@ -501,17 +562,19 @@ struct Engine {
     if (n_epoch(n) == epoch) n_flags(n) = n_flags(n) | NF_KILLED;
     info_kill(n, epoch);
   }
-  MSIM_FN void restart(int n) {
+  MSIM_HD void restart(int n) {
     drop_parked(n);
     info_kill(n, n_epoch(n));  // old_info.kill()
     n_epoch(n) = n_epoch(n) + 1;
     n_flags(n) = n_flags(n) & ~(NF_KILLED | NF_PAUSED);
-    WL::node_init(*this, n);
+    int kind = WL::init_kind(n);
+    if (kind >= 0) spawn((u32)kind, n, TF_INIT);
   }
   MSIM_HD void pause(int n) { n_flags(n) = n_flags(n) | NF_PAUSED; }
   MSIM_HD void resume(int n) {
     n_flags(n) = n_flags(n) & ~NF_PAUSED;
     u32 len = w(L::W_PK_LEN), keep = 0;
+MSIM_NOUNROLL
     for (u32 i = 0; i < len; i++) {
       int t = b(L::B_PK, i);
       if (t_node(t) == n)
@@ -522,19 +585,6 @@ struct Engine {
     w(L::W_PK_LEN) = keep;
   }
   MSIM_HD bool is_exit(int n) const { return n_flags(n) & NF_KILLED; }
-  /// Handle::create_node + NodeBuilder::build (runtime/mod.rs:405-418): ids start at 1
-  MSIM_HD int create_node(bool has_ip, bool with_init, bool restart_on_panic = false) {
-    u32 n = w(L::W_NEXT_NODE);
-    if (n >= (u32)C::NNODE) {
-      fail_cap(MSIM_CAP_TASKS);
-      return 0;
-    }
-    w(L::W_NEXT_NODE) = n + 1;
-    n_flags(n) = NF_EXISTS | (has_ip ? NF_HAS_IP : 0) | (restart_on_panic ? NF_RESTART_ON_PANIC : 0);
-    n_epoch(n) = 0;
-    if (with_init) WL::node_init(*this, n);
-    return (int)n;
-  }
 
   // ---------------- network (net/network.rs, net/mod.rs, net/endpoint.rs) ----------------
   MSIM_HD u8& sk_state(int k) const { return b(L::B_SK_STATE, k); }
@@ -552,20 +602,22 @@ struct Engine {
   }
   MSIM_HD void msg_free(int m) { q(L::Q_MFREE) |= 1ull << m; }
   MSIM_HD int sock_find(int node, u32 ipk, u32 port) const {
+MSIM_NOUNROLL
     for (int k = 0; k < C::NSOCK; k++)
       if (sk_state(k) && b(L::B_SK_NODE, k) == node && b(L::B_SK_IPK, k) == ipk && sk_port(k) == port) return k;
     return -1;
   }
   /// Network::bind (network.rs:206-251).  >= 0 socket slot; -1 AddrNotAvailable; -2 AddrInUse
-  MSIM_FN int sock_bind(int node, u32 addr) {
+  MSIM_HD int sock_bind(int node, u32 addr) {
     u32 ipk = addr_ipk(addr), port = addr_port(addr);
     if (ipk == IPK_NODE && (int)addr_node(addr) != node) return -1;
     if (port == 0) {
       port = 1;
       while (port <= 0xffff && sock_find(node, ipk, port) >= 0) port++;
       if (port > 0xffff) return -2;
+    } else if (sock_find(node, ipk, port) >= 0) {
+      return -2;
     }
-    if (sock_find(node, ipk, port) >= 0) return -2;
     int k = 0;
     while (k < C::NSOCK && sk_state(k)) k++;
     if (k >= C::NSOCK) {
@@ -584,6 +636,7 @@ struct Engine {
   }
   MSIM_HD void sock_release_storage(int k) {
     u32 ml = b(L::B_SK_MBLEN, k);
+MSIM_NOUNROLL
     for (u32 i = 0; i < ml; i++) msg_free(b(L::B_MB, k * C::NMBOX + i));
     b(L::B_SK_MBLEN, k) = 0;
     b(L::B_SK_REGLEN, k) = 0;
@@ -591,6 +644,7 @@ struct Engine {
     w(L::W_SK_PORTGEN, k) = (w(L::W_SK_PORTGEN, k) & 0xffff0000u) + 0x10000u;  // gen++ : stale refs miss
   }
   MSIM_HD void reset_node_sockets(int n) {
+MSIM_NOUNROLL
     for (int k = 0; k < C::NSOCK; k++)
       if (sk_state(k) && b(L::B_SK_NODE, k) == n) sock_release_storage(k);
   }
@@ -630,46 +684,37 @@ struct Engine {
   MSIM_HD void unclog_link(int sN, int d) { w(L::W_CLOG_LINK, sN) &= ~(1u << d); }
 
   /// NetSim::rand_delay (net/mod.rs:287-295): returns the Sleep deadline (always >= now + 1 ms)
-  MSIM_FN u64 rand_delay_deadline() {
-    u64 delay = gen_range_u64(0, 5) * 1000ull;
+  MSIM_HD u64 rand_delay_deadline() {
+    u64 delay = (u64)gen_range_small(0, 5) * 1000ull;
     if (P->buggify) {
-      if (next_u64() < P->buggify_p10_int) delay = gen_range_u64(1, 5) * NS_PER_SEC;
+      if (next_u64() < P->buggify_p10_int) delay = (u64)gen_range_small(1, 5) * NS_PER_SEC;
     }
     return sleep_deadline(now + delay);
   }
   /// The part of NetSim::send after rand_delay (net/mod.rs:304-332) + Network::try_send
   /// (network.rs:296-313).  `m` is a prepared message slot (tag, w, v0, v1); consumed.
-  MSIM_FN void net_send(int src_node, u32 src_port, u32 dst, int m) {
+  MSIM_HD void net_send(int src_node, u32 src_port, u32 dst, int m) {
     // resolve_dest_node (network.rs:273-291)
-    int dst_node;
-    u32 ipk = addr_ipk(dst);
-    if (ipk == IPK_LOOPBACK || (ipk != IPK_NODE ? sock_find(src_node, ipk, addr_port(dst)) >= 0
-                                                : ((int)addr_node(dst) == src_node &&
-                                                   sock_find(src_node, IPK_NODE, addr_port(dst)) >= 0))) {
+    int dst_node = -1;
+    u32 ipk = addr_ipk(dst), dport = addr_port(dst);
+    bool own = (ipk != IPK_NODE || (int)addr_node(dst) == src_node) && sock_find(src_node, ipk, dport) >= 0;
+    if (ipk == IPK_LOOPBACK || own) {
       dst_node = src_node;
-    } else if (!(n_flags(src_node) & NF_HAS_IP)) {
-      msg_free(m);
-      return;  // "ip not set": before any draw
-    } else if (ipk == IPK_NODE && addr_node(dst) < (u32)C::NNODE && (n_flags(addr_node(dst)) & NF_HAS_IP)) {
+    } else if ((n_flags(src_node) & NF_HAS_IP) && ipk == IPK_NODE && addr_node(dst) < (u32)C::NNODE &&
+               (n_flags(addr_node(dst)) & NF_HAS_IP)) {
       dst_node = (int)addr_node(dst);
-    } else {
-      msg_free(m);
-      return;  // destination not found
     }
-    // test_link (network.rs:261-270): `clogged || gen_bool(loss)` — no draw when clogged
-    if (link_clogged(src_node, dst_node)) {
-      msg_free(m);
-      return;
-    }
-    if (P->loss_always || next_u64() < P->loss_p_int) {
+    // "ip not set" / destination not found: before any draw.  test_link (network.rs:261-270):
+    // `clogged || gen_bool(loss)` — no draw when clogged
+    if (dst_node < 0 || link_clogged(src_node, dst_node) || P->loss_always || next_u64() < P->loss_p_int) {
       msg_free(m);
       return;
     }
     u32 serial = ++w(L::W_MSG_COUNT);
     u64 latency = sample_latency();
     // socket lookup AFTER the draws: exact address, then (UNSPECIFIED, port)
-    int k = sock_find(dst_node, ipk, addr_port(dst));
-    if (k < 0) k = sock_find(dst_node, IPK_UNSPEC, addr_port(dst));
+    int k = sock_find(dst_node, ipk, dport);
+    if (k < 0 && ipk != IPK_UNSPEC) k = sock_find(dst_node, IPK_UNSPEC, dport);
     if (k < 0) {
       msg_free(m);
       return;
@@ -679,10 +724,10 @@ struct Engine {
     w(L::W_M_SERIAL, m) = serial & 0xffffffu;
     timer_push(now + latency, timer_payload(TK_DELIVER, m, 0));
   }
-  /// Timer callback of NetSim::send → EndpointSocket::deliver → Mailbox::deliver
+  /// Timer callback of NetSim::send -> EndpointSocket::deliver -> Mailbox::deliver
   /// (endpoint.rs:310-351).  The target socket OBJECT was captured at send time: if it has
   /// been closed/reset since, the message lands in a mailbox nobody can read (dropped here).
-  MSIM_FN void deliver(int m) {
+  MSIM_HD void deliver(int m) {
     u32 d = w(L::W_M_DST, m);
     int k = d >> 16;
     if (!sk_state(k) || (sk_gen(k) & 0xffff) != (d & 0xffff)) {
@@ -691,11 +736,11 @@ struct Engine {
     }
     u64 tag = q(L::Q_M_TAG, m);
     u32 rl = b(L::B_SK_REGLEN, k);
+MSIM_NOUNROLL
     for (u32 i = 0; i < rl; i++) {
       if (q(L::Q_RG_TAG, k * C::NREG + i) == tag) {
         u32 waiter = w(L::W_RG_WAITER, k * C::NREG + i);
-        // swap_remove(i)
-        rl--;
+        rl--;  // swap_remove(i)
         q(L::Q_RG_TAG, k * C::NREG + i) = q(L::Q_RG_TAG, k * C::NREG + rl);
         w(L::W_RG_WAITER, k * C::NREG + i) = w(L::W_RG_WAITER, k * C::NREG + rl);
         b(L::B_SK_REGLEN, k) = (u8)rl;
@@ -718,8 +763,9 @@ struct Engine {
   }
   /// Mailbox::recv(tag) (endpoint.rs:353-362) on the endpoint the task holds: either fills the
   /// task's oneshot at once (t_rx) or registers (tag, oneshot sender)
-  MSIM_FN void mbox_recv(int t, int k, u64 tag) {
+  MSIM_HD void mbox_recv(int t, int k, u64 tag) {
     u32 ml = b(L::B_SK_MBLEN, k);
+MSIM_NOUNROLL
     for (u32 i = 0; i < ml; i++) {
       int m = b(L::B_MB, k * C::NMBOX + i);
       if (q(L::Q_M_TAG, m) == tag) {
@@ -743,12 +789,13 @@ struct Engine {
   /// Dropping a oneshot::Receiver that is still registered.  The reference leaves the dead
   /// sender in `registered` until a message with its tag arrives; removing it eagerly is
   /// unobservable as long as no two LIVE registrations of a mailbox share a tag (the shipped
-  /// workloads guarantee it; the oracle checks it) — DESIGN.md "eager registration GC".
-  MSIM_FN void mbox_unregister(int t) {
+  /// workloads guarantee it) — DESIGN.md "eager registration GC".
+  MSIM_HD void mbox_unregister(int t) {
     int k = t_sock(t);
     if (k == NONE8 || !sk_state(k) || (u8)sk_gen(k) != t_sockgen(t)) return;
     u32 me = ((u32)t << 20) | t_gen(t);
     u32 rl = b(L::B_SK_REGLEN, k);
+MSIM_NOUNROLL
     for (u32 i = 0; i < rl; i++)
       if (w(L::W_RG_WAITER, k * C::NREG + i) == me) {
         rl--;
@@ -758,37 +805,42 @@ struct Engine {
         return;
       }
   }
-  /// Generic cleanup of what a future may hold (oneshot value, prepared message, registration,
-  /// endpoint clone).  Workload on_drop hooks call this.
-  MSIM_FN void drop_task_resources(int t, bool registered) {
-    if (registered) mbox_unregister(t);
-    if (t_rx(t) != NONE8) {
-      msg_free(t_rx(t));
-      t_rx(t) = NONE8;
-    }
-    if (t_msg(t) != NONE8) {
-      msg_free(t_msg(t));
-      t_msg(t) = NONE8;
-    }
-    sock_unref(t);
+  /// take the message out of the task's oneshot into the result registers
+  MSIM_HD void unpack_rx(int t) {
+    int m = t_rx(t);
+    rv0 = w(L::W_M_V0, m);
+    rv1 = w(L::W_M_V1, m);
+    rfrom = w(L::W_M_FROM, m);
+    rw = q(L::Q_M_W, m);
+    msg_free(m);
+    t_rx(t) = NONE8;
+  }
+  MSIM_HD int msg_prepare(u64 tag, u64 wv, u32 v0, u32 v1, u32 dst) {
+    int m = msg_alloc();
+    if (m < 0) return -1;
+    q(L::Q_M_TAG, m) = tag;
+    q(L::Q_M_W, m) = wv;
+    w(L::W_M_V0, m) = v0;
+    w(L::W_M_V1, m) = v1;
+    w(L::W_M_FROM, m) = dst;  // the destination rides in the FROM field until the send
+    return m;
   }
 
   // ---------------- lifecycle ----------------
   /// Runtime::with_seed_and_config (runtime/mod.rs:53-69) for this seed + block_on's spawn of main
-  MSIM_FN void init(u64 seed) {
-    // zero this seed's columns
-    for (int i = 0; i < L::NQ; i++) q(i) = 0;
-    for (int i = 0; i < L::NW; i++) w(i) = 0;
-    for (int i = 0; i < L::NB; i++) b(i) = 0;
+  MSIM_HD void init(u64 seed) {
+    u64* z = reinterpret_cast<u64*>(sb);
+MSIM_NOUNROLL
+    for (int i = 0; i < L::BYTES / 8; i++) z[i] = 0;
     // seed_from_u64: SplitMix64 x4
     u64 x = seed;
     u64 st[4];
     for (int i = 0; i < 4; i++) {
       x += 0x9e3779b97f4a7c15ull;
-      u64 z = x;
-      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-      st[i] = z ^ (z >> 31);
+      u64 zz = x;
+      zz = (zz ^ (zz >> 30)) * 0xbf58476d1ce4e5b9ull;
+      zz = (zz ^ (zz >> 27)) * 0x94d049bb133111ebull;
+      st[i] = zz ^ (zz >> 31);
     }
     r0 = st[0], r1 = st[1], r2 = st[2], r3 = st[3];
     now = 0;
@@ -796,6 +848,7 @@ struct Engine {
     draws = 0;
     ev_pop = ev_fire = heap_len = rq_len = peak_timers = 0;
     status = MSIM_ST_RUNNING;
+MSIM_NOUNROLL
     for (int t = 0; t < C::NT; t++) t_spawn(t) = NONE32;
     for (int wd = 0; wd < (C::NT + 63) / 64; wd++) {
       int n = C::NT - wd * 64;
@@ -810,7 +863,7 @@ struct Engine {
     int m = spawn(WL::MAIN_KIND, 0, TF_JOINABLE);
     w(L::W_MAIN_SLOT) = (u32)m;
   }
-  /// registers ← state block
+  /// registers <- state block
   MSIM_HD void load() {
     r0 = q(L::Q_RNG, 0), r1 = q(L::Q_RNG, 1), r2 = q(L::Q_RNG, 2), r3 = q(L::Q_RNG, 3);
     now = q(L::Q_NOW);
@@ -821,7 +874,7 @@ struct Engine {
     status = w(L::W_STATUS);
     peak_timers = w(L::W_PEAK_TIMERS);
   }
-  /// registers → state block
+  /// registers -> state block
   MSIM_HD void store() {
     q(L::Q_RNG, 0) = r0, q(L::Q_RNG, 1) = r1, q(L::Q_RNG, 2) = r2, q(L::Q_RNG, 3) = r3;
     q(L::Q_NOW) = now;
@@ -845,6 +898,196 @@ struct Engine {
     r.peak_tasks = w(L::W_PEAK_TASKS);
   }
 
+  /// The poll of one task: resume whatever primitive its future is suspended in, then run the
+  /// state machine, executing the primitives it requests, until it is Pending / Ready / panics.
+  /// Each primitive reproduces the poll-by-poll behaviour of SURVEY.md §3.4 (timers pushed per
+  /// pending poll, draws in program order).
+  MSIM_HD int poll_task(int t) {
+    for (;;) {
+      if (!running()) return POLL_PENDING;
+      u8 wt = t_wait(t);
+      if (wt != W_NONE) {
+        u8 st = wt & 0x0f;
+        bool pend = false;
+        if (wt & WF_RD) {  // NetSim::rand_delay: draw, then `sleep(delay).await`
+          t_dl0(t) = rand_delay_deadline();
+          wt = (wt & ~WF_RD) | WF_SLEEP;
+        }
+        if (wt & WF_SLEEP) {  // Sleep::poll (time/sleep.rs:47-54): EVERY pending poll registers another timer
+          u64 dl = t_dl0(t);
+          if (now < dl) {
+            timer_push(dl, timer_payload(TK_WAKE, t, t_gen(t)));
+            pend = true;
+          } else {
+            wt &= ~WF_SLEEP;
+          }
+        }
+        if (!pend) {
+          int k = t_sock(t);
+          switch (st) {
+            case W_SLEEP:
+              wt = W_NONE;
+              break;
+            case W_BIND:  // BindGuard::bind after rand_delay (net/mod.rs:446-480)
+              ret = sock_bind(t_node(t), (u32)t_dl1(t));
+              if (ret >= 0) sock_adopt(t, ret);
+              wt = W_NONE;
+              break;
+            case W_SEND: {  // NetSim::send after rand_delay
+              int m = t_msg(t);
+              t_msg(t) = NONE8;
+              net_send(b(L::B_SK_NODE, k), sk_port(k), w(L::W_M_FROM, m), m);
+              wt = W_NONE;
+              break;
+            }
+            case W_CALL_SEND: {  // call: send_to_raw done -> recv_from_raw(rsp_tag): mailbox.recv
+              int m = t_msg(t);
+              t_msg(t) = NONE8;
+              u64 rsp_tag = q(L::Q_M_W, m);
+              net_send(b(L::B_SK_NODE, k), sk_port(k), w(L::W_M_FROM, m), m);
+              mbox_recv(t, k, rsp_tag);
+              wt = st = W_CALL_RX;
+            }
+            // fallthrough
+            case W_CALL_RX:
+            case W_RECV_RX:  // oneshot::Receiver await; then rand_delay AFTER the receipt
+              if (t_rx(t) == NONE8) {
+                pend = true;
+              } else {
+                t_wait(t) = (st == W_RECV_RX ? W_RECV_DELAY : W_CALL_DELAY) | WF_RD;
+                continue;
+              }
+              break;
+            case W_RECV_DELAY:
+              unpack_rx(t);
+              wt = W_NONE;
+              break;
+            case W_CALL_DELAY:
+              unpack_rx(t);
+              wt = W_NONE;
+              ret = CALL_OK;
+              if (rfrom != t_c(t)) return panic(31);  // assert_eq!(from, dst) (rpc.rs:125)
+              break;
+            case W_JOIN: {
+              int target = (int)t_c(t);
+              int r = join_poll(t, target);
+              if (r == 0) {
+                pend = true;
+              } else {
+                ret = r;
+                rv0 = t_a(target);
+                maybe_free(target);
+                wt = W_NONE;
+              }
+              break;
+            }
+          }
+        }
+        t_wait(t) = wt;
+        if (pend) {
+          if (st < W_CALL_SEND || st > W_CALL_DELAY) return POLL_PENDING;
+          // timeout(): select_biased polls the call first, then the timeout's Sleep (time/mod.rs:128-140)
+          u64 dl1 = t_dl1(t);
+          if (now < dl1) {
+            timer_push(dl1, timer_payload(TK_WAKE, t, t_gen(t)));
+            return POLL_PENDING;
+          }
+          // Elapsed: the call future is dropped where it stands
+          if (st == W_CALL_RX) mbox_unregister(t);
+          if (t_rx(t) != NONE8) {
+            msg_free(t_rx(t));
+            t_rx(t) = NONE8;
+          }
+          if (t_msg(t) != NONE8) {
+            msg_free(t_msg(t));
+            t_msg(t) = NONE8;
+          }
+          t_wait(t) = W_NONE;
+          ret = CALL_TIMEOUT;
+        }
+      }
+      // ---- run the state machine until its next request ----
+      int rq = WL::fsm(*this, t);
+      switch (rq) {
+        case RQ_PENDING:
+          return POLL_PENDING;
+        case RQ_READY:
+          return POLL_READY;
+        case RQ_PANIC:
+          return panic(ya);
+        case RQ_SLEEP_FOR:
+          xa += now;
+          // fallthrough
+        case RQ_SLEEP_UNTIL:
+          t_dl0(t) = sleep_deadline(xa);
+          t_wait(t) = W_SLEEP | WF_SLEEP;
+          break;
+        case RQ_RAND_DELAY:
+          t_wait(t) = W_SLEEP | WF_RD;
+          break;
+        case RQ_BIND:
+          t_dl1(t) = ya;
+          t_wait(t) = W_BIND | WF_RD;
+          break;
+        case RQ_CALL:  // call_timeout: the timeout's Sleep is created first; call: rsp_tag = random::<u64>()
+          t_dl1(t) = sleep_deadline(now + xb);
+          t_c(t) = ya;
+          xb = next_u64();
+          yd = W_CALL_SEND | WF_RD;
+          goto prepare;
+        case RQ_SEND:
+          yd = W_SEND | WF_RD;
+        prepare : {
+          int m = msg_prepare(xa, xb, yb, yc, ya);
+          if (m < 0) return POLL_PENDING;
+          t_msg(t) = (u8)m;
+          t_wait(t) = (u8)yd;
+          break;
+        }
+        case RQ_RECV:
+          mbox_recv(t, t_sock(t), xa);
+          t_wait(t) = W_RECV_RX;
+          break;
+        case RQ_CREATE_NODE: {  // Handle::create_node + NodeBuilder::build (runtime/mod.rs:405-418): ids start at 1
+          u32 n = w(L::W_NEXT_NODE);
+          if (n >= (u32)C::NNODE) {
+            fail_cap(MSIM_CAP_TASKS);
+            return POLL_PENDING;
+          }
+          w(L::W_NEXT_NODE) = n + 1;
+          n_flags(n) = NF_EXISTS | ((ya & NODE_IP) ? NF_HAS_IP : 0) | ((ya & NODE_RESTART_ON_PANIC) ? NF_RESTART_ON_PANIC : 0);
+          n_epoch(n) = 0;
+          int kind = (ya & NODE_INIT) ? WL::init_kind((int)n) : -1;
+          if (kind >= 0) spawn((u32)kind, n, TF_INIT);  // init(&handle) runs at build time
+          ret = (int)n;
+          break;
+        }
+        case RQ_SPAWN: {
+          int c = spawn(ya & 0xff, yb, (ya & SPAWN_JOINABLE) ? TF_JOINABLE : 0);
+          ret = c;
+          if (c < 0) return POLL_PENDING;
+          t_a(c) = yc;
+          t_b(c) = yd;
+          t_c(c) = (u32)xa;
+          t_dl1(c) = xb;
+          if (ya & SPAWN_EP) sock_ref(c, t_sock(t));
+          break;
+        }
+        case RQ_GEN_RANGE:
+          ret64 = gen_range_u64(xa, xb);
+          break;
+        case RQ_JOIN:
+          t_c(t) = ya;
+          t_wait(t) = W_JOIN;
+          break;
+        case RQ_ADVANCE:  // time::advance (time/mod.rs:103-106,195-198): fires due timers inside this poll
+          now += xa;
+          expire(now);
+          break;
+      }
+    }
+  }
+
   /// Runnable::run (async-task) + the panic policy of run_all_ready (task/mod.rs:285-317)
   MSIM_HD void run_task(int t) {
     u8 f = t_flags(t);
@@ -856,7 +1099,7 @@ struct Engine {
       return;
     }
     t_flags(t) = (f & ~TF_SCHEDULED) | TF_RUNNING;
-    int r = WL::poll(*this, t);
+    int r = poll_task(t);
     if (r == POLL_READY) {
       if (t_flags(t) & TF_INIT) node_exit(t_node(t), t_epoch(t));  // `future.await; h.exit()`
       drop_future(t);
@@ -869,7 +1112,7 @@ struct Engine {
       drop_future(t);
       notify_awaiter(t);
       int n = t_node(t);
-      bool rop = (n_flags(n) & NF_RESTART_ON_PANIC) && t_epoch(t) == n_epoch(n);
+      bool rop = (n_flags(n) & NF_RESTART_ON_PANIC) != 0;
       maybe_free(t);
       if (rop) {
         u64 delay = sample_inclusive_u64(NS_PER_SEC, 10 * NS_PER_SEC - 1);  // gen_range(1s..10s): Medium
@@ -900,10 +1143,11 @@ struct Engine {
   /// pop a random runnable, dispatch it and advance the clock 50-100 ns; otherwise finish, or
   /// jump to the next timer.  Returns false when the seed has stopped.
   MSIM_HD bool step() {
+    u64 limit;
     if (rq_len > 0) {
       // try_recv_random (utils/mpsc.rs:73-83)
       u32 len = rq_len;
-      u32 idx = (u32)gen_range_u64(0, len);
+      u32 idx = gen_range_small(0, len);
       int t = b(L::B_RQ, idx);
       b(L::B_RQ, idx) = b(L::B_RQ, len - 1);  // swap_remove
       rq_len = len - 1;
@@ -935,33 +1179,34 @@ struct Engine {
       else
         run_task(t);
       if (!running()) return false;
-      // advance time: 50-100ns (task/mod.rs:319-321)
-      u64 dur = gen_range_u64(50, 100);
-      time_advance(dur);
-      return running();
-    }
-    // ready Vec drained: task.is_finished()?
-    int m = (int)w(L::W_MAIN_SLOT);
-    if (t_flags(m) & (TF_COMPLETED | TF_CLOSED)) {
-      if (t_flags(m) & TF_COMPLETED) {
-        status = MSIM_ST_PASS;
-        WL::finish(*this);
-      } else {
-        fail(MSIM_ST_FAIL_ASSERT, 0xdead);  // main task cancelled
+      // advance time: 50-100ns (task/mod.rs:319-321): clock += dur, expire(clock)
+      now += gen_range_small(50, 100);
+      limit = now;
+    } else {
+      // ready Vec drained: task.is_finished()?
+      int m = (int)w(L::W_MAIN_SLOT);
+      u8 mf = t_flags(m);
+      if (mf & (TF_COMPLETED | TF_CLOSED)) {
+        if (mf & TF_COMPLETED)
+          status = MSIM_ST_PASS;
+        else
+          fail(MSIM_ST_FAIL_ASSERT, 0xdead);  // main task cancelled
+        return false;
       }
-      return false;
+      // advance_to_next_event (time/mod.rs:45-60): callbacks fire under the OLD clock
+      if (heap_len == 0) {
+        fail(MSIM_ST_FAIL_DEADLOCK, 0);
+        return false;
+      }
+      limit = h_dl(0) + 50;
     }
-    // advance_to_next_event (time/mod.rs:45-60)
-    if (heap_len == 0) {
-      fail(MSIM_ST_FAIL_DEADLOCK, 0);
-      return false;
-    }
-    u64 t_next = h_dl(0) + 50;
-    expire(t_next);
-    now = t_next;
-    if (P->time_limit_ns && now >= P->time_limit_ns) {
-      fail(MSIM_ST_FAIL_TIME_LIMIT, 0);
-      return false;
+    expire(limit);  // the one place timers fire from the event loop
+    if (now != limit) {
+      now = limit;
+      if (P->time_limit_ns && now >= P->time_limit_ns) {
+        fail(MSIM_ST_FAIL_TIME_LIMIT, 0);
+        return false;
+      }
     }
     return running();
   }

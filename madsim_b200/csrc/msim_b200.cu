@@ -1,9 +1,9 @@
 // libmsim_b200.so — CUDA kernels (sm_100a) + the C-ABI of include/msim_b200.h.
 //
 // Kernel shape (B200-first):
-//   * one CTA owns S consecutive seeds; their whole state is a columnar block
-//     `field[slot][seed]` of S * Layout::BYTES bytes that lives in SHARED MEMORY for the
-//     duration of the launch (up to 227 KB per CTA → grid sized to one CTA per SM);
+//   * one CTA owns S consecutive seeds; their whole state is S seed-major blocks of
+//     Layout::BYTES bytes that live in SHARED MEMORY for the duration of the launch (up to
+//     227 KB per CTA → grid sized to one CTA per SM);
 //   * the block is staged HBM→smem / smem→HBM with 1-D bulk async copies (TMA, UBLKCP in SASS)
 //     completed through an mbarrier — only when a run is split into bursts; a run-to-completion
 //     launch initialises the block in place from the seed and writes back 64 B per seed;
@@ -128,9 +128,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
   }
 
   E e;
-  e.base = block;
-  e.S = S;
-  e.s = col;
+  e.sb = block + (size_t)col * E::L::BYTES;  // seed-major: one base register per lane
   e.P = &a.P;
   e.tr = nullptr;
   e.tr_cap = 0;

@@ -1,8 +1,8 @@
 // MSIM_WL_PINGPONG — BASELINE config 1: 2-node ping-pong over net::Endpoint + time::sleep
 // (reference test net/endpoint.rs:550-584 `connect_send_recv`, repeated p[0] times with the
 // un-simulated tokio Barrier replaced by a 1 s sleep).  Oracle twin: oracle/workloads.hpp
-// pp_server / pp_client / wl_pingpong_main — each `case` below is one await point of that
-// async code, expanded to the poll-level behaviour of SURVEY.md §3.4.
+// pp_server / pp_client / wl_pingpong_main: every `case` is the code between two await points of
+// that async code; the awaited primitive itself is a request executed by the engine.
 #pragma once
 #include "../engine/engine.h"
 
@@ -17,175 +17,113 @@ struct WL_PingPong {
   static constexpr u32 MAIN_KIND = K_MAIN;
   static constexpr u32 PING = 0x676e6970u, PONG = 0x676e6f70u;
   static constexpr u32 SERVER_ADDR = (IPK_NODE << 24) | (1u << 16) | 1u;  // 10.0.0.1:1
+  static MSIM_HD int init_kind(int) { return -1; }
 
   template <class E>
-  static MSIM_HD int poll_main(E& e, int t) {
+  static MSIM_HD int fsm(E& e, int t) {
     using L = typename E::L;
-    switch (e.t_pc(t)) {
-      case 0: {
-        int n1 = e.create_node(true, false);
-        int n2 = e.create_node(true, false);
-        e.spawn(K_SERVER, n1);                      // node1.spawn(server) — handle dropped (detached)
-        int c = e.spawn(K_CLIENT, n2, TF_JOINABLE);  // let f = node2.spawn(client)
-        if (c < 0) return POLL_PENDING;
-        e.t_a(t) = (u32)c;
+    u32 pc = e.t_pc(t);
+    switch (e.t_kind(t) * 8 + pc) {
+      // ---- wl_pingpong_main ----
+      case K_MAIN * 8 + 0:  // node1 = create_node().ip(10.0.0.1).build()
+      case K_MAIN * 8 + 1:  // node2 = ...
+        e.t_pc(t) = pc + 1;
+        e.ya = NODE_IP;
+        return RQ_CREATE_NODE;
+      case K_MAIN * 8 + 2:  // node1.spawn(pp_server)
+        e.t_pc(t) = 3;
+        e.ya = K_SERVER, e.yb = 1, e.yc = e.yd = 0, e.xa = e.xb = 0;
+        return RQ_SPAWN;
+      case K_MAIN * 8 + 3:  // let f = node2.spawn(pp_client)
+        e.t_pc(t) = 4;
+        e.ya = K_CLIENT | SPAWN_JOINABLE, e.yb = 2, e.yc = e.yd = 0, e.xa = e.xb = 0;
+        return RQ_SPAWN;
+      case K_MAIN * 8 + 4:  // f.await
+        e.t_pc(t) = 5;
+        e.ya = (u32)e.ret;
+        return RQ_JOIN;
+      case K_MAIN * 8 + 5:
+        if (e.ret == 2) {
+          e.ya = 14;  // .unwrap() on a JoinError
+          return RQ_PANIC;
+        }
+        e.w(L::W_USER0) = e.rv0;
+        return RQ_READY;
+
+      // ---- pp_server ----
+      case K_SERVER * 8 + 0:  // Endpoint::bind(addr)
         e.t_pc(t) = 1;
-      }
-      // fallthrough
-      case 1: {
-        int target = (int)e.t_a(t);
-        int r = e.join_poll(t, target);  // f.await
-        if (r == 0) return POLL_PENDING;
-        if (r == 2) return e.panic(14);  // .unwrap() on JoinError
-        e.w(L::W_USER0) = e.t_a(target);
-        e.join_release(target);
-        return POLL_READY;
-      }
+        e.ya = SERVER_ADDR;
+        return RQ_BIND;
+      case K_SERVER * 8 + 1:
+        if (e.ret < 0) {
+          e.ya = 10;
+          return RQ_PANIC;
+        }
+        // fallthrough
+      case K_SERVER * 8 + 2:  // loop { recv_from(1)
+        e.t_pc(t) = 3;
+        e.xa = 1;
+        return RQ_RECV;
+      case K_SERVER * 8 + 3:  // send_to(from, 1, "pong") }
+        if (e.rv0 != PING) {
+          e.ya = 11;
+          return RQ_PANIC;
+        }
+        e.t_pc(t) = 2;
+        e.ya = e.rfrom, e.xa = 1, e.xb = 0, e.yb = PONG, e.yc = 0;
+        return RQ_SEND;
+
+      // ---- pp_client ----
+      case K_CLIENT * 8 + 0:  // sleep(1 s)
+        e.t_pc(t) = 1;
+        e.xa = NS_PER_SEC;
+        return RQ_SLEEP_FOR;
+      case K_CLIENT * 8 + 1:  // Endpoint::connect = bind("0.0.0.0:0")
+        e.t_pc(t) = 2;
+        e.ya = mk_addr(IPK_UNSPEC, 0, 0);
+        return RQ_BIND;
+      case K_CLIENT * 8 + 2:
+        if (e.ret < 0) {
+          e.ya = 12;
+          return RQ_PANIC;
+        }
+        e.t_a(t) = 0;  // done
+        e.t_b(t) = 0;  // r
+        // fallthrough
+      case K_CLIENT * 8 + 3:  // for r in 0..rounds { ep.send(1, "ping")
+        if ((u64)e.t_b(t) >= e.P->p[0]) return RQ_READY;  // output = t_a; the Endpoint drops with the future
+        e.t_pc(t) = 4;
+        e.ya = SERVER_ADDR, e.xa = 1, e.xb = 0, e.yb = PING, e.yc = 0;
+        return RQ_SEND;
+      case K_CLIENT * 8 + 4:  // ep.recv(1)
+        e.t_pc(t) = 5;
+        e.xa = 1;
+        return RQ_RECV;
+      case K_CLIENT * 8 + 5:
+        if (e.rfrom != SERVER_ADDR) {
+          e.ya = 15;  // "receive a message but not from the connected address"
+          return RQ_PANIC;
+        }
+        if (e.rv0 != PONG) {
+          e.ya = 13;
+          return RQ_PANIC;
+        }
+        e.t_a(t) = e.t_a(t) + 1;
+        e.t_pc(t) = 6;
+        e.xa = e.P->p[1];  // sleep(think)
+        return RQ_SLEEP_FOR;
+      case K_CLIENT * 8 + 6:
+        e.t_b(t) = e.t_b(t) + 1;
+        e.t_pc(t) = 3;
+        if ((u64)e.t_b(t) >= e.P->p[0]) return RQ_READY;
+        e.t_pc(t) = 4;
+        e.ya = SERVER_ADDR, e.xa = 1, e.xb = 0, e.yb = PING, e.yc = 0;
+        return RQ_SEND;
     }
-    return e.panic(0xbad);
+    e.ya = 0xbad;
+    return RQ_PANIC;
   }
-
-  template <class E>
-  static MSIM_HD int poll_server(E& e, int t) {
-    using L = typename E::L;
-    for (;;) switch (e.t_pc(t)) {
-        case 0:  // Endpoint::bind(addr): BindGuard::bind → rand_delay
-          e.t_dl0(t) = e.rand_delay_deadline();
-          e.t_pc(t) = 1;
-          // fallthrough
-        case 1: {
-          if (!e.sleep_poll(t, e.t_dl0(t))) return POLL_PENDING;
-          int k = e.sock_bind(e.t_node(t), SERVER_ADDR);
-          if (k < 0) return e.panic(10);
-          e.sock_adopt(t, k);
-          e.t_pc(t) = 2;
-        }
-        // fallthrough
-        case 2:  // loop { recv_from(1): mailbox.recv(tag)
-          e.mbox_recv(t, e.t_sock(t), 1);
-          e.t_pc(t) = 3;
-          // fallthrough
-        case 3:  // oneshot::Receiver await
-          if (e.t_rx(t) == NONE8) return POLL_PENDING;
-          e.t_dl0(t) = e.rand_delay_deadline();  // rand_delay AFTER the receipt
-          e.t_pc(t) = 4;
-          // fallthrough
-        case 4: {
-          if (!e.sleep_poll(t, e.t_dl0(t))) return POLL_PENDING;
-          int m = e.t_rx(t);
-          u32 from = e.w(L::W_M_FROM, m), v0 = e.w(L::W_M_V0, m);
-          e.msg_free(m);
-          e.t_rx(t) = NONE8;
-          if (v0 != PING) return e.panic(11);
-          e.t_a(t) = from;
-          e.t_dl0(t) = e.rand_delay_deadline();  // send_to(from, 1, "pong"): rand_delay
-          e.t_pc(t) = 5;
-        }
-        // fallthrough
-        case 5: {
-          if (!e.sleep_poll(t, e.t_dl0(t))) return POLL_PENDING;
-          int m = e.msg_alloc();
-          if (m < 0) return POLL_PENDING;
-          e.q(L::Q_M_TAG, m) = 1;
-          e.q(L::Q_M_W, m) = 0;
-          e.w(L::W_M_V0, m) = PONG;
-          e.w(L::W_M_V1, m) = 0;
-          int k = e.t_sock(t);
-          e.net_send(e.b(L::B_SK_NODE, k), e.sk_port(k), e.t_a(t), m);
-          e.t_pc(t) = 2;  // }
-          continue;
-        }
-        default:
-          return e.panic(0xbad);
-      }
-  }
-
-  template <class E>
-  static MSIM_HD int poll_client(E& e, int t) {
-    using L = typename E::L;
-    for (;;) switch (e.t_pc(t)) {
-        case 0:  // sleep(1 s)
-          e.t_dl0(t) = e.sleep_deadline(e.now + NS_PER_SEC);
-          e.t_pc(t) = 1;
-          // fallthrough
-        case 1:
-          if (!e.sleep_poll(t, e.t_dl0(t))) return POLL_PENDING;
-          e.t_dl0(t) = e.rand_delay_deadline();  // Endpoint::connect = bind("0.0.0.0:0")
-          e.t_pc(t) = 2;
-          // fallthrough
-        case 2: {
-          if (!e.sleep_poll(t, e.t_dl0(t))) return POLL_PENDING;
-          int k = e.sock_bind(e.t_node(t), mk_addr(IPK_UNSPEC, 0, 0));
-          if (k < 0) return e.panic(12);
-          e.sock_adopt(t, k);
-          e.t_a(t) = 0;  // done
-          e.t_b(t) = 0;  // r
-          e.t_pc(t) = 3;
-        }
-        // fallthrough
-        case 3:  // for r in 0..rounds {
-          if ((u64)e.t_b(t) >= e.P->p[0]) return POLL_READY;  // output = t_a; the Endpoint drops with the future
-          e.t_dl0(t) = e.rand_delay_deadline();  // ep.send(1, "ping"): rand_delay
-          e.t_pc(t) = 4;
-          // fallthrough
-        case 4: {
-          if (!e.sleep_poll(t, e.t_dl0(t))) return POLL_PENDING;
-          int m = e.msg_alloc();
-          if (m < 0) return POLL_PENDING;
-          e.q(L::Q_M_TAG, m) = 1;
-          e.q(L::Q_M_W, m) = 0;
-          e.w(L::W_M_V0, m) = PING;
-          e.w(L::W_M_V1, m) = 0;
-          int k = e.t_sock(t);
-          e.net_send(e.b(L::B_SK_NODE, k), e.sk_port(k), SERVER_ADDR, m);
-          e.mbox_recv(t, k, 1);  // ep.recv(1): mailbox.recv(tag)
-          e.t_pc(t) = 5;
-        }
-        // fallthrough
-        case 5:
-          if (e.t_rx(t) == NONE8) return POLL_PENDING;
-          e.t_dl0(t) = e.rand_delay_deadline();
-          e.t_pc(t) = 6;
-          // fallthrough
-        case 6: {
-          if (!e.sleep_poll(t, e.t_dl0(t))) return POLL_PENDING;
-          int m = e.t_rx(t);
-          u32 from = e.w(L::W_M_FROM, m), v0 = e.w(L::W_M_V0, m);
-          e.msg_free(m);
-          e.t_rx(t) = NONE8;
-          if (from != SERVER_ADDR) return e.panic(15);  // "not from the connected address"
-          if (v0 != PONG) return e.panic(13);
-          e.t_a(t) = e.t_a(t) + 1;
-          e.t_dl0(t) = e.sleep_deadline(e.now + e.P->p[1]);  // sleep(think)
-          e.t_pc(t) = 7;
-        }
-        // fallthrough
-        case 7:
-          if (!e.sleep_poll(t, e.t_dl0(t))) return POLL_PENDING;
-          e.t_b(t) = e.t_b(t) + 1;
-          e.t_pc(t) = 3;  // }
-          continue;
-        default:
-          return e.panic(0xbad);
-      }
-  }
-
-  template <class E>
-  static MSIM_HD int poll(E& e, int t) {
-    switch (e.t_kind(t)) {
-      case K_MAIN: return poll_main(e, t);
-      case K_SERVER: return poll_server(e, t);
-      default: return poll_client(e, t);
-    }
-  }
-  template <class E>
-  static MSIM_HD void on_drop(E& e, int t) {
-    e.drop_task_resources(t, e.t_kind(t) != K_MAIN);
-  }
-  template <class E>
-  static MSIM_HD void node_init(E&, int) {}
-  template <class E>
-  static MSIM_HD void finish(E&) {}
 };
 
 }  // namespace msim

@@ -11,25 +11,16 @@ struct WL_Sleep {
     static constexpr int WQ = 0, WW = 0, WS = 0;
   };
   static constexpr u32 MAIN_KIND = 0;
+  static MSIM_HD int init_kind(int) { return -1; }
   template <class E>
-  static MSIM_HD int poll(E& e, int t) {
-    switch (e.t_pc(t)) {
-      case 0:
-        e.t_dl0(t) = e.sleep_deadline(e.now + e.P->p[0]);
-        e.t_pc(t) = 1;
-        // fallthrough
-      case 1:
-        if (!e.sleep_poll(t, e.t_dl0(t))) return POLL_PENDING;
-        return POLL_READY;
+  static MSIM_HD int fsm(E& e, int t) {
+    if (e.t_pc(t) == 0) {
+      e.t_pc(t) = 1;
+      e.xa = e.P->p[0];
+      return RQ_SLEEP_FOR;
     }
-    return e.panic(0xbad);
+    return RQ_READY;
   }
-  template <class E>
-  static MSIM_HD void on_drop(E&, int) {}
-  template <class E>
-  static MSIM_HD void node_init(E&, int) {}
-  template <class E>
-  static MSIM_HD void finish(E&) {}
 };
 
 }  // namespace msim

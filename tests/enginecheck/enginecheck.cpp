@@ -25,9 +25,7 @@ static int run_wl(const Params& P, uint64_t seed_base, uint64_t n, uint32_t S, u
       uint64_t i = blk * S + s;
       E e;
       std::memset(&e, 0, sizeof(e));
-      e.base = block.data();
-      e.S = S;
-      e.s = s;
+      e.sb = block.data() + (size_t)s * E::L::BYTES;
       e.P = &P;
       bool want_trace = tr && (seed_base + i) == trace_seed;
       e.tr = want_trace ? tr : nullptr;

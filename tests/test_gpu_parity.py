@@ -192,7 +192,8 @@ def test_capacity_overflow_is_reported_not_silent():
     cfg = m.Config()
     wl = m.Workload.raft(duration_ms=3000, rpc_timeout_ms=3, heartbeat_ms=20, election_ms=(40, 80), faults=4)
     res, bm, st = run_gpu(cfg, wl, 0, 32)
-    assert (res["status"] == m.ST_FAIL_CAPACITY).all() and (res["fail_code"] == 5).all()
+    # MSIM_CAP_MAILBOX (5) or MSIM_CAP_MSGS (4): the leaked responses exhaust one of the two tables first
+    assert (res["status"] == m.ST_FAIL_CAPACITY).all() and np.isin(res["fail_code"], [4, 5]).all()
     assert st["n_fail"] == 32 and bm[0] == 0xFFFFFFFF
 
 

@@ -35,6 +35,11 @@ B_PUSH = 32           # one timer push (>= 32 B)
 B_MSG = 40            # one datagram send/deliver
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the bench configuration,
+# from the `ncu --set full` capture summarised in profiles/r1c_step_kernel_v2_bench_config.json
+TRAFFIC_BYTES_PER_LAUNCH = {"raft": 597760}
+
+
 def algorithmic_bytes(ev_pop, ev_fire, msgs):
     pushes = ev_fire  # every fired timer was pushed once
     return ev_pop * B_POP + ev_fire * (B_FIRE_BASE + B_FIRE_PER_LEVEL * MEAN_LOG2_HEAP) + pushes * B_PUSH + msgs * B_MSG
@@ -300,10 +305,10 @@ def main():
     achieved = alg_bytes / (local_ms / 1e3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "kernel": "msim_step_kernel<WL_Raft>", "peak_source": peak_src,
+        "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.workload), "kernel": "msim_step_kernel<WL_Raft>", "peak_source": peak_src,
         "bytes_per_launch": alg_bytes / args.steps, "launch_ms": local_ms / args.steps,
         "note": "algorithmic bytes (SURVEY §8d model: 168 B/pop, 92+40*3.8 B/fire, 32 B/push, 40 B/msg). The kernel keeps "
-                "all per-seed state in shared memory: measured DRAM traffic is ~0.3 MB per launch (profiles/), so the "
+                "all per-seed state in shared memory: measured DRAM traffic is ~0.6 MB per launch (profiles/r1c), so the "
                 "kernel is instruction-issue/latency bound, not HBM bound; frac is reported against HBM as the contract asks.",
     }
 

@@ -79,8 +79,9 @@ typedef struct msim_trace_rec {
 } msim_trace_rec;
 
 /* Per-seed trace hash: h0 = MSIM_HASH_INIT; for each record, in order,
- *   h = mix(mix(mix(h, now_ns), aux), ((uint64_t)kind_id << 32) | draws)
- *   mix(h, w): h ^= w; h *= MSIM_HASH_MUL; h ^= h >> 32;                      */
+ *   w = now_ns ^ rotl64(aux, 17) ^ rotl64(((uint64_t)kind_id << 32) | draws, 41)
+ *   h = (h ^ w) * MSIM_HASH_MUL;  h ^= h >> 32;
+ * (one 64-bit multiply per event: the hash is on the device's critical path)  */
 #define MSIM_HASH_INIT 0xcbf29ce484222325ull
 #define MSIM_HASH_MUL 0x9e3779b97f4a7c15ull
 

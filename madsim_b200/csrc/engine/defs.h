@@ -73,7 +73,7 @@ constexpr u64 NS_PER_MS = 1000000ull;
 constexpr u64 NS_PER_SEC = 1000000000ull;
 
 // ---- poll results ----
-enum : int { POLL_PENDING = 0, POLL_READY = 1, POLL_PANIC = 2 };
+enum : int { POLL_PENDING = 0, POLL_READY = 1, POLL_PANIC = 2, POLL_ADVANCE = 3 };
 
 // ---- task flags (async-task's state bits + bookkeeping) ----
 enum : u8 {
@@ -92,6 +92,7 @@ enum : u8 { NF_EXISTS = 1, NF_KILLED = 2, NF_PAUSED = 4, NF_HAS_IP = 8, NF_RESTA
 
 // ---- timer payload: kind[31:28] | a[27:20] | b[19:0] ----
 enum : u32 { TK_WAKE = 0, TK_DELIVER = 1, TK_RESTART = 2 };
+static_assert(MSIM_EV_DELIVER == MSIM_EV_WAKE + 1 && MSIM_EV_RESTART == MSIM_EV_WAKE + 2, "event kinds follow TK_*");
 MSIM_HD u32 timer_payload(u32 kind, u32 a, u32 b) { return (kind << 28) | ((a & 0xffu) << 20) | (b & 0xfffffu); }
 
 // ---- socket addresses as the device sees them: ipk[31:24] | node[23:16] | port[15:0] ----

@@ -96,7 +96,7 @@ struct Layout {
   enum : int {
     W_EV_POP = 0, W_EV_FIRE, W_HEAP_LEN, W_RQ_LEN, W_NEXT_SPAWN, W_MSG_COUNT, W_STATUS, W_FAIL_CODE,
     W_PEAK_TIMERS, W_LIVE_TASKS, W_PEAK_TASKS, W_USER0, W_USER1, W_USER2, W_USER3, W_CLOG_IN, W_CLOG_OUT,
-    W_PK_LEN, W_BASE_SECS, W_NEXT_NODE, W_MAIN_SLOT, W_PANIC_CODE, W_NSCALAR
+    W_PK_LEN, W_BASE_SECS, W_NEXT_NODE, W_MAIN_SLOT, W_PANIC_CODE, W_RESUME, W_NSCALAR
   };
   static constexpr int W_CLOG_LINK = W_NSCALAR;                 // [NNODE] bit d set: link n->d clogged
   static constexpr int W_HEAP_PL = W_CLOG_LINK + C::NNODE;      // [TQ]
@@ -213,7 +213,8 @@ struct Engine {
   MSIM_HD void trace(u64 t_now, u64 aux, u32 kind, u32 id24) {
     u32 kind_id = (kind << 24) | (id24 & 0xffffffu);
     u32 d = (u32)draws;
-    hash = mix(mix(mix(hash, t_now), aux), ((u64)kind_id << 32) | d);
+    u64 kd = ((u64)kind_id << 32) | d;
+    hash = mix(hash, t_now ^ rotl64(aux, 17) ^ rotl64(kd, 41));
     if (tr) {
       if (tr_n < tr_cap) {
         tr[tr_n].now_ns = t_now;
@@ -360,16 +361,14 @@ struct Engine {
       timer_pop(dl, pl);
       ev_fire++;
       u32 kind = pl >> 28, a = (pl >> 20) & 0xff, g = pl & 0xfffffu;
-      if (kind == TK_WAKE) {
-        trace(now, dl, MSIM_EV_WAKE, g);
+      u32 id = kind == TK_WAKE ? g : (kind == TK_DELIVER ? w(L::W_M_SERIAL, a) : a);
+      trace(now, dl, MSIM_EV_WAKE + kind, id);  // MSIM_EV_WAKE / DELIVER / RESTART = 5 + TK_*
+      if (kind == TK_WAKE)
         wake(a, g);
-      } else if (kind == TK_DELIVER) {
-        trace(now, dl, MSIM_EV_DELIVER, w(L::W_M_SERIAL, a));
+      else if (kind == TK_DELIVER)
         deliver(a);
-      } else {
-        trace(now, dl, MSIM_EV_RESTART, a);
+      else
         restart(a);
-      }
     }
   }
   /// sleep()/sleep_until(): deadline = max(deadline, now + 1 ms)  (time/mod.rs:111-124)
@@ -860,6 +859,7 @@ MSIM_NOUNROLL
     // node 0 = "madsim-main" (task/mod.rs:187-198)
     n_flags(0) = NF_EXISTS;
     w(L::W_NEXT_NODE) = 1;
+    w(L::W_RESUME) = NONE32;
     int m = spawn(WL::MAIN_KIND, 0, TF_JOINABLE);
     w(L::W_MAIN_SLOT) = (u32)m;
   }
@@ -933,19 +933,17 @@ MSIM_NOUNROLL
               if (ret >= 0) sock_adopt(t, ret);
               wt = W_NONE;
               break;
-            case W_SEND: {  // NetSim::send after rand_delay
-              int m = t_msg(t);
-              t_msg(t) = NONE8;
-              net_send(b(L::B_SK_NODE, k), sk_port(k), w(L::W_M_FROM, m), m);
-              wt = W_NONE;
-              break;
-            }
-            case W_CALL_SEND: {  // call: send_to_raw done -> recv_from_raw(rsp_tag): mailbox.recv
+            case W_SEND:
+            case W_CALL_SEND: {  // NetSim::send after rand_delay (shared by send_to_raw and call's send)
               int m = t_msg(t);
               t_msg(t) = NONE8;
               u64 rsp_tag = q(L::Q_M_W, m);
               net_send(b(L::B_SK_NODE, k), sk_port(k), w(L::W_M_FROM, m), m);
-              mbox_recv(t, k, rsp_tag);
+              if (st == W_SEND) {
+                wt = W_NONE;
+                break;
+              }
+              mbox_recv(t, k, rsp_tag);  // call: recv_from_raw(rsp_tag): mailbox.recv
               wt = st = W_CALL_RX;
             }
             // fallthrough
@@ -1080,26 +1078,28 @@ MSIM_NOUNROLL
           t_c(t) = ya;
           t_wait(t) = W_JOIN;
           break;
-        case RQ_ADVANCE:  // time::advance (time/mod.rs:103-106,195-198): fires due timers inside this poll
-          now += xa;
-          expire(now);
-          break;
+        case RQ_ADVANCE:  // time::advance (time/mod.rs:103-106,195-198): clock += d, then the due timers fire
+          now += xa;      // inside this poll: the event loop fires them at its single expire site and
+          return POLL_ADVANCE;  // re-enters this poll (W_RESUME) before anything else runs
       }
     }
   }
 
   /// Runnable::run (async-task) + the panic policy of run_all_ready (task/mod.rs:285-317)
-  MSIM_HD void run_task(int t) {
+  MSIM_HD bool run_task(int t, bool cont) {
     u8 f = t_flags(t);
-    if (f & TF_CLOSED) {
-      drop_future(t);
-      t_flags(t) = t_flags(t) & ~TF_SCHEDULED;
-      notify_awaiter(t);
-      maybe_free(t);
-      return;
+    if (!cont) {
+      if (f & TF_CLOSED) {
+        drop_future(t);
+        t_flags(t) = t_flags(t) & ~TF_SCHEDULED;
+        notify_awaiter(t);
+        maybe_free(t);
+        return false;
+      }
+      t_flags(t) = (f & ~TF_SCHEDULED) | TF_RUNNING;
     }
-    t_flags(t) = (f & ~TF_SCHEDULED) | TF_RUNNING;
     int r = poll_task(t);
+    if (r == POLL_ADVANCE) return true;  // still RUNNING: the poll continues after the timers fired
     if (r == POLL_READY) {
       if (t_flags(t) & TF_INIT) node_exit(t_node(t), t_epoch(t));  // `future.await; h.exit()`
       drop_future(t);
@@ -1133,6 +1133,7 @@ MSIM_NOUNROLL
         rq_push(t);  // woken while running
       }
     }
+    return false;
   }
   MSIM_HD int panic(u32 code) {
     w(L::W_PANIC_CODE) = code;
@@ -1144,43 +1145,60 @@ MSIM_NOUNROLL
   /// jump to the next timer.  Returns false when the seed has stopped.
   MSIM_HD bool step() {
     u64 limit;
-    if (rq_len > 0) {
-      // try_recv_random (utils/mpsc.rs:73-83)
-      u32 len = rq_len;
-      u32 idx = gen_range_small(0, len);
-      int t = b(L::B_RQ, idx);
-      b(L::B_RQ, idx) = b(L::B_RQ, len - 1);  // swap_remove
-      rq_len = len - 1;
-      ev_pop++;
-      u64 aux = ((u64)len << 32) | idx;
-      u8 f = t_flags(t);
-      u32 id = t_spawn(t);
-      if (!(f & TF_ALIVE)) {  // metadata().upgrade() failed: future already dropped
-        trace(now, aux, MSIM_EV_SKIP, id);
-        t_flags(t) = f & ~TF_SCHEDULED;
-        maybe_free(t);
-        return true;
-      }
-      bool do_drop = (f & TF_CANCELLED) || task_node_killed(t);
-      if (!do_drop && (n_flags(t_node(t)) & NF_PAUSED)) {
-        trace(now, aux, MSIM_EV_PARK, id);
-        u32 pl = w(L::W_PK_LEN);
-        if (pl >= (u32)C::NPARK) {
-          fail_cap(MSIM_CAP_PARKED);
-          return false;
+    u32 rs = w(L::W_RESUME);
+    bool cont = rs != NONE32;  // a poll interrupted by time::advance continues before anything else
+    if (cont || rq_len > 0) {
+      int t;
+      bool do_drop = false;
+      if (cont) {
+        t = (int)rs;
+        w(L::W_RESUME) = NONE32;
+      } else {
+        // try_recv_random (utils/mpsc.rs:73-83)
+        u32 len = rq_len;
+        u32 idx = gen_range_small(0, len);
+        t = b(L::B_RQ, idx);
+        b(L::B_RQ, idx) = b(L::B_RQ, len - 1);  // swap_remove
+        rq_len = len - 1;
+        ev_pop++;
+        u64 aux = ((u64)len << 32) | idx;
+        u8 f = t_flags(t);
+        u32 kind = MSIM_EV_POLL;
+        if (!(f & TF_ALIVE))
+          kind = MSIM_EV_SKIP;  // metadata().upgrade() failed: future already dropped
+        else if ((f & TF_CANCELLED) || task_node_killed(t))
+          kind = MSIM_EV_DROP;
+        else if (n_flags(t_node(t)) & NF_PAUSED)
+          kind = MSIM_EV_PARK;
+        trace(now, aux, kind, t_spawn(t));
+        if (kind == MSIM_EV_SKIP) {
+          t_flags(t) = f & ~TF_SCHEDULED;
+          maybe_free(t);
+          return true;
         }
-        b(L::B_PK, pl) = (u8)t;
-        w(L::W_PK_LEN) = pl + 1;
-        return true;
+        if (kind == MSIM_EV_PARK) {
+          u32 pl = w(L::W_PK_LEN);
+          if (pl >= (u32)C::NPARK) {
+            fail_cap(MSIM_CAP_PARKED);
+            return false;
+          }
+          b(L::B_PK, pl) = (u8)t;
+          w(L::W_PK_LEN) = pl + 1;
+          return true;
+        }
+        do_drop = kind == MSIM_EV_DROP;
       }
-      trace(now, aux, do_drop ? MSIM_EV_DROP : MSIM_EV_POLL, id);
+      bool adv = false;
       if (do_drop)
         drop_runnable(t);
       else
-        run_task(t);
+        adv = run_task(t, cont);
       if (!running()) return false;
-      // advance time: 50-100ns (task/mod.rs:319-321): clock += dur, expire(clock)
-      now += gen_range_small(50, 100);
+      if (adv) {
+        w(L::W_RESUME) = (u32)t;
+      } else {
+        now += gen_range_small(50, 100);  // advance time: 50-100ns (task/mod.rs:319-321)
+      }
       limit = now;
     } else {
       // ready Vec drained: task.is_finished()?

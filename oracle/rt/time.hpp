@@ -31,7 +31,8 @@ struct Tracer {
   void record(u64 now_ns, u64 aux, u32 kind, u32 id24, u64 draws) {
     u32 kind_id = (kind << 24) | (id24 & 0xffffffu);
     u32 d = u32(draws);
-    hash = mix(mix(mix(hash, now_ns), aux), (u64(kind_id) << 32) | d);
+    u64 kd = (u64(kind_id) << 32) | d;
+    hash = mix(hash, now_ns ^ ((aux << 17) | (aux >> 47)) ^ ((kd << 41) | (kd >> 23)));
     if (kind <= MSIM_EV_SKIP)
       n_pop++;
     else

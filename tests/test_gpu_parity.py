@@ -158,11 +158,12 @@ def test_device_trace_replay_equals_oracle_trace_and_hash(oracle):
             # checksum of checksums: recompute the hash from the records
             h = 0xCBF29CE484222325
             M = (1 << 64) - 1
+            rotl = lambda v, k: ((v << k) | (v >> (64 - k))) & M
             for t in tr:
-                for wd in (int(t["now_ns"]), int(t["aux"]), (int(t["kind_id"]) << 32) | int(t["draws"])):
-                    h ^= wd
-                    h = (h * 0x9E3779B97F4A7C15) & M
-                    h ^= h >> 32
+                kd = (int(t["kind_id"]) << 32) | int(t["draws"])
+                h ^= int(t["now_ns"]) ^ rotl(int(t["aux"]), 17) ^ rotl(kd, 41)
+                h = (h * 0x9E3779B97F4A7C15) & M
+                h ^= h >> 32
             assert h == int(rec["trace_hash"])
 
 

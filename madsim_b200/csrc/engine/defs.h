@@ -18,6 +18,15 @@
 #define MSIM_HD inline
 #define MSIM_HD_NOINLINE inline
 #endif
+// MSIM_NI: rarely executed runtime paths get ONE out-of-line copy on the device, so that the hot
+// event loop stays dense in the instruction cache
+#if defined(__CUDACC__)
+#define MSIM_NI __host__ __device__ __noinline__
+#else
+#define MSIM_NI inline
+#endif
+#define MSIM_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define MSIM_LIKELY(x) __builtin_expect(!!(x), 1)
 #if defined(__CUDACC__)
 #define MSIM_NOUNROLL _Pragma("unroll 1")
 #else

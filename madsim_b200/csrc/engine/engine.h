@@ -298,7 +298,7 @@ struct Engine {
   /// Timer::add = BinaryHeap::push: append, sift_up while STRICTLY earlier than the parent
   MSIM_HD void timer_push(u64 dl, u32 pl) {
     u32 pos = heap_len;
-    if (pos >= (u32)C::TQ) {
+    if (MSIM_UNLIKELY(pos >= (u32)C::TQ)) {
       fail_cap(MSIM_CAP_TIMERS);
       return;
     }
@@ -365,7 +365,7 @@ struct Engine {
       trace(now, dl, MSIM_EV_WAKE + kind, id);  // MSIM_EV_WAKE / DELIVER / RESTART = 5 + TK_*
       if (kind == TK_WAKE)
         wake(a, g);
-      else if (kind == TK_DELIVER)
+      else if (MSIM_LIKELY(kind == TK_DELIVER))
         deliver(a);
       else
         restart(a);
@@ -379,7 +379,7 @@ struct Engine {
 
   // ---------------- tasks (async-task state machine) ----------------
   MSIM_HD void rq_push(int t) {
-    if (rq_len >= (u32)C::NT) {
+    if (MSIM_UNLIKELY(rq_len >= (u32)C::NT)) {
       fail_cap(MSIM_CAP_READY);
       return;
     }
@@ -433,13 +433,28 @@ struct Engine {
     }
   }
   /// impl Drop for Runnable: the kill / cancel path (task/mod.rs:273)
-  MSIM_HD void drop_runnable(int t) {
+  MSIM_HD void drop_runnable_inl(int t) {
     u8 f = t_flags(t);
     if (!(f & (TF_COMPLETED | TF_CLOSED))) t_flags(t) = f | TF_CLOSED;
     drop_future(t);
     t_flags(t) = t_flags(t) & ~TF_SCHEDULED;
     notify_awaiter(t);
     maybe_free(t);
+  }
+  static MSIM_NI void drop_runnable_cold(unsigned char* sb_, const Params* P_, u64 now_, int t) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.load();
+    e_.now = now_;
+    e_.drop_runnable_inl(t);
+    e_.store();
+  }
+  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
+  MSIM_HD void drop_runnable(int t) {
+    store();
+    drop_runnable_cold(sb, P, now, t);
+    load();
   }
   /// Spawner::spawn_inner (task/mod.rs:627-654): returns the slot or -1
   MSIM_HD int spawn(u32 kind, u32 node, u8 extra_flags) {
@@ -455,7 +470,7 @@ MSIM_NOUNROLL
       }
     }
     u32 idx = w(L::W_NEXT_SPAWN);
-    if (t < 0 || t >= C::NT || idx >= 0xfffffu) {
+    if (MSIM_UNLIKELY(t < 0 || t >= C::NT || idx >= 0xfffffu)) {
       fail_cap(MSIM_CAP_TASKS);
       return -1;
     }
@@ -550,18 +565,48 @@ MSIM_NOUNROLL
     }
     w(L::W_PK_LEN) = keep;
   }
-  MSIM_HD void kill(int n) {
+  MSIM_HD void kill_inl(int n) {
     drop_parked(n);
     n_flags(n) = n_flags(n) | NF_KILLED;
     info_kill(n, n_epoch(n));
     reset_node_sockets(n);  // NetSim::reset_node: all sockets of the node closed (network.rs:142-147)
   }
+  static MSIM_NI void kill_cold(unsigned char* sb_, const Params* P_, u64 now_, int n) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.load();
+    e_.now = now_;
+    e_.kill_inl(n);
+    e_.store();
+  }
+  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
+  MSIM_HD void kill(int n) {
+    store();
+    kill_cold(sb, P, now, n);
+    load();
+  }
   /// Spawner::exit (task/mod.rs:656-661): info.kill() only — no reset_node, paused list kept
-  MSIM_HD void node_exit(int n, u8 epoch) {
+  MSIM_HD void node_exit_inl(int n, u8 epoch) {
     if (n_epoch(n) == epoch) n_flags(n) = n_flags(n) | NF_KILLED;
     info_kill(n, epoch);
   }
-  MSIM_HD void restart(int n) {
+  static MSIM_NI void node_exit_cold(unsigned char* sb_, const Params* P_, u64 now_, int n, u8 epoch) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.load();
+    e_.now = now_;
+    e_.node_exit_inl(n, epoch);
+    e_.store();
+  }
+  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
+  MSIM_HD void node_exit(int n, u8 epoch) {
+    store();
+    node_exit_cold(sb, P, now, n, epoch);
+    load();
+  }
+  MSIM_HD void restart_inl(int n) {
     drop_parked(n);
     info_kill(n, n_epoch(n));  // old_info.kill()
     n_epoch(n) = n_epoch(n) + 1;
@@ -569,8 +614,23 @@ MSIM_NOUNROLL
     int kind = WL::init_kind(n);
     if (kind >= 0) spawn((u32)kind, n, TF_INIT);
   }
+  static MSIM_NI void restart_cold(unsigned char* sb_, const Params* P_, u64 now_, int n) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.load();
+    e_.now = now_;
+    e_.restart_inl(n);
+    e_.store();
+  }
+  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
+  MSIM_HD void restart(int n) {
+    store();
+    restart_cold(sb, P, now, n);
+    load();
+  }
   MSIM_HD void pause(int n) { n_flags(n) = n_flags(n) | NF_PAUSED; }
-  MSIM_HD void resume(int n) {
+  MSIM_HD void resume_inl(int n) {
     n_flags(n) = n_flags(n) & ~NF_PAUSED;
     u32 len = w(L::W_PK_LEN), keep = 0;
 MSIM_NOUNROLL
@@ -583,7 +643,54 @@ MSIM_NOUNROLL
     }
     w(L::W_PK_LEN) = keep;
   }
+  static MSIM_NI void resume_cold(unsigned char* sb_, const Params* P_, u64 now_, int n) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.load();
+    e_.now = now_;
+    e_.resume_inl(n);
+    e_.store();
+  }
+  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
+  MSIM_HD void resume(int n) {
+    store();
+    resume_cold(sb, P, now, n);
+    load();
+  }
   MSIM_HD bool is_exit(int n) const { return n_flags(n) & NF_KILLED; }
+  /// Handle::create_node + NodeBuilder::build (runtime/mod.rs:405-418): ids start at 1; the init
+  /// closure runs (spawns the init task) at build time
+  MSIM_HD int create_node_inl(u32 flags) {
+    u32 n = w(L::W_NEXT_NODE);
+    if (n >= (u32)C::NNODE) {
+      fail_cap(MSIM_CAP_TASKS);
+      return -1;
+    }
+    w(L::W_NEXT_NODE) = n + 1;
+    n_flags(n) = NF_EXISTS | ((flags & NODE_IP) ? NF_HAS_IP : 0) | ((flags & NODE_RESTART_ON_PANIC) ? NF_RESTART_ON_PANIC : 0);
+    n_epoch(n) = 0;
+    int kind = (flags & NODE_INIT) ? WL::init_kind((int)n) : -1;
+    if (kind >= 0) spawn((u32)kind, n, TF_INIT);
+    return (int)n;
+  }
+  static MSIM_NI int create_node_cold(unsigned char* sb_, const Params* P_, u64 now_, u32 flags) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.load();
+    e_.now = now_;
+    int r_ = e_.create_node_inl(flags);
+    e_.store();
+    return r_;
+  }
+  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
+  MSIM_HD int create_node(u32 flags) {
+    store();
+    auto r_ = create_node_cold(sb, P, now, flags);
+    load();
+    return r_;
+  }
 
   // ---------------- network (net/network.rs, net/mod.rs, net/endpoint.rs) ----------------
   MSIM_HD u8& sk_state(int k) const { return b(L::B_SK_STATE, k); }
@@ -591,7 +698,7 @@ MSIM_NOUNROLL
   MSIM_HD u32 sk_port(int k) const { return w(L::W_SK_PORTGEN, k) & 0xffff; }
   MSIM_HD int msg_alloc() {
     u64 m = q(L::Q_MFREE);
-    if (!m) {
+    if (MSIM_UNLIKELY(!m)) {
       fail_cap(MSIM_CAP_MSGS);
       return -1;
     }
@@ -607,7 +714,7 @@ MSIM_NOUNROLL
     return -1;
   }
   /// Network::bind (network.rs:206-251).  >= 0 socket slot; -1 AddrNotAvailable; -2 AddrInUse
-  MSIM_HD int sock_bind(int node, u32 addr) {
+  MSIM_HD int sock_bind_inl(int node, u32 addr) {
     u32 ipk = addr_ipk(addr), port = addr_port(addr);
     if (ipk == IPK_NODE && (int)addr_node(addr) != node) return -1;
     if (port == 0) {
@@ -632,6 +739,23 @@ MSIM_NOUNROLL
     b(L::B_SK_EPOCH, k) = n_epoch(node);
     w(L::W_SK_PORTGEN, k) = port | ((sk_gen(k) + 1) << 16);
     return k;
+  }
+  static MSIM_NI int sock_bind_cold(unsigned char* sb_, const Params* P_, u64 now_, int node, u32 addr) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.load();
+    e_.now = now_;
+    int r_ = e_.sock_bind_inl(node, addr);
+    e_.store();
+    return r_;
+  }
+  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
+  MSIM_HD int sock_bind(int node, u32 addr) {
+    store();
+    auto r_ = sock_bind_cold(sb, P, now, node, addr);
+    load();
+    return r_;
   }
   MSIM_HD void sock_release_storage(int k) {
     u32 ml = b(L::B_SK_MBLEN, k);
@@ -752,7 +876,7 @@ MSIM_NOUNROLL
       }
     }
     u32 ml = b(L::B_SK_MBLEN, k);
-    if (ml >= (u32)C::NMBOX) {
+    if (MSIM_UNLIKELY(ml >= (u32)C::NMBOX)) {
       fail_cap(MSIM_CAP_MAILBOX);
       msg_free(m);
       return;
@@ -776,7 +900,7 @@ MSIM_NOUNROLL
       }
     }
     u32 rl = b(L::B_SK_REGLEN, k);
-    if (rl >= (u32)C::NREG) {
+    if (MSIM_UNLIKELY(rl >= (u32)C::NREG)) {
       fail_cap(MSIM_CAP_REGISTERED);
       return;
     }
@@ -827,7 +951,7 @@ MSIM_NOUNROLL
 
   // ---------------- lifecycle ----------------
   /// Runtime::with_seed_and_config (runtime/mod.rs:53-69) for this seed + block_on's spawn of main
-  MSIM_HD void init(u64 seed) {
+  MSIM_HD void init_inl(u64 seed) {
     u64* z = reinterpret_cast<u64*>(sb);
 MSIM_NOUNROLL
     for (int i = 0; i < L::BYTES / 8; i++) z[i] = 0;
@@ -862,6 +986,18 @@ MSIM_NOUNROLL
     w(L::W_RESUME) = NONE32;
     int m = spawn(WL::MAIN_KIND, 0, TF_JOINABLE);
     w(L::W_MAIN_SLOT) = (u32)m;
+  }
+  static MSIM_NI void init_cold(unsigned char* sb_, const Params* P_, u64 now_, u64 seed) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.now = now_;
+    e_.init_inl(seed);
+    e_.store();
+  }
+  MSIM_HD void init(u64 seed) {
+    init_cold(sb, P, 0, seed);
+    load();
   }
   /// registers <- state block
   MSIM_HD void load() {
@@ -904,7 +1040,7 @@ MSIM_NOUNROLL
   /// pending poll, draws in program order).
   MSIM_HD int poll_task(int t) {
     for (;;) {
-      if (!running()) return POLL_PENDING;
+      if (MSIM_UNLIKELY(!running())) return POLL_PENDING;
       u8 wt = t_wait(t);
       if (wt != W_NONE) {
         u8 st = wt & 0x0f;
@@ -1046,20 +1182,10 @@ MSIM_NOUNROLL
           mbox_recv(t, t_sock(t), xa);
           t_wait(t) = W_RECV_RX;
           break;
-        case RQ_CREATE_NODE: {  // Handle::create_node + NodeBuilder::build (runtime/mod.rs:405-418): ids start at 1
-          u32 n = w(L::W_NEXT_NODE);
-          if (n >= (u32)C::NNODE) {
-            fail_cap(MSIM_CAP_TASKS);
-            return POLL_PENDING;
-          }
-          w(L::W_NEXT_NODE) = n + 1;
-          n_flags(n) = NF_EXISTS | ((ya & NODE_IP) ? NF_HAS_IP : 0) | ((ya & NODE_RESTART_ON_PANIC) ? NF_RESTART_ON_PANIC : 0);
-          n_epoch(n) = 0;
-          int kind = (ya & NODE_INIT) ? WL::init_kind((int)n) : -1;
-          if (kind >= 0) spawn((u32)kind, n, TF_INIT);  // init(&handle) runs at build time
-          ret = (int)n;
+        case RQ_CREATE_NODE:
+          ret = create_node(ya);
+          if (ret < 0) return POLL_PENDING;
           break;
-        }
         case RQ_SPAWN: {
           int c = spawn(ya & 0xff, yb, (ya & SPAWN_JOINABLE) ? TF_JOINABLE : 0);
           ret = c;
@@ -1089,7 +1215,7 @@ MSIM_NOUNROLL
   MSIM_HD bool run_task(int t, bool cont) {
     u8 f = t_flags(t);
     if (!cont) {
-      if (f & TF_CLOSED) {
+      if (MSIM_UNLIKELY(f & TF_CLOSED)) {
         drop_future(t);
         t_flags(t) = t_flags(t) & ~TF_SCHEDULED;
         notify_awaiter(t);
@@ -1099,32 +1225,25 @@ MSIM_NOUNROLL
       t_flags(t) = (f & ~TF_SCHEDULED) | TF_RUNNING;
     }
     int r = poll_task(t);
-    if (r == POLL_ADVANCE) return true;  // still RUNNING: the poll continues after the timers fired
+    if (MSIM_UNLIKELY(r == POLL_ADVANCE)) return true;  // still RUNNING: the poll continues after the timers fired
     if (r == POLL_READY) {
-      if (t_flags(t) & TF_INIT) node_exit(t_node(t), t_epoch(t));  // `future.await; h.exit()`
+      if (MSIM_UNLIKELY(t_flags(t) & TF_INIT)) node_exit(t_node(t), t_epoch(t));  // `future.await; h.exit()`
       drop_future(t);
       t_flags(t) = (t_flags(t) & ~(TF_RUNNING | TF_SCHEDULED)) | TF_COMPLETED;
       notify_awaiter(t);
       maybe_free(t);
-    } else if (r == POLL_PANIC) {
+    } else if (MSIM_UNLIKELY(r == POLL_PANIC)) {
       // async-task's guard: close, drop the future, notify the awaiter
       t_flags(t) = (t_flags(t) & ~(TF_RUNNING | TF_SCHEDULED)) | TF_CLOSED;
       drop_future(t);
       notify_awaiter(t);
       int n = t_node(t);
-      bool rop = (n_flags(n) & NF_RESTART_ON_PANIC) != 0;
       maybe_free(t);
-      if (rop) {
-        u64 delay = sample_inclusive_u64(NS_PER_SEC, 10 * NS_PER_SEC - 1);  // gen_range(1s..10s): Medium
-        kill(n);
-        timer_push(now + delay, timer_payload(TK_RESTART, n, 0));
-      } else {
-        fail(MSIM_ST_FAIL_ASSERT, w(L::W_PANIC_CODE));
-      }
+      panicked(n);
     } else {
       f = t_flags(t) & ~TF_RUNNING;
       t_flags(t) = f;
-      if (f & TF_CLOSED) {
+      if (MSIM_UNLIKELY(f & TF_CLOSED)) {
         t_flags(t) = f & ~TF_SCHEDULED;
         drop_future(t);
         notify_awaiter(t);
@@ -1134,6 +1253,32 @@ MSIM_NOUNROLL
       }
     }
     return false;
+  }
+  /// run_all_ready's panic policy (task/mod.rs:289-317): restart_on_panic nodes are killed and
+  /// restarted after gen_range(1s..10s); anything else fails the test
+  MSIM_HD void panicked_inl(int n) {
+    if (n_flags(n) & NF_RESTART_ON_PANIC) {
+      u64 delay = sample_inclusive_u64(NS_PER_SEC, 10 * NS_PER_SEC - 1);  // UniformDuration Medium
+      kill(n);
+      timer_push(now + delay, timer_payload(TK_RESTART, n, 0));
+    } else {
+      fail(MSIM_ST_FAIL_ASSERT, w(L::W_PANIC_CODE));
+    }
+  }
+  static MSIM_NI void panicked_cold(unsigned char* sb_, const Params* P_, u64 now_, int n) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.load();
+    e_.now = now_;
+    e_.panicked_inl(n);
+    e_.store();
+  }
+  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
+  MSIM_HD void panicked(int n) {
+    store();
+    panicked_cold(sb, P, now, n);
+    load();
   }
   MSIM_HD int panic(u32 code) {
     w(L::W_PANIC_CODE) = code;
@@ -1171,12 +1316,12 @@ MSIM_NOUNROLL
         else if (n_flags(t_node(t)) & NF_PAUSED)
           kind = MSIM_EV_PARK;
         trace(now, aux, kind, t_spawn(t));
-        if (kind == MSIM_EV_SKIP) {
+        if (MSIM_UNLIKELY(kind == MSIM_EV_SKIP)) {
           t_flags(t) = f & ~TF_SCHEDULED;
           maybe_free(t);
           return true;
         }
-        if (kind == MSIM_EV_PARK) {
+        if (MSIM_UNLIKELY(kind == MSIM_EV_PARK)) {
           u32 pl = w(L::W_PK_LEN);
           if (pl >= (u32)C::NPARK) {
             fail_cap(MSIM_CAP_PARKED);
@@ -1189,12 +1334,12 @@ MSIM_NOUNROLL
         do_drop = kind == MSIM_EV_DROP;
       }
       bool adv = false;
-      if (do_drop)
+      if (MSIM_UNLIKELY(do_drop))
         drop_runnable(t);
       else
         adv = run_task(t, cont);
-      if (!running()) return false;
-      if (adv) {
+      if (MSIM_UNLIKELY(!running())) return false;
+      if (MSIM_UNLIKELY(adv)) {
         w(L::W_RESUME) = (u32)t;
       } else {
         now += gen_range_small(50, 100);  // advance time: 50-100ns (task/mod.rs:319-321)
@@ -1204,7 +1349,7 @@ MSIM_NOUNROLL
       // ready Vec drained: task.is_finished()?
       int m = (int)w(L::W_MAIN_SLOT);
       u8 mf = t_flags(m);
-      if (mf & (TF_COMPLETED | TF_CLOSED)) {
+      if (MSIM_UNLIKELY(mf & (TF_COMPLETED | TF_CLOSED))) {
         if (mf & TF_COMPLETED)
           status = MSIM_ST_PASS;
         else
@@ -1212,7 +1357,7 @@ MSIM_NOUNROLL
         return false;
       }
       // advance_to_next_event (time/mod.rs:45-60): callbacks fire under the OLD clock
-      if (heap_len == 0) {
+      if (MSIM_UNLIKELY(heap_len == 0)) {
         fail(MSIM_ST_FAIL_DEADLOCK, 0);
         return false;
       }
@@ -1221,7 +1366,7 @@ MSIM_NOUNROLL
     expire(limit);  // the one place timers fire from the event loop
     if (now != limit) {
       now = limit;
-      if (P->time_limit_ns && now >= P->time_limit_ns) {
+      if (MSIM_UNLIKELY(P->time_limit_ns && now >= P->time_limit_ns)) {
         fail(MSIM_ST_FAIL_TIME_LIMIT, 0);
         return false;
       }

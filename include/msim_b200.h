@@ -111,7 +111,8 @@ typedef struct msim_config {
  *  RAFT     p0 = virtual duration ms (default 10000), p1 = fault mask (MSIM_RAFT_FAULT_*),
  *           p2 = bug mode (0 none, 1 double-vote), p3 = rpc timeout ms (default 40),
  *           p4 = heartbeat ms (default 50), p5 = election timeout lo ms (150), p6 = hi ms (300)
- *  CHAOS    p0 = rounds, p1 = period ms                                                        */
+ *  CHAOS    p0 = rounds, p1 = period ms, p2 = worker panics on its first p2 starts (restart_on_panic)
+ *                                                         */
 #define MSIM_RAFT_FAULT_CLOG_NODE 1u
 #define MSIM_RAFT_FAULT_CLOG_LINK 2u
 #define MSIM_RAFT_FAULT_CLOCK_JUMP 4u

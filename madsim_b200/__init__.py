@@ -30,6 +30,7 @@ from ._native import (  # noqa: F401
     ST_PASS,
     ST_RUNNING,
     STATUS_NAMES,
+    WL_CHAOS,
     WL_PINGPONG,
     WL_RAFT,
     WL_SLEEP,

@@ -92,6 +92,12 @@ class Workload:
             [duration_ms, faults, bug, rpc_timeout_ms, heartbeat_ms, election_ms[0], election_ms[1], 0],
         )
 
+    @staticmethod
+    def chaos(rounds: int = 8, period_ms: int = 2000, panics: int = 0) -> "Workload":
+        """kill / restart / pause / resume supervisor schedule (task/mod.rs:858-1016); with
+        `panics` > 0 the worker panics on its first starts under restart_on_panic (:939-963)."""
+        return Workload(N.WL_CHAOS, 1, [rounds, period_ms, panics, 0, 0, 0, 0, 0])
+
     def to_c(self) -> N.MsimWorkloadDesc:
         return N.MsimWorkloadDesc(self.workload, self.n_nodes, (C.c_uint64 * 8)(*[int(x) for x in self.p]))
 

@@ -121,6 +121,12 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
         return MSIM_EINVAL;
       }
       break;
+    case MSIM_WL_CHAOS:
+      if (wl.p[1] == 0) {
+        if (err) *err = "chaos: period must be > 0";
+        return MSIM_EINVAL;
+      }
+      break;
     default:
       if (err) *err = "unknown workload";
       return MSIM_EINVAL;

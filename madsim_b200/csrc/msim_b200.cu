@@ -248,6 +248,7 @@ int state_bytes_of(uint32_t workload) {
     case MSIM_WL_SLEEP: return Layout<WL_Sleep::Caps>::BYTES;
     case MSIM_WL_PINGPONG: return Layout<WL_PingPong::Caps>::BYTES;
     case MSIM_WL_RAFT: return Layout<WL_Raft::Caps>::BYTES;
+    case MSIM_WL_CHAOS: return Layout<WL_Chaos::Caps>::BYTES;
   }
   return -1;
 }
@@ -342,6 +343,7 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
     case MSIM_WL_SLEEP: e = launch_wl<WL_Sleep>(a, grid, block, b->smem, b->stream); break;
     case MSIM_WL_PINGPONG: e = launch_wl<WL_PingPong>(a, grid, block, b->smem, b->stream); break;
     case MSIM_WL_RAFT: e = launch_wl<WL_Raft>(a, grid, block, b->smem, b->stream); break;
+    case MSIM_WL_CHAOS: e = launch_wl<WL_Chaos>(a, grid, block, b->smem, b->stream); break;
     default: return set_err(MSIM_EINVAL, "unknown workload");
   }
   if (e != cudaSuccess) return set_err(MSIM_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
@@ -433,7 +435,6 @@ int msim_config_default(msim_config* cfg) {
 int msim_workload_default(uint32_t workload, msim_workload_desc* out) {
   if (!out) return set_err(MSIM_EINVAL, "null descriptor");
   if (workload_defaults(workload, out)) return set_err(MSIM_EINVAL, "unknown workload");
-  if (workload == MSIM_WL_CHAOS) return set_err(MSIM_EINVAL, "MSIM_WL_CHAOS is not available on the device yet");
   return MSIM_OK;
 }
 

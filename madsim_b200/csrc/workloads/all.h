@@ -1,4 +1,5 @@
 #pragma once
+#include "chaos.h"
 #include "pingpong.h"
 #include "raft.h"
 #include "sleep.h"

@@ -275,18 +275,22 @@ inline Async<u32> wl_raft_main(std::shared_ptr<RaftCluster> c, RaftOutcome* out)
 struct ChaosState {
   u32 flag = 0, starts = 0;
 };
-inline Async<Unit> chaos_worker(std::shared_ptr<ChaosState> st, u64 period_ns) {
+inline Async<Unit> chaos_worker(std::shared_ptr<ChaosState> st, u64 period_ns, u32 panics) {
   st->starts++;
+  if (st->starts <= panics) panic("chaos worker boom", 23);  // restart_on_panic (task/mod.rs:939-963)
   for (;;) {
     co_await sleep(period_ns);
     st->flag += 2;
   }
 }
-inline Async<u32> wl_chaos_main(u64 rounds, u64 period_ms, std::array<u32, 4>* user) {
+inline Async<u32> wl_chaos_main(u64 rounds, u64 period_ms, u32 panics, std::array<u32, 4>* user) {
   auto& rt = current_runtime();
   auto st = std::make_shared<ChaosState>();
   u64 period = period_ms * MS;
-  auto node = rt.create_node().init([st, period]() { return chaos_worker(st, period); }).build();
+  auto nb = rt.create_node();
+  nb.init([st, period, panics]() { return chaos_worker(st, period, panics); });
+  if (panics) nb.restart_on_panic();
+  auto node = nb.build();
   u64 id = node.id();
   GlobalRng& rng = thread_rng();
   for (u64 r = 0; r < rounds; r++) {

@@ -58,9 +58,8 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
   switch (wl->workload) {
     case MSIM_WL_SLEEP: return run_wl<WL_Sleep>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_PINGPONG: return run_wl<WL_PingPong>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
-#ifdef MSIM_HAVE_RAFT
     case MSIM_WL_RAFT: return run_wl<WL_Raft>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
-#endif
+    case MSIM_WL_CHAOS: return run_wl<WL_Chaos>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
   }
   return MSIM_EINVAL;
 }
@@ -69,9 +68,8 @@ extern "C" int enginecheck_state_bytes(uint32_t workload) {
   switch (workload) {
     case MSIM_WL_SLEEP: return Layout<WL_Sleep::Caps>::BYTES;
     case MSIM_WL_PINGPONG: return Layout<WL_PingPong::Caps>::BYTES;
-#ifdef MSIM_HAVE_RAFT
     case MSIM_WL_RAFT: return Layout<WL_Raft::Caps>::BYTES;
-#endif
+    case MSIM_WL_CHAOS: return Layout<WL_Chaos::Caps>::BYTES;
   }
   return -1;
 }

@@ -42,6 +42,7 @@ def test_defaults_and_validation_need_no_device():
     assert lib.msim_workload_default(99, C.byref(d)) == N.EINVAL
     assert lib.msim_workload_state_bytes(N.WL_RAFT) > 1000
     assert lib.msim_workload_state_bytes(77) == N.EINVAL
+    assert lib.msim_workload_default(N.WL_CHAOS, C.byref(d)) == 0 and list(d.p)[:2] == [8, 2000]
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is present")

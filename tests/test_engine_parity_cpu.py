@@ -42,6 +42,10 @@ CASES = [
     ("raft-fast-timeouts", m.Config(), m.Workload.raft(duration_ms=1500, rpc_timeout_ms=25, heartbeat_ms=30,
                                                         election_ms=(80, 160), faults=4), 0, 32),
     ("raft-zero-duration", m.Config(), m.Workload.raft(duration_ms=0), 0, 4),
+    # Handle::{kill,restart,pause,resume} + restart_on_panic (task/mod.rs:356-424,289-317)
+    ("chaos", m.Config(), m.Workload.chaos(), 0, 200),
+    ("chaos-long-panics", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 200),
+    ("chaos-always-panicking", m.Config(), m.Workload.chaos(rounds=4, period_ms=3000, panics=50), 0, 100),
 ]
 
 

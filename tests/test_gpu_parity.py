@@ -78,6 +78,9 @@ CASES = [
     ("raft-fast-timeouts", m.Config(), m.Workload.raft(duration_ms=1500, rpc_timeout_ms=25, heartbeat_ms=30,
                                                         election_ms=(80, 160), faults=4), 0, 100),
     ("raft-huge-seeds", m.Config(), m.Workload.raft(duration_ms=1500, faults=7), 2**64 - 50, 50),
+    ("chaos-kill-restart-pause", m.Config(), m.Workload.chaos(), 0, 500),
+    ("chaos-restart-on-panic", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 500),
+    ("chaos-always-panicking", m.Config(), m.Workload.chaos(rounds=4, period_ms=3000, panics=50), 0, 200),
 ]
 
 

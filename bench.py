@@ -231,10 +231,13 @@ def main():
         first = step_idx * n_total + rank * n_local
         run.batch.run(first, n_local, sync=False)
 
-    # ---------------- warm-up ----------------
+    # ---------------- warm-up (both paths: kernels, NCCL communicator, pinned staging) ----------------
     for w_i in range(max(args.warmup, 3)):
         step_resident(1_000_000 + w_i)
         run.batch.sync()
+        run.run((2_000 + w_i) * n_total, n_total, sync=False)
+        run.reduce()
+        run.batch.results()
     barrier()
 
     # ---------------- device-timed steps (value) ----------------

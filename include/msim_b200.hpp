@@ -1,0 +1,194 @@
+// msim_b200.hpp — C++ host mirror of the reference's runtime interface, over the C-ABI
+// (include/msim_b200.h → libmsim_b200.so).  Header-only; same names, argument meaning and
+// error behaviour as the Rust API for the hot path:
+//
+//   madsim::Config                         madsim/src/sim/config.rs:11-35, net/network.rs:66-89
+//   madsim::runtime::Runtime               madsim/src/sim/runtime/mod.rs:34-210
+//       ::with_seed_and_config(seed, cfg)    :53-69
+//       ::block_on(workload)                 :127-130   (one seed; panics ⇒ exception with the seed note)
+//       ::set_time_limit(d)                  :132-137
+//       ::check_determinism(seed, cfg, wl)   :178-202   (run twice, compare the traces)
+//   madsim::runtime::Builder               madsim/src/sim/runtime/builder.rs:7-162
+//       ::from_env()                         :64-118    MADSIM_TEST_{SEED,NUM,JOBS,TIME_LIMIT,CHECK_DETERMINISM}
+//       ::run(workload)                      :121-162   seeds seed..seed+count on the GPU; the first
+//                                                        failing seed is re-raised with the reference's note
+//
+// A `Workload` is the registered program that stands where the reference takes an async closure
+// (arbitrary futures cannot run on a GPU; see include/msim_b200.h MSIM_WL_*).
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "msim_b200.h"
+
+namespace madsim {
+
+/// A panic that escaped `block_on` in the reference (runtime/mod.rs:205-210).
+struct SimulationFailure : std::runtime_error {
+  uint64_t seed;
+  uint32_t status, fail_code;
+  SimulationFailure(uint64_t s, uint32_t st, uint32_t code)
+      : std::runtime_error("seed " + std::to_string(s) + " failed: status " + std::to_string(st) + " code " +
+                           std::to_string(code) + "\nnote: run with `MADSIM_TEST_SEED=" + std::to_string(s) +
+                           "` environment variable to reproduce this error"),
+        seed(s), status(st), fail_code(code) {}
+};
+/// any non-zero return of the C-ABI
+struct MsimError : std::runtime_error {
+  int code;
+  MsimError(int c, const char* m) : std::runtime_error(std::string("msim error ") + std::to_string(c) + ": " + m), code(c) {}
+};
+inline void check(int rc) {
+  if (rc != MSIM_OK) throw MsimError(rc, msim_last_error());
+}
+
+/// madsim::Config { net: { packet_loss_rate, send_latency } }
+struct Config {
+  struct Net {
+    double packet_loss_rate = 0.0;
+    uint64_t send_latency_lo_ns = 1000000, send_latency_hi_ns = 10000000;  // 1 ms..10 ms
+  } net;
+  bool buggify = false;
+  msim_config to_c(uint64_t time_limit_ns = 0) const {
+    msim_config c{};
+    c.packet_loss_rate = net.packet_loss_rate;
+    c.send_latency_lo_ns = net.send_latency_lo_ns;
+    c.send_latency_hi_ns = net.send_latency_hi_ns;
+    c.time_limit_ns = time_limit_ns;
+    c.buggify = buggify ? 1 : 0;
+    return c;
+  }
+};
+
+struct Workload {
+  msim_workload_desc desc{};
+  static Workload sleep(uint64_t duration_ns) {
+    Workload w;
+    check(msim_workload_default(MSIM_WL_SLEEP, &w.desc));
+    w.desc.p[0] = duration_ns;
+    return w;
+  }
+  static Workload pingpong(uint64_t rounds = 1000, uint64_t think_ns = 10000000) {
+    Workload w;
+    check(msim_workload_default(MSIM_WL_PINGPONG, &w.desc));
+    w.desc.p[0] = rounds, w.desc.p[1] = think_ns;
+    return w;
+  }
+  static Workload raft(uint32_t n_nodes = 5, uint64_t duration_ms = 10000, uint32_t faults = 0, uint32_t bug = 0) {
+    Workload w;
+    check(msim_workload_default(MSIM_WL_RAFT, &w.desc));
+    w.desc.n_nodes = n_nodes, w.desc.p[0] = duration_ms, w.desc.p[1] = faults, w.desc.p[2] = bug;
+    return w;
+  }
+  static Workload chaos(uint64_t rounds = 8, uint64_t period_ms = 2000, uint64_t panics = 0) {
+    Workload w;
+    check(msim_workload_default(MSIM_WL_CHAOS, &w.desc));
+    w.desc.p[0] = rounds, w.desc.p[1] = period_ms, w.desc.p[2] = panics;
+    return w;
+  }
+};
+
+namespace runtime {
+
+/// RAII owner of a msim_batch
+class Batch {
+ public:
+  Batch(const Config& cfg, uint64_t time_limit_ns, int device) {
+    msim_config c = cfg.to_c(time_limit_ns);
+    check(msim_batch_create(&c, device, &b_));
+  }
+  ~Batch() { msim_batch_destroy(b_); }
+  Batch(const Batch&) = delete;
+  Batch& operator=(const Batch&) = delete;
+  msim_batch* get() const { return b_; }
+
+ private:
+  msim_batch* b_ = nullptr;
+};
+
+struct RunOutput {
+  std::vector<msim_seed_result> results;
+  msim_stats stats{};
+};
+
+inline RunOutput run_seeds(const Config& cfg, uint64_t time_limit_ns, const Workload& wl, uint64_t seed, uint64_t count,
+                           int device = 0) {
+  Batch b(cfg, time_limit_ns, device);
+  check(msim_workload_load(b.get(), &wl.desc));
+  check(msim_batch_run(b.get(), seed, count, 0));
+  RunOutput out;
+  out.results.resize(count);
+  check(msim_batch_results(b.get(), out.results.data(), nullptr, &out.stats));
+  return out;
+}
+
+/// madsim::runtime::Runtime — one seed
+class Runtime {
+ public:
+  Runtime() : Runtime(0, Config{}) {}
+  static Runtime with_seed_and_config(uint64_t seed, Config cfg) { return Runtime(seed, std::move(cfg)); }
+  void set_time_limit(uint64_t ns) { time_limit_ns_ = ns; }
+  uint64_t seed() const { return seed_; }
+  /// Runs the program to completion; a failing seed is the reference's panic
+  msim_seed_result block_on(const Workload& wl) const {
+    RunOutput o = run_seeds(cfg_, time_limit_ns_, wl, seed_, 1);
+    const msim_seed_result& r = o.results[0];
+    if (r.status != MSIM_ST_PASS) throw SimulationFailure(seed_, r.status, r.fail_code);
+    return r;
+  }
+  /// Runtime::check_determinism: run the seed twice and compare the event traces
+  static msim_seed_result check_determinism(uint64_t seed, Config cfg, const Workload& wl) {
+    Runtime rt(seed, std::move(cfg));
+    msim_seed_result a = rt.block_on(wl), b2 = rt.block_on(wl);
+    if (a.trace_hash != b2.trace_hash || a.draws != b2.draws) throw std::runtime_error("non-determinism detected");
+    return a;
+  }
+
+ private:
+  Runtime(uint64_t seed, Config cfg) : seed_(seed), cfg_(std::move(cfg)) {}
+  uint64_t seed_;
+  Config cfg_;
+  uint64_t time_limit_ns_ = 0;
+};
+
+/// madsim::runtime::Builder — the many-seed test driver behind #[madsim::test]
+struct Builder {
+  uint64_t seed = 0;
+  uint64_t count = 1;
+  uint64_t jobs = 1;  // MADSIM_TEST_JOBS: GPUs a sweep may use (one process per GPU shards the range)
+  Config config;
+  uint64_t time_limit_ns = 0;
+  bool check = false;
+
+  static Builder from_env() {
+    Builder b;
+    if (const char* s = std::getenv("MADSIM_TEST_SEED")) b.seed = std::strtoull(s, nullptr, 10);
+    if (const char* s = std::getenv("MADSIM_TEST_NUM")) b.count = std::strtoull(s, nullptr, 10);
+    if (const char* s = std::getenv("MADSIM_TEST_JOBS")) b.jobs = std::strtoull(s, nullptr, 10);
+    if (const char* s = std::getenv("MADSIM_TEST_TIME_LIMIT")) b.time_limit_ns = uint64_t(std::strtod(s, nullptr) * 1e9);
+    b.check = std::getenv("MADSIM_TEST_CHECK_DETERMINISM") != nullptr;
+    return b;
+  }
+  /// seeds seed..seed+count; throws SimulationFailure for the FIRST failing seed (builder.rs:155-159)
+  RunOutput run(const Workload& wl, int device = 0) const {
+    RunOutput o = run_seeds(config, time_limit_ns, wl, seed, count, device);
+    if (check) {
+      RunOutput o2 = run_seeds(config, time_limit_ns, wl, seed, count, device);
+      for (uint64_t i = 0; i < count; i++)
+        if (o.results[i].trace_hash != o2.results[i].trace_hash)
+          throw std::runtime_error("non-determinism detected (seed " + std::to_string(seed + i) + ")");
+    }
+    if (o.stats.n_fail) {
+      const msim_seed_result& r = o.results[o.stats.first_fail_seed - seed];
+      throw SimulationFailure(o.stats.first_fail_seed, r.status, r.fail_code);
+    }
+    return o;
+  }
+};
+
+}  // namespace runtime
+}  // namespace madsim

@@ -93,3 +93,16 @@ def test_summary_from_results_matches_manual():
     c, bm = D.summary_from_results(res, 1000)
     assert list(c[:6]) == [700, 1400, 2100, 66, 3, 1] and int(c[6]) == 1003 and int(c[7]) == 70
     assert bm[0] == (1 << 3) and bm[1] == (1 << 8) and bm[2] == (1 << 5)
+
+
+def test_cpp_host_header_compiles_and_fails_loudly_without_device():
+    """The C++ host mirror builds against the C-ABI; without a GPU it must refuse to run."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "tests", "cpp", "host_api_test")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "host_api_test.cpp"), "-L" + os.path.join(ROOT, "madsim_b200"),
+                    "-lmsim_b200", "-Wl,-rpath," + os.path.join(ROOT, "madsim_b200")], check=True)
+    if not os.path.exists("/dev/nvidia0"):
+        p = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert p.returncode == 2 and "no CPU fallback" in p.stdout

@@ -239,3 +239,19 @@ def test_sharded_run_single_rank_and_device_summary():
     assert out["first_fail_seed"] == (None if st["n_fail"] == 0 else st["first_fail_seed"])
     assert np.array_equal(bitmap.cpu().numpy().view(np.uint32), bm)
     run.close()
+
+
+def test_cpp_host_api_program():
+    """include/msim_b200.hpp (C++ mirror of madsim::runtime::{Runtime, Builder}) driving the C-ABI:
+    the reference's unit tests for the path, written as they read in Rust (tests/cpp/host_api_test.cpp)."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "host_api_test")
+    src = os.path.join(root, "tests", "cpp", "host_api_test.cpp")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, src, "-L" + os.path.join(root, "madsim_b200"),
+                        "-lmsim_b200", "-Wl,-rpath," + os.path.join(root, "madsim_b200")], check=True)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "HOST API TEST PASSED" in p.stdout, p.stdout + p.stderr

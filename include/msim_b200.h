@@ -104,6 +104,7 @@ typedef struct msim_config {
 #define MSIM_WL_PINGPONG 1  /* 2-node ping-pong, BASELINE config 1 (endpoint.rs:550-584)       */
 #define MSIM_WL_RAFT 2      /* 5-node Raft leader election, BASELINE configs 2 and 3           */
 #define MSIM_WL_CHAOS 3     /* kill/restart/pause supervisor schedule (task/mod.rs:852-1016)   */
+#define MSIM_WL_STREAM 4    /* reliable connect1/accept1 echo stream under partitions (net/mod.rs:337-430) */
 
 /* parameter slots p[] per workload
  *  SLEEP    p0 = duration ns
@@ -111,6 +112,7 @@ typedef struct msim_config {
  *  RAFT     p0 = virtual duration ms (default 10000), p1 = fault mask (MSIM_RAFT_FAULT_*),
  *           p2 = bug mode (0 none, 1 double-vote), p3 = rpc timeout ms (default 40),
  *           p4 = heartbeat ms (default 50), p5 = election timeout lo ms (150), p6 = hi ms (300)
+ *  STREAM   p0 = messages, p1 = think time ns, p2 = faults (1 = partition schedule)
  *  CHAOS    p0 = rounds, p1 = period ms, p2 = worker panics on its first p2 starts (restart_on_panic)
  *                                                         */
 #define MSIM_RAFT_FAULT_CLOG_NODE 1u

@@ -34,6 +34,7 @@ from ._native import (  # noqa: F401
     WL_PINGPONG,
     WL_RAFT,
     WL_SLEEP,
+    WL_STREAM,
     MsimError,
 )
 

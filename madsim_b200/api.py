@@ -98,11 +98,16 @@ class Workload:
         `panics` > 0 the worker panics on its first starts under restart_on_panic (:939-963)."""
         return Workload(N.WL_CHAOS, 1, [rounds, period_ms, panics, 0, 0, 0, 0, 0])
 
+    @staticmethod
+    def stream(messages: int = 200, think_ns: int = 5 * MS, faults: int = 1) -> "Workload":
+        """reliable-channel echo (connect1/accept1/Sender/Receiver, net/mod.rs:337-430) under partitions."""
+        return Workload(N.WL_STREAM, 2, [messages, think_ns, faults, 0, 0, 0, 0, 0])
+
     def to_c(self) -> N.MsimWorkloadDesc:
         return N.MsimWorkloadDesc(self.workload, self.n_nodes, (C.c_uint64 * 8)(*[int(x) for x in self.p]))
 
     def name(self) -> str:
-        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos"}.get(self.workload, "?")
+        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos", 4: "stream"}.get(self.workload, "?")
 
 
 class SimulationFailure(AssertionError):

@@ -45,6 +45,9 @@ enum : u8 {
   W_CALL_RX = 7,     // call_timeout: inside call's recv_from_raw (oneshot)
   W_CALL_DELAY = 8,  // call_timeout: inside call's post-receipt rand_delay
   W_JOIN = 9,        // JoinHandle.await
+  W_CONNECT = 10,    // connect1: rand_delay, then the connection request (net/mod.rs:337-364)
+  W_ACCEPT = 11,     // accept1: rand_delay FIRST, then the next incoming connection (endpoint.rs:197-211)
+  W_CH_RECV = 12,    // Receiver::recv: the channel's delay/back-off stream (net/mod.rs:385-402)
   WF_RD = 0x10,      // rand_delay not drawn yet: draw it now, then sleep on dl0
   WF_SLEEP = 0x20,   // sleeping on dl0
 };
@@ -66,8 +69,12 @@ enum : int {
   RQ_GEN_RANGE,     // thread_rng().gen_range(xa..xb) (u64)                -> ret64
   RQ_JOIN,          // JoinHandle(ya = task slot).await                   -> ret (1 ok / 2 cancelled), rv0 = output
   RQ_ADVANCE,       // time::advance(xa ns)
+  RQ_CONNECT1,      // ep.connect1(ya = addr)          -> ret 0 (the task now holds the connection end) / -1 refused
+  RQ_ACCEPT1,       // ep.accept1()                    -> ret 0, rfrom = peer address
+  RQ_CH_SEND,       // conn.tx.send({yb, yc})          -> ret 0 / -1 ConnectionReset   (no await point)
+  RQ_CH_RECV,       // conn.rx.recv()                  -> ret 0, rv0, rv1 / -1 ConnectionReset
 };
-enum : u32 { SPAWN_EP = 0x100, SPAWN_JOINABLE = 0x200 };  // clone the caller's Endpoint / keep a JoinHandle
+enum : u32 { SPAWN_EP = 0x100, SPAWN_JOINABLE = 0x200, SPAWN_CONN = 0x400 };  // clone the Endpoint / keep a JoinHandle / move the connection end
 enum : u32 { NODE_IP = 1, NODE_INIT = 2, NODE_RESTART_ON_PANIC = 4 };
 enum : int { CALL_OK = 1, CALL_TIMEOUT = 2 };
 
@@ -91,7 +98,13 @@ struct Layout {
   static constexpr int Q_M_W = Q_M_TAG + C::NMSG;           // [NMSG] payload.w (rpc response tag)
   static constexpr int Q_RG_TAG = Q_M_W + C::NMSG;          // [NSOCK*NREG] registered receive tags
   static constexpr int Q_WL = Q_RG_TAG + C::NSOCK * C::NREG;  // [WQ*NNODE] workload per-node u64
-  static constexpr int NQ = Q_WL + C::WQ * C::NNODE;
+  // reliable channels: direction d = 2*conn + side (0: connector->acceptor, 1: the reverse)
+  static constexpr int ND = 2 * C::NCONN;
+  static constexpr int Q_CH_ARRIVE = Q_WL + C::WQ * C::NNODE;  // [ND*NCQ] queued item's link state: arrive time or NONE64
+  static constexpr int Q_CH_CUR = Q_CH_ARRIVE + ND * C::NCQ;   // [ND] link state of the item the stream is delaying
+  static constexpr int Q_CH_DL = Q_CH_CUR + ND;                // [ND] the stream's Sleep deadline
+  static constexpr int Q_CH_BACKOFF = Q_CH_DL + ND;            // [ND]
+  static constexpr int NQ = Q_CH_BACKOFF + ND;
   // ---- u32 section ----
   enum : int {
     W_EV_POP = 0, W_EV_FIRE, W_HEAP_LEN, W_RQ_LEN, W_NEXT_SPAWN, W_MSG_COUNT, W_STATUS, W_FAIL_CODE,
@@ -114,7 +127,15 @@ struct Layout {
   static constexpr int W_SK_PORTGEN = W_RG_WAITER + C::NSOCK * C::NREG;  // [NSOCK] port | gen<<16
   static constexpr int W_WL = W_SK_PORTGEN + C::NSOCK;          // [WW*NNODE] workload per-node u32
   static constexpr int W_WLS = W_WL + C::WW * C::NNODE;         // [WS] workload scalars
-  static constexpr int NW = W_WLS + C::WS;
+  static constexpr int W_CH_V0 = W_WLS + C::WS;                 // [ND*NCQ] queued payloads
+  static constexpr int W_CH_V1 = W_CH_V0 + ND * C::NCQ;
+  static constexpr int W_CH_CUR_V0 = W_CH_V1 + ND * C::NCQ;     // [ND]
+  static constexpr int W_CH_CUR_V1 = W_CH_CUR_V0 + ND;
+  static constexpr int W_CH_DST = W_CH_CUR_V1 + ND;             // [ND] test_link destination address
+  static constexpr int W_CH_WAITER = W_CH_DST + ND;             // [ND] mpsc rx_waker (slot<<20|gen) or NONE32
+  static constexpr int W_CONN_SRC = W_CH_WAITER + ND;           // [NCONN] connector's source address
+  static constexpr int W_ACC_WAITER = W_CONN_SRC + C::NCONN;    // [NSOCK] task waiting in accept1
+  static constexpr int NW = W_ACC_WAITER + C::NSOCK;
   // ---- u8 section ----
   static constexpr int B_RQ = 0;                        // [NT] ready "queue": a Vec popped at a random index
   static constexpr int B_T_KIND = B_RQ + C::NT;
@@ -138,7 +159,16 @@ struct Layout {
   static constexpr int B_N_FLAGS = B_SK_EPOCH + C::NSOCK;  // [NNODE]
   static constexpr int B_N_EPOCH = B_N_FLAGS + C::NNODE;
   static constexpr int B_PK = B_N_EPOCH + C::NNODE;        // [NPARK] parked runnables, park order
-  static constexpr int NB = B_PK + C::NPARK;
+  static constexpr int B_T_CONN = B_PK + C::NPARK;         // [NT] connection end the future holds: conn<<1|side, or NONE8
+  static constexpr int B_CH_HEAD = B_T_CONN + C::NT;       // [ND] FIFO head / length
+  static constexpr int B_CH_LEN = B_CH_HEAD + ND;
+  static constexpr int B_CH_PHASE = B_CH_LEN + ND;         // [ND] 0 idle, 1 back-off sleep, 2 arrival sleep
+  static constexpr int B_CH_SRC = B_CH_PHASE + ND;         // [ND] test_link source node
+  static constexpr int B_CH_FLAGS = B_CH_SRC + ND;         // [ND] CH_TX_ALIVE | CH_RX_ALIVE
+  static constexpr int B_CONN_USED = B_CH_FLAGS + ND;      // [NCONN]
+  static constexpr int B_ACC = B_CONN_USED + C::NCONN;     // [NSOCK*NACC] incoming connections (async_channel)
+  static constexpr int B_ACC_LEN = B_ACC + C::NSOCK * C::NACC;
+  static constexpr int NB = B_ACC_LEN + C::NSOCK;
 
   static constexpr int W_BASE = 8 * NQ;                 // byte offset of the u32 section
   static constexpr int B_BASE = W_BASE + 4 * NW;        // ... of the u8 section
@@ -179,6 +209,7 @@ struct Engine {
   MSIM_HD u8& t_sock(int t) const { return b(L::B_T_SOCK, t); }
   MSIM_HD u8& t_sockgen(int t) const { return b(L::B_T_SOCKGEN, t); }
   MSIM_HD u8& t_msg(int t) const { return b(L::B_T_MSG, t); }
+  MSIM_HD u8& t_conn(int t) const { return b(L::B_T_CONN, t); }
   MSIM_HD u32& t_spawn(int t) const { return w(L::W_T_SPAWN, t); }
   MSIM_HD u32& t_aw(int t) const { return w(L::W_T_AW, t); }
   MSIM_HD u32& t_a(int t) const { return w(L::W_T_A, t); }
@@ -426,6 +457,7 @@ struct Engine {
         t_msg(t) = NONE8;
       }
       if (st == W_JOIN) join_detach((int)t_c(t));
+      if (C::NCONN) conn_drop_end(t);
       sock_unref(t);
       t_wait(t) = W_NONE;
       t_flags(t) = f & ~TF_ALIVE;
@@ -484,6 +516,7 @@ MSIM_NOUNROLL
     t_rx(t) = NONE8;
     t_sock(t) = NONE8;
     t_msg(t) = NONE8;
+    if (C::NCONN) t_conn(t) = NONE8;
     t_spawn(t) = idx;
     t_aw(t) = NONE32;
     u32 live = ++w(L::W_LIVE_TASKS);
@@ -763,6 +796,8 @@ MSIM_NOUNROLL
     for (u32 i = 0; i < ml; i++) msg_free(b(L::B_MB, k * C::NMBOX + i));
     b(L::B_SK_MBLEN, k) = 0;
     b(L::B_SK_REGLEN, k) = 0;
+    b(L::B_ACC_LEN, k) = 0;  // pending incoming connections die with the socket object
+    w(L::W_ACC_WAITER, k) = NONE32;
     sk_state(k) = 0;
     w(L::W_SK_PORTGEN, k) = (w(L::W_SK_PORTGEN, k) & 0xffff0000u) + 0x10000u;  // gen++ : stale refs miss
   }
@@ -814,10 +849,9 @@ MSIM_NOUNROLL
     }
     return sleep_deadline(now + delay);
   }
-  /// The part of NetSim::send after rand_delay (net/mod.rs:304-332) + Network::try_send
-  /// (network.rs:296-313).  `m` is a prepared message slot (tag, w, v0, v1); consumed.
-  MSIM_HD void net_send(int src_node, u32 src_port, u32 dst, int m) {
-    // resolve_dest_node (network.rs:273-291)
+  /// Network::try_send (network.rs:296-313) with resolve_dest_node (:273-291) and test_link
+  /// (:261-270): the destination socket or -1; `latency` is valid on success only.
+  MSIM_HD int try_send(int src_node, u32 dst, u64& latency) {
     int dst_node = -1;
     u32 ipk = addr_ipk(dst), dport = addr_port(dst);
     bool own = (ipk != IPK_NODE || (int)addr_node(dst) == src_node) && sock_find(src_node, ipk, dport) >= 0;
@@ -827,25 +861,98 @@ MSIM_NOUNROLL
                (n_flags(addr_node(dst)) & NF_HAS_IP)) {
       dst_node = (int)addr_node(dst);
     }
-    // "ip not set" / destination not found: before any draw.  test_link (network.rs:261-270):
-    // `clogged || gen_bool(loss)` — no draw when clogged
-    if (dst_node < 0 || link_clogged(src_node, dst_node) || P->loss_always || next_u64() < P->loss_p_int) {
-      msg_free(m);
-      return;
-    }
-    u32 serial = ++w(L::W_MSG_COUNT);
-    u64 latency = sample_latency();
+    // "ip not set" / destination not found: before any draw.  `clogged || gen_bool(loss)`: no
+    // draw when clogged
+    if (dst_node < 0 || link_clogged(src_node, dst_node) || P->loss_always || next_u64() < P->loss_p_int) return -1;
+    ++w(L::W_MSG_COUNT);
+    latency = sample_latency();
     // socket lookup AFTER the draws: exact address, then (UNSPECIFIED, port)
     int k = sock_find(dst_node, ipk, dport);
     if (k < 0 && ipk != IPK_UNSPEC) k = sock_find(dst_node, IPK_UNSPEC, dport);
+    return k;
+  }
+  MSIM_HD u32 src_addr_for(u32 dst, int src_node, u32 src_port) const {
+    return mk_addr(addr_ipk(dst) == IPK_LOOPBACK ? IPK_LOOPBACK : IPK_NODE, src_node, src_port);
+  }
+  /// The part of NetSim::send after rand_delay (net/mod.rs:304-332).  `m` is a prepared message
+  /// slot (tag, w, v0, v1); consumed.
+  MSIM_HD void net_send(int src_node, u32 src_port, u32 dst, int m) {
+    u64 latency;
+    int k = try_send(src_node, dst, latency);
     if (k < 0) {
       msg_free(m);
       return;
     }
-    w(L::W_M_FROM, m) = mk_addr(ipk == IPK_LOOPBACK ? IPK_LOOPBACK : IPK_NODE, src_node, src_port);
+    w(L::W_M_FROM, m) = src_addr_for(dst, src_node, src_port);
     w(L::W_M_DST, m) = ((u32)k << 16) | (sk_gen(k) & 0xffff);
-    w(L::W_M_SERIAL, m) = serial & 0xffffffu;
+    w(L::W_M_SERIAL, m) = w(L::W_MSG_COUNT) & 0xffffffu;
     timer_push(now + latency, timer_payload(TK_DELIVER, m, 0));
+  }
+
+  // ---------------- reliable channels (net/mod.rs:337-430, endpoint.rs:178-274) ----------------
+  enum : u8 { CH_TX_ALIVE = 1, CH_RX_ALIVE = 2 };
+  static constexpr u64 NONE64 = ~0ull;
+  MSIM_HD u8& ch_flags(int d) const { return b(L::B_CH_FLAGS, d); }
+  MSIM_HD void wake_waiter(u32& slot_word) {
+    u32 wv = slot_word;
+    if (wv != NONE32) {  // AtomicWaker::wake takes the waker
+      slot_word = NONE32;
+      wake(wv >> 20, wv & 0xfffffu);
+    }
+  }
+  /// channel()'s test_link closure: try_send(node, dst).map(|lat| now + lat)
+  MSIM_HD u64 ch_test_link(int d) {
+    u64 lat;
+    int k = try_send(b(L::B_CH_SRC, d), w(L::W_CH_DST, d), lat);
+    return k < 0 ? NONE64 : now + lat;
+  }
+  /// NetSim::connect1 after rand_delay.  0 ok / -1 ConnectionRefused
+  MSIM_HD int connect1(int t, u32 dst) {
+    int ks = t_sock(t);
+    int node = b(L::B_SK_NODE, ks);
+    u64 lat;
+    int k = try_send(node, dst, lat);  // the latency is drawn but not used (the reference's FIXME)
+    if (k < 0) return -1;
+    int c = 0;
+    while (c < C::NCONN && b(L::B_CONN_USED, c)) c++;
+    u32 al = b(L::B_ACC_LEN, k);
+    if (c >= C::NCONN || al >= (u32)C::NACC) {
+      fail_cap(MSIM_CAP_SOCKETS);
+      return -1;
+    }
+    u32 src = src_addr_for(dst, node, sk_port(ks));
+    b(L::B_CONN_USED, c) = 1;
+    w(L::W_CONN_SRC, c) = src;
+    for (int side = 0; side < 2; side++) {
+      int d = 2 * c + side;
+      b(L::B_CH_HEAD, d) = 0;
+      b(L::B_CH_LEN, d) = 0;
+      b(L::B_CH_PHASE, d) = 0;
+      ch_flags(d) = CH_TX_ALIVE | CH_RX_ALIVE;
+      w(L::W_CH_WAITER, d) = NONE32;
+    }
+    b(L::B_CH_SRC, 2 * c) = (u8)node;  // channel(node, dst)
+    w(L::W_CH_DST, 2 * c) = dst;
+    b(L::B_CH_SRC, 2 * c + 1) = b(L::B_SK_NODE, k);  // channel(dst_node, src)
+    w(L::W_CH_DST, 2 * c + 1) = src;
+    // socket.new_connection(..): conn_tx.try_send — delivered immediately
+    b(L::B_ACC, k * C::NACC + al) = (u8)c;
+    b(L::B_ACC_LEN, k) = (u8)(al + 1);
+    wake_waiter(w(L::W_ACC_WAITER, k));
+    t_conn(t) = (u8)(2 * c);
+    return 0;
+  }
+  /// Dropping a Sender + Receiver pair (one end of a connection)
+  MSIM_HD void conn_drop_end(int t) {
+    int e = t_conn(t);
+    if (e == NONE8) return;
+    t_conn(t) = NONE8;
+    int c = e >> 1, side = e & 1;
+    int d_tx = 2 * c + side, d_rx = 2 * c + (side ^ 1);
+    ch_flags(d_tx) &= ~CH_TX_ALIVE;  // last UnboundedSender dropped: the peer's recv wakes and drains
+    wake_waiter(w(L::W_CH_WAITER, d_tx));
+    ch_flags(d_rx) &= ~CH_RX_ALIVE;  // UnboundedReceiver dropped: the peer's send fails
+    if (!((ch_flags(d_tx) | ch_flags(d_rx)) & (CH_TX_ALIVE | CH_RX_ALIVE))) b(L::B_CONN_USED, c) = 0;
   }
   /// Timer callback of NetSim::send -> EndpointSocket::deliver -> Mailbox::deliver
   /// (endpoint.rs:310-351).  The target socket OBJECT was captured at send time: if it has
@@ -984,6 +1091,7 @@ MSIM_NOUNROLL
     n_flags(0) = NF_EXISTS;
     w(L::W_NEXT_NODE) = 1;
     w(L::W_RESUME) = NONE32;
+    for (int k = 0; k < C::NSOCK; k++) w(L::W_ACC_WAITER, k) = NONE32;
     int m = spawn(WL::MAIN_KIND, 0, TF_JOINABLE);
     w(L::W_MAIN_SLOT) = (u32)m;
   }
@@ -1102,6 +1210,81 @@ MSIM_NOUNROLL
               ret = CALL_OK;
               if (rfrom != t_c(t)) return panic(31);  // assert_eq!(from, dst) (rpc.rs:125)
               break;
+            case W_CONNECT:
+              ret = connect1(t, (u32)t_dl1(t));
+              wt = W_NONE;
+              break;
+            case W_ACCEPT: {  // conn_rx.recv().await (async_channel): FIFO
+              u32 al = b(L::B_ACC_LEN, k);
+              if (al == 0) {
+                w(L::W_ACC_WAITER, k) = ((u32)t << 20) | t_gen(t);
+                pend = true;
+              } else {
+                int c = b(L::B_ACC, k * C::NACC);
+                for (u32 i = 1; i < al; i++) b(L::B_ACC, k * C::NACC + i - 1) = b(L::B_ACC, k * C::NACC + i);
+                b(L::B_ACC_LEN, k) = (u8)(al - 1);
+                t_conn(t) = (u8)(2 * c + 1);
+                rfrom = w(L::W_CONN_SRC, c);
+                ret = 0;
+                wt = W_NONE;
+              }
+              break;
+            }
+            case W_CH_RECV: {  // poll_next of the channel's stream (net/mod.rs:385-402)
+              int e = t_conn(t);
+              int d = 2 * (e >> 1) + ((e & 1) ^ 1);
+              for (;;) {
+                u8 ph = b(L::B_CH_PHASE, d);
+                if (ph == 0) {  // rx.recv().await
+                  u32 len = b(L::B_CH_LEN, d);
+                  if (len == 0) {
+                    if (!(ch_flags(d) & CH_TX_ALIVE)) {  // None: every sender is gone
+                      ret = -1;
+                      wt = W_NONE;
+                    } else {
+                      w(L::W_CH_WAITER, d) = ((u32)t << 20) | t_gen(t);
+                      pend = true;
+                    }
+                    break;
+                  }
+                  u32 h = b(L::B_CH_HEAD, d);
+                  q(L::Q_CH_CUR, d) = q(L::Q_CH_ARRIVE, d * C::NCQ + h);
+                  w(L::W_CH_CUR_V0, d) = w(L::W_CH_V0, d * C::NCQ + h);
+                  w(L::W_CH_CUR_V1, d) = w(L::W_CH_V1, d * C::NCQ + h);
+                  b(L::B_CH_HEAD, d) = (u8)((h + 1) % C::NCQ);
+                  b(L::B_CH_LEN, d) = (u8)(len - 1);
+                  q(L::Q_CH_BACKOFF, d) = NS_PER_MS;
+                } else {  // the stream's Sleep
+                  u64 dl = q(L::Q_CH_DL, d);
+                  if (now < dl) {
+                    timer_push(dl, timer_payload(TK_WAKE, t, t_gen(t)));
+                    pend = true;
+                    break;
+                  }
+                  if (ph == 2) {  // sleep_until(arrive) done: yield value
+                    b(L::B_CH_PHASE, d) = 0;
+                    rv0 = w(L::W_CH_CUR_V0, d);
+                    rv1 = w(L::W_CH_CUR_V1, d);
+                    ret = 0;
+                    wt = W_NONE;
+                    break;
+                  }
+                  u64 bo = q(L::Q_CH_BACKOFF, d) * 2;  // backoff = (backoff * 2).min(10 s); retry
+                  q(L::Q_CH_BACKOFF, d) = bo > 10 * NS_PER_SEC ? 10 * NS_PER_SEC : bo;
+                  q(L::Q_CH_CUR, d) = ch_test_link(d);
+                }
+                // wait until the link is ready: Some(arrive) -> sleep_until(arrive); None -> sleep(backoff)
+                u64 st8 = q(L::Q_CH_CUR, d);
+                if (st8 != NONE64) {
+                  q(L::Q_CH_DL, d) = sleep_deadline(st8);
+                  b(L::B_CH_PHASE, d) = 2;
+                } else {
+                  q(L::Q_CH_DL, d) = sleep_deadline(now + q(L::Q_CH_BACKOFF, d));
+                  b(L::B_CH_PHASE, d) = 1;
+                }
+              }
+              break;
+            }
             case W_JOIN: {
               int target = (int)t_c(t);
               int r = join_poll(t, target);
@@ -1195,6 +1378,10 @@ MSIM_NOUNROLL
           t_c(c) = (u32)xa;
           t_dl1(c) = xb;
           if (ya & SPAWN_EP) sock_ref(c, t_sock(t));
+          if (C::NCONN && (ya & SPAWN_CONN)) {
+            t_conn(c) = t_conn(t);
+            t_conn(t) = NONE8;
+          }
           break;
         }
         case RQ_GEN_RANGE:
@@ -1204,6 +1391,38 @@ MSIM_NOUNROLL
           t_c(t) = ya;
           t_wait(t) = W_JOIN;
           break;
+        case RQ_CONNECT1:
+          t_dl1(t) = ya;
+          t_wait(t) = W_CONNECT | WF_RD;
+          break;
+        case RQ_ACCEPT1:
+          t_wait(t) = W_ACCEPT | WF_RD;
+          break;
+        case RQ_CH_RECV:
+          t_wait(t) = W_CH_RECV;
+          break;
+        case RQ_CH_SEND: {  // PayloadSender::send: state = test_link(); tx.send((value, state)).ok()
+          int e = t_conn(t);
+          int d = 2 * (e >> 1) + (e & 1);
+          u64 st8 = ch_test_link(d);
+          if (!(ch_flags(d) & CH_RX_ALIVE)) {
+            ret = -1;  // ConnectionReset
+            break;
+          }
+          u32 len = b(L::B_CH_LEN, d);
+          if (len >= (u32)C::NCQ) {
+            fail_cap(MSIM_CAP_MSGS);
+            return POLL_PENDING;
+          }
+          u32 pos = (b(L::B_CH_HEAD, d) + len) % C::NCQ;
+          q(L::Q_CH_ARRIVE, d * C::NCQ + pos) = st8;
+          w(L::W_CH_V0, d * C::NCQ + pos) = yb;
+          w(L::W_CH_V1, d * C::NCQ + pos) = yc;
+          b(L::B_CH_LEN, d) = (u8)(len + 1);
+          wake_waiter(w(L::W_CH_WAITER, d));
+          ret = 0;
+          break;
+        }
         case RQ_ADVANCE:  // time::advance (time/mod.rs:103-106,195-198): clock += d, then the due timers fire
           now += xa;      // inside this poll: the event loop fires them at its single expire site and
           return POLL_ADVANCE;  // re-enters this poll (W_RESUME) before anything else runs

@@ -32,6 +32,12 @@ inline int workload_defaults(uint32_t workload, msim_workload_desc* d) {
       d->p[5] = 150;
       d->p[6] = 300;
       return 0;
+    case MSIM_WL_STREAM:
+      d->n_nodes = 2;
+      d->p[0] = 200;
+      d->p[1] = 5 * NS_PER_MS;
+      d->p[2] = 1;
+      return 0;
     case MSIM_WL_CHAOS:
       d->n_nodes = 1;
       d->p[0] = 8;
@@ -118,6 +124,12 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
       }
       if (wl.p[1] > 7) {
         if (err) *err = "raft: unknown fault mask bits";
+        return MSIM_EINVAL;
+      }
+      break;
+    case MSIM_WL_STREAM:
+      if (wl.p[2] > 1) {
+        if (err) *err = "stream: unknown fault bits";
         return MSIM_EINVAL;
       }
       break;

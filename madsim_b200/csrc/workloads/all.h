@@ -3,4 +3,5 @@
 #include "pingpong.h"
 #include "raft.h"
 #include "sleep.h"
+#include "stream.h"
 #define MSIM_HAVE_RAFT 1

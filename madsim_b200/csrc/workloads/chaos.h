@@ -13,6 +13,7 @@ struct WL_Chaos {
   struct Caps {
     static constexpr int NT = 8, TQ = 32, NMSG = 1, NSOCK = 1, NREG = 1, NMBOX = 1, NNODE = 2, NPARK = 4;
     static constexpr int WQ = 0, WW = 0, WS = 2;
+    static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 { K_MAIN = 0, K_WORKER = 1 };
   static constexpr u32 MAIN_KIND = K_MAIN;

@@ -26,6 +26,7 @@ struct WL_Raft {
   struct Caps {
     static constexpr int NT = 64, TQ = 176, NMSG = 48, NSOCK = 6, NREG = 12, NMBOX = 16, NNODE = 6, NPARK = 2;
     static constexpr int WQ = 1, WW = 6, WS = 1;
+    static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 {
     K_MAIN = 0, K_FAULT, K_NODE, K_LOOP_VOTE, K_LOOP_APPEND, K_REQ_VOTE, K_REQ_APPEND, K_VOTE, K_APPEND, K_LEADER

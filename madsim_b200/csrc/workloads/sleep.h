@@ -9,6 +9,7 @@ struct WL_Sleep {
   struct Caps {
     static constexpr int NT = 2, TQ = 8, NMSG = 1, NSOCK = 1, NREG = 1, NMBOX = 1, NNODE = 1, NPARK = 1;
     static constexpr int WQ = 0, WW = 0, WS = 0;
+    static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   static constexpr u32 MAIN_KIND = 0;
   static MSIM_HD int init_kind(int) { return -1; }

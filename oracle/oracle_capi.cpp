@@ -74,6 +74,10 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
         rt.teardown();
         break;
       }
+      case MSIM_WL_STREAM:
+        rt.block_on(wl_stream_main(wl->p[0], wl->p[1], u32(wl->p[2]), &user));
+        rt.teardown();
+        break;
       case MSIM_WL_CHAOS:
         rt.block_on(wl_chaos_main(wl->p[0], wl->p[1], u32(wl->p[2]), &user));
         break;

@@ -64,11 +64,16 @@ struct Context {
 
 // ---------------------------------------------------------------------------------------
 // Async<T>: a coroutine that IS a pollable future.
+template <class F, bool Owned>
+struct PollAwaiter;
+
 struct PromiseBase {
   Context* cx = nullptr;                         // valid only during a poll
   void* leaf = nullptr;                          // awaiter of the pending sub-future
   bool (*leaf_poll)(void*, Context&) = nullptr;  // re-poll it; true when Ready
   std::exception_ptr ex;
+  template <class F>
+  auto await_transform(F&& f);
 };
 
 template <class F>
@@ -102,6 +107,15 @@ struct PollAwaiter {
   R await_resume() { return std::move(*result); }
 };
 
+template <class F>
+auto PromiseBase::await_transform(F&& f) {
+  using D = std::decay_t<F>;
+  if constexpr (std::is_lvalue_reference_v<F>)
+    return PollAwaiter<D, false>{&f, this, std::nullopt};
+  else
+    return PollAwaiter<D, true>{std::move(f), this, std::nullopt};
+}
+
 template <class T>
 class [[nodiscard]] Async {
  public:
@@ -112,14 +126,6 @@ class [[nodiscard]] Async {
     std::suspend_always final_suspend() noexcept { return {}; }
     void return_value(T v) { value.emplace(std::move(v)); }
     void unhandled_exception() { this->ex = std::current_exception(); }
-    template <class F>
-    auto await_transform(F&& f) {
-      using D = std::decay_t<F>;
-      if constexpr (std::is_lvalue_reference_v<F>)
-        return PollAwaiter<D, false>{&f, this, std::nullopt};
-      else
-        return PollAwaiter<D, true>{std::move(f), this, std::nullopt};
-    }
   };
   using handle_t = std::coroutine_handle<promise_type>;
   using value_type = T;
@@ -169,6 +175,79 @@ class [[nodiscard]] Async {
 
  private:
   handle_t h_{};
+};
+
+/// async_stream::stream! { .. }: a generator that may both `co_await` futures and `co_yield`
+/// items; `poll_next` is futures::Stream::poll_next (Ready(None) once the body returns).
+template <class T>
+class [[nodiscard]] Stream {
+ public:
+  struct promise_type : PromiseBase {
+    std::optional<T> yielded;
+    Stream get_return_object() { return Stream(std::coroutine_handle<promise_type>::from_promise(*this)); }
+    std::suspend_always initial_suspend() noexcept { return {}; }
+    std::suspend_always final_suspend() noexcept { return {}; }
+    std::suspend_always yield_value(T v) {
+      yielded.emplace(std::move(v));
+      return {};
+    }
+    void return_void() {}
+    void unhandled_exception() { this->ex = std::current_exception(); }
+  };
+  using handle_t = std::coroutine_handle<promise_type>;
+  Stream() = default;
+  explicit Stream(handle_t h) : h_(h) {}
+  Stream(Stream&& o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
+  Stream& operator=(Stream&& o) noexcept {
+    if (this != &o) {
+      reset();
+      h_ = std::exchange(o.h_, nullptr);
+    }
+    return *this;
+  }
+  Stream(const Stream&) = delete;
+  ~Stream() { reset(); }
+  void reset() {
+    if (h_) {
+      h_.destroy();
+      h_ = nullptr;
+    }
+  }
+  Poll<std::optional<T>> poll_next(Context& cx) {
+    using R = Poll<std::optional<T>>;
+    if (!h_ || h_.done()) return R::done(std::nullopt);
+    auto& p = h_.promise();
+    p.cx = &cx;
+    if (p.leaf) {
+      if (!p.leaf_poll(p.leaf, cx)) return R::pending();
+      p.leaf = nullptr;
+    }
+    h_.resume();
+    p.cx = nullptr;
+    if (p.yielded) {
+      std::optional<T> v = std::move(p.yielded);
+      p.yielded.reset();
+      return R::done(std::move(v));
+    }
+    if (h_.done()) {
+      if (p.ex) {
+        auto e = p.ex;
+        p.ex = nullptr;
+        std::rethrow_exception(e);
+      }
+      return R::done(std::nullopt);
+    }
+    return R::pending();
+  }
+
+ private:
+  handle_t h_{};
+};
+/// StreamExt::next()
+template <class T>
+struct StreamNext {
+  Stream<T>* s;
+  Poll<std::optional<T>> poll(Context& cx) { return s->poll_next(cx); }
 };
 
 /// std::future::pending()

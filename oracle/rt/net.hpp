@@ -4,8 +4,10 @@
 // net/mod.rs:82-333,436-494 (NetSim::{rand_delay,send}, BindGuard), net/endpoint.rs:11-175,
 // 290-363 (Endpoint, Mailbox) and net/rpc.rs:82-166 (call / call_timeout / add_rpc_handler),
 // plus tokio::sync::oneshot as used by the mailbox.
-// Reliable channels (connect1/accept1, net/mod.rs:337-430) are SURVEY §8(f) row 1: not here yet.
+// Reliable channels: connect1 / accept1 / Sender / Receiver,
+// net/mod.rs:337-430 + net/endpoint.rs:178-274, over tokio's unbounded mpsc and an async stream.
 #pragma once
+#include <deque>
 #include <map>
 #include <set>
 
@@ -42,10 +44,100 @@ struct NetConfig {  // network.rs:66-89
   u64 send_latency_hi = 10000000ull;  // 10 ms
 };
 
+// ---- tokio::sync::mpsc::unbounded_channel (what net/mod.rs:373 and async_channel's single
+// consumer need): FIFO, recv wakes through one registered waker ----
+template <class T>
+struct MpscState {
+  std::deque<T> q;
+  std::optional<Waker> rx_waker;
+  int tx_count = 0;
+  bool rx_closed = false;
+  void wake_rx() {
+    if (rx_waker) {
+      Waker w = std::move(*rx_waker);
+      rx_waker.reset();
+      w.wake();
+    }
+  }
+};
+template <class T>
+struct UnboundedSender {
+  std::shared_ptr<MpscState<T>> st;
+  UnboundedSender() = default;
+  explicit UnboundedSender(std::shared_ptr<MpscState<T>> s) : st(std::move(s)) {
+    if (st) st->tx_count++;
+  }
+  UnboundedSender(const UnboundedSender& o) : st(o.st) {
+    if (st) st->tx_count++;
+  }
+  UnboundedSender(UnboundedSender&& o) noexcept : st(std::move(o.st)) {}
+  UnboundedSender& operator=(UnboundedSender o) {
+    std::swap(st, o.st);
+    return *this;
+  }
+  ~UnboundedSender() {
+    if (st && --st->tx_count == 0) st->wake_rx();  // closed: the receiver sees None after draining
+  }
+  bool send(T v) const {  // Err if the receiver is gone
+    if (st->rx_closed) return false;
+    st->q.push_back(std::move(v));
+    st->wake_rx();
+    return true;
+  }
+  bool is_closed() const { return st->rx_closed; }
+};
+template <class T>
+struct UnboundedReceiver {
+  std::shared_ptr<MpscState<T>> st;
+  UnboundedReceiver() = default;
+  explicit UnboundedReceiver(std::shared_ptr<MpscState<T>> s) : st(std::move(s)) {}
+  UnboundedReceiver(UnboundedReceiver&&) = default;
+  UnboundedReceiver& operator=(UnboundedReceiver&&) = default;
+  ~UnboundedReceiver() {
+    if (st) st->rx_closed = true;
+  }
+  /// `rx.recv().await`
+  struct RecvFut {
+    UnboundedReceiver* rx;
+    Poll<std::optional<T>> poll(Context& cx) {
+      auto& s = *rx->st;
+      if (!s.q.empty()) {
+        T v = std::move(s.q.front());
+        s.q.pop_front();
+        return Poll<std::optional<T>>::done(std::optional<T>(std::move(v)));
+      }
+      if (s.tx_count == 0) return Poll<std::optional<T>>::done(std::nullopt);
+      s.rx_waker = cx.waker;
+      return Poll<std::optional<T>>::pending();
+    }
+  };
+  RecvFut recv() { return RecvFut{this}; }
+};
+template <class T>
+std::pair<UnboundedSender<T>, UnboundedReceiver<T>> unbounded_channel() {
+  auto st = std::make_shared<MpscState<T>>();
+  return {UnboundedSender<T>(st), UnboundedReceiver<T>(st)};
+}
+
+/// The link state when sending a packet (net/mod.rs:411): Some(arrive time) or None (lost / clogged)
+using LinkState = std::optional<u64>;
+/// net/mod.rs:404-430
+struct PayloadSender {
+  std::shared_ptr<std::function<LinkState()>> test_link;
+  UnboundedSender<std::pair<Payload, LinkState>> tx;
+  bool send(Payload value) const {
+    LinkState state = (*test_link)();
+    return tx.send({value, state});
+  }
+  bool is_closed() const { return tx.is_closed(); }
+};
+using PayloadReceiver = Stream<Payload>;
+
 /// network.rs:51-65
 struct Socket {
   virtual ~Socket() = default;
   virtual void deliver(SocketAddr src, SocketAddr dst, u64 tag, Payload msg) = 0;
+  virtual void new_connection(SocketAddr, SocketAddr, PayloadSender, PayloadReceiver) {}
 };
 
 /// network.rs:20-313
@@ -198,6 +290,59 @@ class NetSim : public SimulatorHooks {
   }
 };
 
+/// net/mod.rs:366-402: the receiving half is an async stream that delays every message until
+/// its arrival time and backs off exponentially (1 ms .. 10 s) while the link is down
+inline PayloadReceiver channel_stream(UnboundedReceiver<std::pair<Payload, LinkState>> rx,
+                                      std::shared_ptr<std::function<LinkState()>> test_link, TimeHandle* time) {
+  for (;;) {
+    auto item = co_await rx.recv();
+    if (!item) break;
+    Payload value = item->first;
+    LinkState state = item->second;
+    // wait until the link is ready
+    u64 backoff = 1000000ull;
+    u64 arrive_time;
+    for (;;) {
+      if (state) {
+        arrive_time = *state;
+        break;
+      }
+      co_await time->sleep(backoff);
+      backoff = std::min<u64>(backoff * 2, 10000000000ull);
+      state = (*test_link)();  // retry
+    }
+    co_await time->sleep_until(arrive_time);
+    co_yield value;
+  }
+}
+
+struct Connect1Ok {
+  PayloadSender tx;
+  PayloadReceiver rx;
+  SocketAddr src;
+};
+inline std::pair<PayloadSender, PayloadReceiver> net_channel(NetSim* net, u64 node, SocketAddr dst, IpProtocol proto) {
+  auto [tx, rx] = unbounded_channel<std::pair<Payload, LinkState>>();
+  auto test_link = std::make_shared<std::function<LinkState()>>([net, node, dst, proto]() -> LinkState {
+    auto ok = net->network.try_send(node, dst, proto);
+    if (!ok) return std::nullopt;
+    return net->time.now_instant() + ok->latency;
+  });
+  PayloadSender sender{test_link, std::move(tx)};
+  return {std::move(sender), channel_stream(std::move(rx), test_link, &net->time)};
+}
+/// net/mod.rs:337-364: the connection request is delivered IMMEDIATELY (the reference's FIXME)
+inline Async<Result<Connect1Ok>> net_connect1(NetSim* net, u64 node, u16 port, SocketAddr dst, IpProtocol proto) {
+  co_await net->rand_delay();
+  auto ok = net->network.try_send(node, dst, proto);
+  if (!ok) co_return Result<Connect1Ok>::Error(Err::ConnectionRefused);
+  SocketAddr src{ok->src_ip, port};
+  auto [tx1, rx1] = net_channel(net, node, dst, proto);
+  auto [tx2, rx2] = net_channel(net, ok->dst_node, src, proto);
+  ok->socket->new_connection(src, dst, std::move(tx2), std::move(rx1));
+  co_return Result<Connect1Ok>::Ok(Connect1Ok{std::move(tx1), std::move(rx2), src});
+}
+
 // ---- tokio::sync::oneshot (only what endpoint.rs uses) ----
 template <class T>
 struct OneshotState {
@@ -312,11 +457,48 @@ struct Mailbox {
   }
 };
 
+struct BindGuard;
+struct IncomingConn {
+  PayloadSender tx;
+  PayloadReceiver rx;
+  SocketAddr peer;
+};
 struct EndpointSocket : Socket {
   Mailbox mailbox;
+  /// async_channel::unbounded of incoming connections (endpoint.rs:18,306)
+  std::pair<UnboundedSender<std::shared_ptr<IncomingConn>>, UnboundedReceiver<std::shared_ptr<IncomingConn>>> conns =
+      unbounded_channel<std::shared_ptr<IncomingConn>>();
   void deliver(SocketAddr src, SocketAddr, u64 tag, Payload msg) override {
     mailbox.deliver(Message{tag, msg, src});
   }
+  void new_connection(SocketAddr src, SocketAddr, PayloadSender tx, PayloadReceiver rx) override {
+    conns.first.send(std::make_shared<IncomingConn>(IncomingConn{std::move(tx), std::move(rx), src}));  // try_send
+  }
+};
+
+/// endpoint.rs:228-274 Sender / Receiver of a reliable connection
+struct ConnSender {
+  std::shared_ptr<BindGuard> guard;
+  PayloadSender tx;
+  Result<Unit> send(Payload v) const {  // `async fn send` has no await point
+    if (!tx.send(v)) return Result<Unit>::Error(Err::ConnectionReset);
+    return Result<Unit>::Ok({});
+  }
+  bool is_closed() const { return tx.is_closed(); }
+};
+struct ConnReceiver {
+  std::shared_ptr<BindGuard> guard;
+  PayloadReceiver rx;
+  Async<Result<Payload>> recv() {
+    auto v = co_await StreamNext<Payload>{&rx};
+    if (!v) co_return Result<Payload>::Error(Err::ConnectionReset);
+    co_return Result<Payload>::Ok(*v);
+  }
+};
+struct Connection {
+  ConnSender tx;
+  ConnReceiver rx;
+  SocketAddr peer;
 };
 
 /// net/mod.rs:436-494
@@ -402,6 +584,26 @@ class Endpoint {
     if (r.is_err()) co_return Result<Payload>::Error(r.err);
     if (r.ok->second != *p.ok) panic("receive a message but not from the connected address");
     co_return Result<Payload>::Ok(r.ok->first);
+  }
+
+  // ---- reliable connections (endpoint.rs:178-211) ----
+  /// connect1: NetSim::connect1 with this endpoint's node and port
+  Async<Result<Connection>> connect1(SocketAddr addr) const {
+    auto g = guard;
+    auto r = co_await net_connect1(g->net, g->node->id, g->addr.port, addr, IpProtocol::Udp);
+    if (r.is_err()) co_return Result<Connection>::Error(r.err);
+    co_return Result<Connection>::Ok(
+        Connection{ConnSender{g, std::move(r.ok->tx)}, ConnReceiver{g, std::move(r.ok->rx)}, addr});
+  }
+  /// accept1: rand_delay FIRST, then the next incoming connection
+  Async<Result<Connection>> accept1() const {
+    auto g = guard;
+    auto s = socket;
+    co_await g->net->rand_delay();
+    auto c = co_await s->conns.second.recv();
+    if (!c) co_return Result<Connection>::Error(Err::ConnectionReset);
+    co_return Result<Connection>::Ok(
+        Connection{ConnSender{g, std::move((*c)->tx)}, ConnReceiver{g, std::move((*c)->rx)}, (*c)->peer});
   }
 
   // ---- net/rpc.rs:82-166 ----

@@ -318,4 +318,89 @@ inline Async<u32> wl_chaos_main(u64 rounds, u64 period_ms, u32 panics, std::arra
   co_return 0;
 }
 
+// ------------------------------------------------------------------------------------
+// MSIM_WL_STREAM — SURVEY §8(f) row 1: the reliable channel layer every ecosystem simulator is
+// built on (connect1 / accept1 / Sender / Receiver, net/mod.rs:337-430, endpoint.rs:178-274):
+// an echo server and a client exchanging p[0] messages over ONE ordered connection while a
+// supervisor task partitions the two nodes (in the spirit of tcp/mod.rs:104-179
+// disconnect_and_recovery): lost packets become DELAY (exponential back-off), never loss.
+constexpr u32 STREAM_FAULTS = 1;
+inline Async<Unit> stream_echo(Connection conn) {
+  for (;;) {
+    auto r = co_await conn.rx.recv();
+    if (r.is_err()) break;  // ConnectionReset: the peer dropped its sender
+    Payload v = *r.ok;
+    v.v[1] = v.v[0] ^ 0x5a5a5a5au;
+    if (conn.tx.send(v).is_err()) break;
+  }
+  co_return {};
+}
+inline Async<Unit> stream_server(SocketAddr addr) {
+  Endpoint ep = std::move((co_await Endpoint::bind(addr)).unwrap());
+  for (;;) {
+    Connection conn = std::move((co_await ep.accept1()).unwrap());
+    spawn(stream_echo(std::move(conn)));
+  }
+}
+inline Async<u32> stream_client(SocketAddr server, u64 msgs, u64 think_ns) {
+  co_await sleep(1 * SEC);
+  Endpoint ep = std::move((co_await Endpoint::bind(SocketAddr{IP_UNSPECIFIED, 0})).unwrap());
+  u32 attempts = 0;
+  std::optional<Connection> conn;
+  for (;;) {  // connect1 surfaces ConnectionRefused when the request is lost / clogged: retry
+    attempts++;
+    auto r = co_await ep.connect1(server);
+    if (r.is_ok()) {
+      conn.emplace(std::move(*r.ok));
+      break;
+    }
+    if (r.err != Err::ConnectionRefused) panic("unexpected connect1 error", 40);
+    co_await sleep(100 * MS);
+  }
+  for (u64 i = 0; i < msgs; i++) {
+    Payload p;
+    p.v[0] = u32(i);
+    conn->tx.send(p).unwrap();
+    Payload r = (co_await conn->rx.recv()).unwrap();
+    if (r.v[0] != u32(i) || r.v[1] != (u32(i) ^ 0x5a5a5a5au)) panic("echo mismatch / reordering", 41);
+    co_await sleep(think_ns);
+  }
+  co_return attempts;
+}
+inline Async<Unit> stream_fault_task() {
+  GlobalRng& rng = thread_rng();
+  NetSim& net = current_net();
+  for (;;) {
+    co_await sleep(rng.gen_range_u64(300, 1500) * MS);
+    u64 k = rng.gen_range_u64(0, 3);
+    if (k == 0) {
+      net.clog_link(1, 2);
+      net.clog_link(2, 1);
+    } else {
+      net.clog_node(k);  // node 1 or 2
+    }
+    co_await sleep(rng.gen_range_u64(100, 3000) * MS);
+    if (k == 0) {
+      net.unclog_link(1, 2);
+      net.unclog_link(2, 1);
+    } else {
+      net.unclog_node(k);
+    }
+  }
+}
+inline Async<u32> wl_stream_main(u64 msgs, u64 think_ns, u32 faults, std::array<u32, 4>* user) {
+  auto& rt = current_runtime();
+  SocketAddr a1{ip4(10, 0, 0, 1), 1};
+  auto node1 = rt.create_node().ip(a1.ip).build();
+  auto node2 = rt.create_node().ip(ip4(10, 0, 0, 2)).build();
+  node1.spawn(stream_server(a1));
+  auto f = node2.spawn(stream_client(a1, msgs, think_ns));
+  if (faults & STREAM_FAULTS) spawn(stream_fault_task());
+  auto r = co_await f;
+  (*user)[0] = u32(msgs);
+  (*user)[1] = r.unwrap();
+  (*user)[3] = u32(current_net().msg_count());
+  co_return 0;
+}
+
 }  // namespace msim_oracle

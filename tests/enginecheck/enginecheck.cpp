@@ -60,6 +60,7 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
     case MSIM_WL_PINGPONG: return run_wl<WL_PingPong>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_RAFT: return run_wl<WL_Raft>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_CHAOS: return run_wl<WL_Chaos>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
+    case MSIM_WL_STREAM: return run_wl<WL_Stream>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
   }
   return MSIM_EINVAL;
 }
@@ -70,6 +71,7 @@ extern "C" int enginecheck_state_bytes(uint32_t workload) {
     case MSIM_WL_PINGPONG: return Layout<WL_PingPong::Caps>::BYTES;
     case MSIM_WL_RAFT: return Layout<WL_Raft::Caps>::BYTES;
     case MSIM_WL_CHAOS: return Layout<WL_Chaos::Caps>::BYTES;
+    case MSIM_WL_STREAM: return Layout<WL_Stream::Caps>::BYTES;
   }
   return -1;
 }

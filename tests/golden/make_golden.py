@@ -23,6 +23,8 @@ CASES = {
     "raft_cfg2": (dict(), dict(kind="raft"), list(range(16)) + [4095, 65535]),  # BASELINE config 2
     "raft_cfg3": (dict(), dict(kind="raft", faults=7), list(range(16)) + [4095, 65535]),  # config 3
     "raft_cfg2_bug": (dict(), dict(kind="raft", bug=1), [88, 89, 90]),
+    "stream_partitions": (dict(), dict(kind="stream"), list(range(6))),
+    "stream_loss20": (dict(packet_loss_rate=0.2), dict(kind="stream", messages=500), [0, 1]),
     "chaos": (dict(), dict(kind="chaos"), list(range(6))),
     "chaos_panics": (dict(), dict(kind="chaos", rounds=30, period_ms=700, panics=3), list(range(6))),
     "raft_cfg3_loss5": (dict(packet_loss_rate=0.05), dict(kind="raft", faults=7), list(range(4))),

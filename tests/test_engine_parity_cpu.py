@@ -42,6 +42,12 @@ CASES = [
     ("raft-fast-timeouts", m.Config(), m.Workload.raft(duration_ms=1500, rpc_timeout_ms=25, heartbeat_ms=30,
                                                         election_ms=(80, 160), faults=4), 0, 32),
     ("raft-zero-duration", m.Config(), m.Workload.raft(duration_ms=0), 0, 4),
+    # reliable channels: connect1 / accept1 / Sender / Receiver (net/mod.rs:337-430), SURVEY §8(f) row 1
+    ("stream", m.Config(), m.Workload.stream(faults=0), 0, 100),
+    ("stream-partitions", m.Config(), m.Workload.stream(faults=1), 0, 200),
+    ("stream-partitions-loss20", m.Config(packet_loss_rate=0.2), m.Workload.stream(messages=500, faults=1), 0, 100),
+    ("stream-unreachable-timelimit", m.Config(packet_loss_rate=1.0, time_limit_ns=5 * m.SEC),
+     m.Workload.stream(messages=3, faults=0), 0, 16),
     # Handle::{kill,restart,pause,resume} + restart_on_panic (task/mod.rs:356-424,289-317)
     ("chaos", m.Config(), m.Workload.chaos(), 0, 200),
     ("chaos-long-panics", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 200),

@@ -78,6 +78,11 @@ CASES = [
     ("raft-fast-timeouts", m.Config(), m.Workload.raft(duration_ms=1500, rpc_timeout_ms=25, heartbeat_ms=30,
                                                         election_ms=(80, 160), faults=4), 0, 100),
     ("raft-huge-seeds", m.Config(), m.Workload.raft(duration_ms=1500, faults=7), 2**64 - 50, 50),
+    ("stream-reliable-channel", m.Config(), m.Workload.stream(faults=0), 0, 300),
+    ("stream-partitions", m.Config(), m.Workload.stream(faults=1), 0, 1000),
+    ("stream-partitions-loss20", m.Config(packet_loss_rate=0.2), m.Workload.stream(messages=500, faults=1), 0, 300),
+    ("stream-unreachable-timelimit", m.Config(packet_loss_rate=1.0, time_limit_ns=5 * m.SEC),
+     m.Workload.stream(messages=3, faults=0), 0, 40),
     ("chaos-kill-restart-pause", m.Config(), m.Workload.chaos(), 0, 500),
     ("chaos-restart-on-panic", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 500),
     ("chaos-always-panicking", m.Config(), m.Workload.chaos(rounds=4, period_ms=3000, panics=50), 0, 200),

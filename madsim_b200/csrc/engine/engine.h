@@ -134,8 +134,9 @@ struct Layout {
   static constexpr int W_CH_DST = W_CH_CUR_V1 + ND;             // [ND] test_link destination address
   static constexpr int W_CH_WAITER = W_CH_DST + ND;             // [ND] mpsc rx_waker (slot<<20|gen) or NONE32
   static constexpr int W_CONN_SRC = W_CH_WAITER + ND;           // [NCONN] connector's source address
-  static constexpr int W_ACC_WAITER = W_CONN_SRC + C::NCONN;    // [NSOCK] task waiting in accept1
-  static constexpr int NW = W_ACC_WAITER + C::NSOCK;
+  static constexpr int NSA = C::NCONN ? C::NSOCK : 0;           // accept state exists only with connections
+  static constexpr int W_ACC_WAITER = W_CONN_SRC + C::NCONN;    // [NSA] task waiting in accept1
+  static constexpr int NW = W_ACC_WAITER + NSA;
   // ---- u8 section ----
   static constexpr int B_RQ = 0;                        // [NT] ready "queue": a Vec popped at a random index
   static constexpr int B_T_KIND = B_RQ + C::NT;
@@ -160,15 +161,15 @@ struct Layout {
   static constexpr int B_N_EPOCH = B_N_FLAGS + C::NNODE;
   static constexpr int B_PK = B_N_EPOCH + C::NNODE;        // [NPARK] parked runnables, park order
   static constexpr int B_T_CONN = B_PK + C::NPARK;         // [NT] connection end the future holds: conn<<1|side, or NONE8
-  static constexpr int B_CH_HEAD = B_T_CONN + C::NT;       // [ND] FIFO head / length
+  static constexpr int B_CH_HEAD = B_T_CONN + (C::NCONN ? C::NT : 0);  // [ND] FIFO head / length
   static constexpr int B_CH_LEN = B_CH_HEAD + ND;
   static constexpr int B_CH_PHASE = B_CH_LEN + ND;         // [ND] 0 idle, 1 back-off sleep, 2 arrival sleep
   static constexpr int B_CH_SRC = B_CH_PHASE + ND;         // [ND] test_link source node
   static constexpr int B_CH_FLAGS = B_CH_SRC + ND;         // [ND] CH_TX_ALIVE | CH_RX_ALIVE
   static constexpr int B_CONN_USED = B_CH_FLAGS + ND;      // [NCONN]
   static constexpr int B_ACC = B_CONN_USED + C::NCONN;     // [NSOCK*NACC] incoming connections (async_channel)
-  static constexpr int B_ACC_LEN = B_ACC + C::NSOCK * C::NACC;
-  static constexpr int NB = B_ACC_LEN + C::NSOCK;
+  static constexpr int B_ACC_LEN = B_ACC + NSA * C::NACC;
+  static constexpr int NB = B_ACC_LEN + NSA;
 
   static constexpr int W_BASE = 8 * NQ;                 // byte offset of the u32 section
   static constexpr int B_BASE = W_BASE + 4 * NW;        // ... of the u8 section
@@ -796,8 +797,10 @@ MSIM_NOUNROLL
     for (u32 i = 0; i < ml; i++) msg_free(b(L::B_MB, k * C::NMBOX + i));
     b(L::B_SK_MBLEN, k) = 0;
     b(L::B_SK_REGLEN, k) = 0;
-    b(L::B_ACC_LEN, k) = 0;  // pending incoming connections die with the socket object
-    w(L::W_ACC_WAITER, k) = NONE32;
+    if (C::NCONN) {
+      b(L::B_ACC_LEN, k) = 0;  // pending incoming connections die with the socket object
+      w(L::W_ACC_WAITER, k) = NONE32;
+    }
     sk_state(k) = 0;
     w(L::W_SK_PORTGEN, k) = (w(L::W_SK_PORTGEN, k) & 0xffff0000u) + 0x10000u;  // gen++ : stale refs miss
   }
@@ -1091,7 +1094,7 @@ MSIM_NOUNROLL
     n_flags(0) = NF_EXISTS;
     w(L::W_NEXT_NODE) = 1;
     w(L::W_RESUME) = NONE32;
-    for (int k = 0; k < C::NSOCK; k++) w(L::W_ACC_WAITER, k) = NONE32;
+    for (int k = 0; k < L::NSA; k++) w(L::W_ACC_WAITER, k) = NONE32;
     int m = spawn(WL::MAIN_KIND, 0, TF_JOINABLE);
     w(L::W_MAIN_SLOT) = (u32)m;
   }

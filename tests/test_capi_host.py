@@ -40,7 +40,8 @@ def test_defaults_and_validation_need_no_device():
     assert lib.msim_workload_default(N.WL_RAFT, C.byref(d)) == 0
     assert (d.n_nodes, list(d.p)[:7]) == (5, [10000, 0, 0, 40, 50, 150, 300])
     assert lib.msim_workload_default(99, C.byref(d)) == N.EINVAL
-    assert lib.msim_workload_state_bytes(N.WL_RAFT) > 1000
+    # Raft must keep 28 seeds per 227 KB CTA (4096 seeds = 147 CTAs = one wave on 148 SMs)
+    assert 1000 < lib.msim_workload_state_bytes(N.WL_RAFT) <= (232448 - 128) // 28
     assert lib.msim_workload_state_bytes(77) == N.EINVAL
     assert lib.msim_workload_default(N.WL_CHAOS, C.byref(d)) == 0 and list(d.p)[:2] == [8, 2000]
 

@@ -1214,10 +1214,11 @@ MSIM_NOUNROLL
               if (rfrom != t_c(t)) return panic(31);  // assert_eq!(from, dst) (rpc.rs:125)
               break;
             case W_CONNECT:
-              ret = connect1(t, (u32)t_dl1(t));
+              if (C::NCONN) ret = connect1(t, (u32)t_dl1(t));
               wt = W_NONE;
               break;
             case W_ACCEPT: {  // conn_rx.recv().await (async_channel): FIFO
+              if (!C::NCONN) break;  // workloads without connections carry none of this code
               u32 al = b(L::B_ACC_LEN, k);
               if (al == 0) {
                 w(L::W_ACC_WAITER, k) = ((u32)t << 20) | t_gen(t);
@@ -1234,6 +1235,7 @@ MSIM_NOUNROLL
               break;
             }
             case W_CH_RECV: {  // poll_next of the channel's stream (net/mod.rs:385-402)
+              if (!C::NCONN) break;
               int e = t_conn(t);
               int d = 2 * (e >> 1) + ((e & 1) ^ 1);
               for (;;) {
@@ -1405,6 +1407,7 @@ MSIM_NOUNROLL
           t_wait(t) = W_CH_RECV;
           break;
         case RQ_CH_SEND: {  // PayloadSender::send: state = test_link(); tx.send((value, state)).ok()
+          if (!C::NCONN) break;
           int e = t_conn(t);
           int d = 2 * (e >> 1) + (e & 1);
           u64 st8 = ch_test_link(d);

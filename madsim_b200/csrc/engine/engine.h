@@ -428,6 +428,7 @@ struct Engine {
   }
   MSIM_HD void wake_task(int t) { wake(t, t_gen(t)); }
   MSIM_HD void notify_awaiter(int t) {
+    if (!C::USES_JOIN) return;  // nobody ever awaits a JoinHandle in this program
     u32 aw = t_aw(t);
     if (aw != NONE32) {
       t_aw(t) = NONE32;
@@ -457,7 +458,7 @@ struct Engine {
         msg_free(t_msg(t));
         t_msg(t) = NONE8;
       }
-      if (st == W_JOIN) join_detach((int)t_c(t));
+      if (C::USES_JOIN && st == W_JOIN) join_detach((int)t_c(t));
       if (C::NCONN) conn_drop_end(t);
       sock_unref(t);
       t_wait(t) = W_NONE;
@@ -1291,6 +1292,7 @@ MSIM_NOUNROLL
               break;
             }
             case W_JOIN: {
+              if (!C::USES_JOIN) break;
               int target = (int)t_c(t);
               int r = join_poll(t, target);
               if (r == 0) {
@@ -1440,7 +1442,7 @@ MSIM_NOUNROLL
   MSIM_HD bool run_task(int t, bool cont) {
     u8 f = t_flags(t);
     if (!cont) {
-      if (MSIM_UNLIKELY(f & TF_CLOSED)) {
+      if (C::USES_KILL && MSIM_UNLIKELY(f & TF_CLOSED)) {
         drop_future(t);
         t_flags(t) = t_flags(t) & ~TF_SCHEDULED;
         notify_awaiter(t);
@@ -1452,7 +1454,7 @@ MSIM_NOUNROLL
     int r = poll_task(t);
     if (MSIM_UNLIKELY(r == POLL_ADVANCE)) return true;  // still RUNNING: the poll continues after the timers fired
     if (r == POLL_READY) {
-      if (MSIM_UNLIKELY(t_flags(t) & TF_INIT)) node_exit(t_node(t), t_epoch(t));  // `future.await; h.exit()`
+      if (C::USES_KILL && MSIM_UNLIKELY(t_flags(t) & TF_INIT)) node_exit(t_node(t), t_epoch(t));  // `future.await; h.exit()`
       drop_future(t);
       t_flags(t) = (t_flags(t) & ~(TF_RUNNING | TF_SCHEDULED)) | TF_COMPLETED;
       notify_awaiter(t);
@@ -1468,7 +1470,7 @@ MSIM_NOUNROLL
     } else {
       f = t_flags(t) & ~TF_RUNNING;
       t_flags(t) = f;
-      if (MSIM_UNLIKELY(f & TF_CLOSED)) {
+      if (C::USES_KILL && MSIM_UNLIKELY(f & TF_CLOSED)) {
         t_flags(t) = f & ~TF_SCHEDULED;
         drop_future(t);
         notify_awaiter(t);
@@ -1532,14 +1534,17 @@ MSIM_NOUNROLL
         rq_len = len - 1;
         ev_pop++;
         u64 aux = ((u64)len << 32) | idx;
-        u8 f = t_flags(t);
+        u8 f = 0;
         u32 kind = MSIM_EV_POLL;
-        if (!(f & TF_ALIVE))
-          kind = MSIM_EV_SKIP;  // metadata().upgrade() failed: future already dropped
-        else if ((f & TF_CANCELLED) || task_node_killed(t))
-          kind = MSIM_EV_DROP;
-        else if (n_flags(t_node(t)) & NF_PAUSED)
-          kind = MSIM_EV_PARK;
+        if (C::USES_KILL) {  // programs that never kill / pause / abort / exit a node only ever POLL
+          f = t_flags(t);
+          if (!(f & TF_ALIVE))
+            kind = MSIM_EV_SKIP;  // metadata().upgrade() failed: future already dropped
+          else if ((f & TF_CANCELLED) || task_node_killed(t))
+            kind = MSIM_EV_DROP;
+          else if (n_flags(t_node(t)) & NF_PAUSED)
+            kind = MSIM_EV_PARK;
+        }
         trace(now, aux, kind, t_spawn(t));
         if (MSIM_UNLIKELY(kind == MSIM_EV_SKIP)) {
           t_flags(t) = f & ~TF_SCHEDULED;

@@ -13,6 +13,9 @@ struct WL_Chaos {
   struct Caps {
     static constexpr int NT = 8, TQ = 32, NMSG = 1, NSOCK = 1, NREG = 1, NMBOX = 1, NNODE = 2, NPARK = 4;
     static constexpr int WQ = 0, WW = 0, WS = 2;
+    // USES_KILL: can a task be dropped while queued (kill / restart / pause / abort / a returning init task)?
+    static constexpr bool USES_JOIN = false;  // does any task await a JoinHandle?
+    static constexpr bool USES_KILL = true;
     static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 { K_MAIN = 0, K_WORKER = 1 };

@@ -12,6 +12,9 @@ struct WL_PingPong {
   struct Caps {
     static constexpr int NT = 4, TQ = 16, NMSG = 4, NSOCK = 2, NREG = 2, NMBOX = 2, NNODE = 3, NPARK = 1;
     static constexpr int WQ = 0, WW = 0, WS = 0;
+    // USES_KILL: can a task be dropped while queued (kill / restart / pause / abort / a returning init task)?
+    static constexpr bool USES_JOIN = true;  // does any task await a JoinHandle?
+    static constexpr bool USES_KILL = false;
     static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 { K_MAIN = 0, K_SERVER = 1, K_CLIENT = 2 };

@@ -26,6 +26,9 @@ struct WL_Raft {
   struct Caps {
     static constexpr int NT = 64, TQ = 176, NMSG = 48, NSOCK = 6, NREG = 12, NMBOX = 16, NNODE = 6, NPARK = 2;
     static constexpr int WQ = 1, WW = 6, WS = 1;
+    // USES_KILL: can a task be dropped while queued (kill / restart / pause / abort / a returning init task)?
+    static constexpr bool USES_JOIN = false;  // does any task await a JoinHandle?
+    static constexpr bool USES_KILL = false;
     static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 {

@@ -9,6 +9,9 @@ struct WL_Sleep {
   struct Caps {
     static constexpr int NT = 2, TQ = 8, NMSG = 1, NSOCK = 1, NREG = 1, NMBOX = 1, NNODE = 1, NPARK = 1;
     static constexpr int WQ = 0, WW = 0, WS = 0;
+    // USES_KILL: can a task be dropped while queued (kill / restart / pause / abort / a returning init task)?
+    static constexpr bool USES_JOIN = false;  // does any task await a JoinHandle?
+    static constexpr bool USES_KILL = false;
     static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   static constexpr u32 MAIN_KIND = 0;

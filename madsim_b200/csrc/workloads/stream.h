@@ -13,6 +13,9 @@ struct WL_Stream {
   struct Caps {
     static constexpr int NT = 8, TQ = 32, NMSG = 2, NSOCK = 2, NREG = 2, NMBOX = 2, NNODE = 3, NPARK = 1;
     static constexpr int WQ = 0, WW = 0, WS = 0;
+    // USES_KILL: can a task be dropped while queued (kill / restart / pause / abort / a returning init task)?
+    static constexpr bool USES_JOIN = true;  // does any task await a JoinHandle?
+    static constexpr bool USES_KILL = false;
     static constexpr int NCONN = 2, NCQ = 4, NACC = 2;
   };
   enum : u32 { K_MAIN = 0, K_SERVER, K_ECHO, K_CLIENT, K_FAULT };

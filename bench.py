@@ -37,7 +37,7 @@ B_MSG = 40            # one datagram send/deliver
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the bench configuration,
 # from the `ncu --set full` capture summarised in profiles/r1c_step_kernel_v2_bench_config.json
-TRAFFIC_BYTES_PER_LAUNCH = {"raft": 597760}
+TRAFFIC_BYTES_PER_LAUNCH = {"raft": 457472}
 
 
 def algorithmic_bytes(ev_pop, ev_fire, msgs):

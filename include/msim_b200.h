@@ -105,6 +105,7 @@ typedef struct msim_config {
 #define MSIM_WL_RAFT 2      /* 5-node Raft leader election, BASELINE configs 2 and 3           */
 #define MSIM_WL_CHAOS 3     /* kill/restart/pause supervisor schedule (task/mod.rs:852-1016)   */
 #define MSIM_WL_STREAM 4    /* reliable connect1/accept1 echo stream under partitions (net/mod.rs:337-430) */
+#define MSIM_WL_ETCD 5      /* madsim-etcd-client SimServer + KV clients + linearizability check, BASELINE config 4 */
 
 /* parameter slots p[] per workload
  *  SLEEP    p0 = duration ns
@@ -113,6 +114,10 @@ typedef struct msim_config {
  *           p2 = bug mode (0 none, 1 double-vote), p3 = rpc timeout ms (default 40),
  *           p4 = heartbeat ms (default 50), p5 = election timeout lo ms (150), p6 = hi ms (300)
  *  STREAM   p0 = messages, p1 = think time ns, p2 = faults (1 = partition schedule)
+ *  ETCD     n_nodes = 1 server + (n_nodes-1) clients (default 3); p0 = operations per client (default 32, clients x p0 <= 128),
+ *           p1 = think time ns (default 50 ms), p2 = SimServer::timeout_rate as IEEE f32 bits (default 0),
+ *           p3 = bug bits (1 = server read cache that delete does not invalidate,
+ *           2 = clients also delete the leased key: reaches the crate's own expect("no lease")), p4 = lease ttl s (default 1)
  *  CHAOS    p0 = rounds, p1 = period ms, p2 = worker panics on its first p2 starts (restart_on_panic)
  *                                                         */
 #define MSIM_RAFT_FAULT_CLOG_NODE 1u

@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <stdexcept>
+#include <cstring>
 #include <string>
 #include <utility>
 #include <vector>
@@ -88,6 +89,23 @@ struct Workload {
     Workload w;
     check(msim_workload_default(MSIM_WL_CHAOS, &w.desc));
     w.desc.p[0] = rounds, w.desc.p[1] = period_ms, w.desc.p[2] = panics;
+    return w;
+  }
+  /// connect1 / accept1 echo stream under partitions (net/mod.rs:337-430)
+  static Workload stream(uint64_t messages = 200, uint64_t think_ns = 5000000, uint32_t faults = 1) {
+    Workload w;
+    check(msim_workload_default(MSIM_WL_STREAM, &w.desc));
+    w.desc.p[0] = messages, w.desc.p[1] = think_ns, w.desc.p[2] = faults;
+    return w;
+  }
+  /// madsim-etcd-client SimServer (timeout_rate: server.rs:21-25) + KV clients + linearizability check
+  static Workload etcd(uint32_t clients = 2, uint64_t ops = 32, float timeout_rate = 0.0f, uint32_t bug = 0) {
+    Workload w;
+    check(msim_workload_default(MSIM_WL_ETCD, &w.desc));
+    uint32_t bits;
+    static_assert(sizeof(bits) == sizeof(timeout_rate), "f32");
+    std::memcpy(&bits, &timeout_rate, 4);
+    w.desc.n_nodes = clients + 1, w.desc.p[0] = ops, w.desc.p[2] = bits, w.desc.p[3] = bug;
     return w;
   }
 };

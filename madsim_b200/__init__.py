@@ -35,6 +35,7 @@ from ._native import (  # noqa: F401
     WL_RAFT,
     WL_SLEEP,
     WL_STREAM,
+    WL_ETCD,
     MsimError,
 )
 

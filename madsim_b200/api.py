@@ -103,11 +103,22 @@ class Workload:
         """reliable-channel echo (connect1/accept1/Sender/Receiver, net/mod.rs:337-430) under partitions."""
         return Workload(N.WL_STREAM, 2, [messages, think_ns, faults, 0, 0, 0, 0, 0])
 
+    @staticmethod
+    def etcd(clients: int = 2, ops: int = 32, think_ns: int = 50 * MS, timeout_rate: float = 0.0, bug: int = 0,
+             lease_ttl_s: int = 1) -> "Workload":
+        """madsim-etcd-client SimServer + `clients` KV clients (one connection per request) with a
+        linearizability check of the history (BASELINE config 4); `timeout_rate` is
+        SimServer::timeout_rate (an f32 in the reference: passed as its bit pattern)."""
+        import struct
+
+        bits = struct.unpack("<I", struct.pack("<f", timeout_rate))[0]
+        return Workload(N.WL_ETCD, clients + 1, [ops, think_ns, bits, bug, lease_ttl_s, 0, 0, 0])
+
     def to_c(self) -> N.MsimWorkloadDesc:
         return N.MsimWorkloadDesc(self.workload, self.n_nodes, (C.c_uint64 * 8)(*[int(x) for x in self.p]))
 
     def name(self) -> str:
-        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos", 4: "stream"}.get(self.workload, "?")
+        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos", 4: "stream", 5: "etcd"}.get(self.workload, "?")
 
 
 class SimulationFailure(AssertionError):

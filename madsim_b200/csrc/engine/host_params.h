@@ -38,6 +38,12 @@ inline int workload_defaults(uint32_t workload, msim_workload_desc* d) {
       d->p[1] = 5 * NS_PER_MS;
       d->p[2] = 1;
       return 0;
+    case MSIM_WL_ETCD:
+      d->n_nodes = 3;
+      d->p[0] = 32;
+      d->p[1] = 50 * NS_PER_MS;
+      d->p[4] = 1;
+      return 0;
     case MSIM_WL_CHAOS:
       d->n_nodes = 1;
       d->p[0] = 8;
@@ -133,6 +139,21 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
         return MSIM_EINVAL;
       }
       break;
+    case MSIM_WL_ETCD: {
+      if (P.n_nodes == 0) P.n_nodes = 3;
+      float rate;
+      u32 bits = (u32)wl.p[2];
+      std::memcpy(&rate, &bits, 4);
+      if (P.n_nodes < 2 || P.n_nodes > 4 || wl.p[0] * (P.n_nodes - 1) > 128 || wl.p[3] > 3 || wl.p[4] > 0xffff ||
+          !(rate >= 0.0f && rate <= 1.0f)) {
+        if (err) *err = "etcd: need 1..3 clients, clients x ops <= 128, bug bits <= 3, 0 <= timeout_rate <= 1";
+        return MSIM_EINVAL;
+      }
+      // Bernoulli::new(timeout_rate as f64) (service.rs:166)
+      P.p[5] = rate == 1.0f ? 1 : 0;
+      P.p[6] = rate == 1.0f ? 0 : (u64)((double)rate * 18446744073709551616.0);
+      break;
+    }
     case MSIM_WL_CHAOS:
       if (wl.p[1] == 0) {
         if (err) *err = "chaos: period must be > 0";

@@ -250,6 +250,7 @@ int state_bytes_of(uint32_t workload) {
     case MSIM_WL_RAFT: return Layout<WL_Raft::Caps>::BYTES;
     case MSIM_WL_CHAOS: return Layout<WL_Chaos::Caps>::BYTES;
     case MSIM_WL_STREAM: return Layout<WL_Stream::Caps>::BYTES;
+    case MSIM_WL_ETCD: return Layout<WL_Etcd::Caps>::BYTES;
   }
   return -1;
 }
@@ -346,6 +347,7 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
     case MSIM_WL_RAFT: e = launch_wl<WL_Raft>(a, grid, block, b->smem, b->stream); break;
     case MSIM_WL_CHAOS: e = launch_wl<WL_Chaos>(a, grid, block, b->smem, b->stream); break;
     case MSIM_WL_STREAM: e = launch_wl<WL_Stream>(a, grid, block, b->smem, b->stream); break;
+    case MSIM_WL_ETCD: e = launch_wl<WL_Etcd>(a, grid, block, b->smem, b->stream); break;
     default: return set_err(MSIM_EINVAL, "unknown workload");
   }
   if (e != cudaSuccess) return set_err(MSIM_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));

@@ -4,4 +4,5 @@
 #include "raft.h"
 #include "sleep.h"
 #include "stream.h"
+#include "etcd.h"
 #define MSIM_HAVE_RAFT 1

@@ -78,6 +78,20 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
         rt.block_on(wl_stream_main(wl->p[0], wl->p[1], u32(wl->p[2]), &user));
         rt.teardown();
         break;
+      case MSIM_WL_ETCD: {
+        EtcdParams ep;
+        ep.n_clients = (wl->n_nodes ? wl->n_nodes : 3) - 1;
+        ep.ops = wl->p[0];
+        ep.think_ns = wl->p[1];
+        u32 bits = u32(wl->p[2]);
+        std::memcpy(&ep.timeout_rate, &bits, 4);
+        ep.bug = u32(wl->p[3]);
+        ep.lease_ttl = u32(wl->p[4]);
+        if (ep.n_clients < 1 || ep.n_clients > 3 || !(ep.timeout_rate >= 0.0f && ep.timeout_rate <= 1.0f)) return MSIM_EINVAL;
+        rt.block_on(wl_etcd_main(ep, &user));
+        rt.teardown();
+        break;
+      }
       case MSIM_WL_CHAOS:
         rt.block_on(wl_chaos_main(wl->p[0], wl->p[1], u32(wl->p[2]), &user));
         break;

@@ -320,6 +320,64 @@ static Async<Unit> join_unwrap(JoinHandle<T> h) {
   co_return {};
 }
 
+
+// ---- madsim-etcd-client/tests/test.rs:9-62 kv(), :64-128 lease() on the restated SimServer ----
+static Async<Unit> etcd_kv_client(SocketAddr server) {
+  Endpoint ep = std::move((co_await Endpoint::connect(server)).unwrap());
+  auto call = [&](u32 op, u32 key, u32 value, u32 lease = 0, u32 ttl = 0) {
+    EtcdRequest q;
+    q.op = op, q.key = key, q.value = value, q.lease = lease, q.ttl = ttl;
+    return etcd_call(ep, server, q);
+  };
+  EtcdResponse r = co_await call(ETCD_PUT, 0, 0xba5);  // put foo bar
+  CHECK(r.status == ETCD_OK);
+  r = co_await call(ETCD_GET, 0, 0);
+  u32 revision = r.revision;
+  CHECK(r.flag == 1 && r.value == 0xba5 && r.mod_revision == revision);  // create == mod == header revision
+  r = co_await call(ETCD_PUT, 0, 0x99);  // put again
+  r = co_await call(ETCD_GET, 0, 0);
+  CHECK(r.value == 0x99 && r.mod_revision == r.revision && r.revision == revision + 1);
+  r = co_await call(ETCD_DELETE, 0, 0);
+  CHECK(r.flag == 1);
+  r = co_await call(ETCD_GET, 0, 0);
+  CHECK(r.flag == 0);
+  co_return {};
+}
+static Async<Unit> etcd_lease_client(SocketAddr server) {
+  Endpoint ep = std::move((co_await Endpoint::connect(server)).unwrap());
+  auto call = [&](u32 op, u32 key, u32 value, u32 lease = 0, u32 ttl = 0) {
+    EtcdRequest q;
+    q.op = op, q.key = key, q.value = value, q.lease = lease, q.ttl = ttl;
+    return etcd_call(ep, server, q);
+  };
+  EtcdResponse r = co_await call(ETCD_GRANT, 0, 0, 9, 60);  // grant(60)
+  CHECK(r.status == ETCD_OK);
+  r = co_await call(ETCD_PUT, 1, 7, 9);  // put with the lease
+  CHECK(r.status == ETCD_OK);
+  r = co_await call(ETCD_GET, 1, 0);
+  CHECK(r.flag == 1);
+  co_await sleep(45 * SEC);
+  r = co_await call(ETCD_GET, 1, 0);
+  CHECK(r.flag == 1);
+  co_await sleep(60 * SEC);  // wait for the lease to expire
+  r = co_await call(ETCD_GET, 1, 0);
+  CHECK(r.flag == 0);
+  r = co_await call(ETCD_PUT, 1, 7, 1);  // put with an invalid lease
+  CHECK(r.status == ETCD_LEASE_NOT_FOUND);
+  co_return {};
+}
+template <class F>
+static void etcd_case(F client) {
+  Runtime rt;
+  SocketAddr a{ip4(10, 0, 0, 1), 2379};
+  auto server = rt.create_node().ip(a.ip).build();
+  auto cl = rt.create_node().ip(ip4(10, 0, 0, 2)).build();
+  server.spawn(etcd_serve(a, 0.0f, 0));
+  auto h = cl.spawn(client(a));
+  rt.block_on(join_unwrap(std::move(h)));
+  rt.teardown();
+}
+
 int main() {
   run_case("task::spawn_in_block_on", [] {
     Runtime rt;
@@ -500,6 +558,8 @@ int main() {
     }
     CHECK(detected);
   });
+  run_case("etcd::kv (madsim-etcd-client/tests/test.rs:9-62)", [] { etcd_case(etcd_kv_client); });
+  run_case("etcd::lease expiry + lease not found (tests/test.rs:64-128)", [] { etcd_case(etcd_lease_client); });
   run_case("workload::raft elects exactly one leader", [] {
     for (u64 seed = 0; seed < 20; seed++) {
       Runtime rt(seed);

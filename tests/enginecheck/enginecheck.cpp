@@ -61,6 +61,7 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
     case MSIM_WL_RAFT: return run_wl<WL_Raft>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_CHAOS: return run_wl<WL_Chaos>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_STREAM: return run_wl<WL_Stream>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
+    case MSIM_WL_ETCD: return run_wl<WL_Etcd>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
   }
   return MSIM_EINVAL;
 }
@@ -72,6 +73,7 @@ extern "C" int enginecheck_state_bytes(uint32_t workload) {
     case MSIM_WL_RAFT: return Layout<WL_Raft::Caps>::BYTES;
     case MSIM_WL_CHAOS: return Layout<WL_Chaos::Caps>::BYTES;
     case MSIM_WL_STREAM: return Layout<WL_Stream::Caps>::BYTES;
+    case MSIM_WL_ETCD: return Layout<WL_Etcd::Caps>::BYTES;
   }
   return -1;
 }

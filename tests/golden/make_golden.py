@@ -27,6 +27,9 @@ CASES = {
     "stream_loss20": (dict(packet_loss_rate=0.2), dict(kind="stream", messages=500), [0, 1]),
     "chaos": (dict(), dict(kind="chaos"), list(range(6))),
     "chaos_panics": (dict(), dict(kind="chaos", rounds=30, period_ms=700, panics=3), list(range(6))),
+    "etcd_cfg4": (dict(), dict(kind="etcd"), list(range(8)) + [16383]),  # BASELINE config 4
+    "etcd_cfg4_loss30": (dict(packet_loss_rate=0.3), dict(kind="etcd"), list(range(4))),
+    "etcd_cfg4_timeouts_bug": (dict(packet_loss_rate=0.1), dict(kind="etcd", timeout_rate=0.125, bug=3), list(range(8))),
     "raft_cfg3_loss5": (dict(packet_loss_rate=0.05), dict(kind="raft", faults=7), list(range(4))),
 }
 

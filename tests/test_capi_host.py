@@ -44,6 +44,10 @@ def test_defaults_and_validation_need_no_device():
     assert 1000 < lib.msim_workload_state_bytes(N.WL_RAFT) <= (232448 - 128) // 28
     assert lib.msim_workload_state_bytes(77) == N.EINVAL
     assert lib.msim_workload_default(N.WL_CHAOS, C.byref(d)) == 0 and list(d.p)[:2] == [8, 2000]
+    assert lib.msim_workload_default(N.WL_ETCD, C.byref(d)) == 0
+    assert (d.n_nodes, list(d.p)[:5]) == (3, [32, 50_000_000, 0, 0, 1])
+    assert m.Workload.etcd().p == list(d.p) and m.Workload.etcd().n_nodes == 3
+    assert m.Workload.etcd(timeout_rate=0.5).p[2] == 0x3F000000  # SimServer::timeout_rate is an f32
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is present")

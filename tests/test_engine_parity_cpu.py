@@ -48,6 +48,13 @@ CASES = [
     ("stream-partitions-loss20", m.Config(packet_loss_rate=0.2), m.Workload.stream(messages=500, faults=1), 0, 100),
     ("stream-unreachable-timelimit", m.Config(packet_loss_rate=1.0, time_limit_ns=5 * m.SEC),
      m.Workload.stream(messages=3, faults=0), 0, 16),
+    # madsim-etcd-client SimServer + one-connection-per-request clients (BASELINE config 4), SURVEY §8(f) row 3
+    ("etcd", m.Config(), m.Workload.etcd(), 0, 64),
+    ("etcd-loss30", m.Config(packet_loss_rate=0.3), m.Workload.etcd(), 0, 64),
+    ("etcd-timeouts-3clients", m.Config(packet_loss_rate=0.1), m.Workload.etcd(clients=3, ops=42, timeout_rate=0.15), 50, 48),
+    ("etcd-stale-read-bug", m.Config(packet_loss_rate=0.05), m.Workload.etcd(bug=1), 0, 64),
+    ("etcd-reference-no-lease-panic", m.Config(), m.Workload.etcd(bug=2), 0, 64),
+    ("etcd-always-timeout", m.Config(), m.Workload.etcd(ops=3, timeout_rate=1.0), 0, 16),
     # Handle::{kill,restart,pause,resume} + restart_on_panic (task/mod.rs:356-424,289-317)
     ("chaos", m.Config(), m.Workload.chaos(), 0, 200),
     ("chaos-long-panics", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 200),

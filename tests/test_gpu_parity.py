@@ -83,6 +83,12 @@ CASES = [
     ("stream-partitions-loss20", m.Config(packet_loss_rate=0.2), m.Workload.stream(messages=500, faults=1), 0, 300),
     ("stream-unreachable-timelimit", m.Config(packet_loss_rate=1.0, time_limit_ns=5 * m.SEC),
      m.Workload.stream(messages=3, faults=0), 0, 40),
+    ("etcd-kv", m.Config(), m.Workload.etcd(), 0, 500),
+    ("etcd-kv-loss30", m.Config(packet_loss_rate=0.3), m.Workload.etcd(), 0, 500),
+    ("etcd-timeouts-3clients", m.Config(packet_loss_rate=0.1), m.Workload.etcd(clients=3, ops=42, timeout_rate=0.15), 50, 300),
+    ("etcd-stale-read-bug", m.Config(packet_loss_rate=0.05), m.Workload.etcd(bug=1), 0, 300),
+    ("etcd-reference-no-lease-panic", m.Config(), m.Workload.etcd(bug=2), 0, 300),
+    ("etcd-always-timeout-buggify", m.Config(buggify=True), m.Workload.etcd(ops=3, timeout_rate=1.0), 0, 64),
     ("chaos-kill-restart-pause", m.Config(), m.Workload.chaos(), 0, 500),
     ("chaos-restart-on-panic", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 500),
     ("chaos-always-panicking", m.Config(), m.Workload.chaos(rounds=4, period_ms=3000, panics=50), 0, 200),
@@ -130,6 +136,36 @@ def test_config3_full_65536_seeds_properties():
     parts = [run_gpu(cfg, wl, r * 8192, 8192)[0] for r in range(8)]
     assert np.array_equal(full, np.concatenate(parts))
     assert len(np.unique(full["trace_hash"])) == 65536, "different seed ⇒ different trace (task/mod.rs:1018-1041)"
+
+
+def test_config4_etcd_16384_seeds_packet_drop_sweep(oracle):
+    """BASELINE config 4: madsim-etcd-client KV linearizability, 3 nodes, 16384 seeds, packet-drop
+    sweep 0-30 %.  Every rate: a 512-seed window bit-exact against the oracle; the whole batch
+    finishes, every history is linearizable (the reliable channel turns loss into delay, refused
+    connects are errors the client records), and loss only ever lowers the number of applied ops."""
+    wl = m.Workload.etcd()
+    prev_ok = None
+    for i, rate in enumerate((0.0, 0.05, 0.10, 0.15, 0.20, 0.25, 0.30)):
+        cfg = m.Config(packet_loss_rate=rate)
+        got, bm, st = run_gpu(cfg, wl, 0, 16384)
+        assert st["n_unfinished"] == 0 and st["n_pass"] == 16384 and not bm.any(), rate
+        lo = 2048 * i
+        ref = oracle.run_many(cfg, wl, lo, 512)
+        assert_same(ref, got[lo:lo + 512], f"config 4 loss {rate}")
+        ok_ops = int(got["user"][:, 0].sum())
+        assert (got["user"][:, 0] + got["user"][:, 3] >= 64).all()  # every op ended as ok or error (+ lease grants)
+        assert prev_ok is None or ok_ops < prev_ok
+        prev_ok = ok_ops
+
+
+def test_config4_seeds_to_first_bug(oracle):
+    # an injected stale-read bug in the server: the first failing seed is the oracle's
+    cfg, wl = m.Config(packet_loss_rate=0.1), m.Workload.etcd(bug=1)
+    got, bm, st = run_gpu(cfg, wl, 0, 16384)
+    assert st["n_fail"] > 0 and (got["fail_code"][got["status"] == m.ST_FAIL_ASSERT] == 61).all()
+    first = int(st["first_fail_seed"])
+    ref = oracle.run_many(cfg, wl, 0, first + 1)
+    assert (ref["status"][:first] == m.ST_PASS).all() and ref["status"][first] == m.ST_FAIL_ASSERT
 
 
 def test_burst_checkpoint_resume_equals_run_to_completion():

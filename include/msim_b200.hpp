@@ -108,6 +108,13 @@ struct Workload {
     w.desc.n_nodes = clients + 1, w.desc.p[0] = ops, w.desc.p[2] = bits, w.desc.p[3] = bug;
     return w;
   }
+  /// tonic-example Greeter under madsim-tonic + kill/restart chaos of the client nodes
+  static Workload tonic(uint32_t clients = 6, uint64_t rounds = 10, uint64_t think_ns = 100000000, bool restart_only = false) {
+    Workload w;
+    check(msim_workload_default(MSIM_WL_TONIC, &w.desc));
+    w.desc.n_nodes = clients + 1, w.desc.p[0] = rounds, w.desc.p[1] = think_ns, w.desc.p[2] = restart_only ? 1 : 0;
+    return w;
+  }
 };
 
 namespace runtime {

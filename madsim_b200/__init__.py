@@ -36,6 +36,7 @@ from ._native import (  # noqa: F401
     WL_SLEEP,
     WL_STREAM,
     WL_ETCD,
+    WL_TONIC,
     MsimError,
 )
 

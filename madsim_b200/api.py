@@ -114,11 +114,17 @@ class Workload:
         bits = struct.unpack("<I", struct.pack("<f", timeout_rate))[0]
         return Workload(N.WL_ETCD, clients + 1, [ops, think_ns, bits, bug, lease_ttl_s, 0, 0, 0])
 
+    @staticmethod
+    def tonic(clients: int = 6, rounds: int = 10, think_ns: int = 100 * MS, restart_only: bool = False) -> "Workload":
+        """tonic-example Greeter service under madsim-tonic (a fresh endpoint + handshake + connection per
+        unary call) while a supervisor kills / restarts the client nodes (BASELINE config 5)."""
+        return Workload(N.WL_TONIC, clients + 1, [rounds, think_ns, int(restart_only), 0, 0, 0, 0, 0])
+
     def to_c(self) -> N.MsimWorkloadDesc:
         return N.MsimWorkloadDesc(self.workload, self.n_nodes, (C.c_uint64 * 8)(*[int(x) for x in self.p]))
 
     def name(self) -> str:
-        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos", 4: "stream", 5: "etcd"}.get(self.workload, "?")
+        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos", 4: "stream", 5: "etcd", 6: "tonic"}.get(self.workload, "?")
 
 
 class SimulationFailure(AssertionError):

@@ -958,6 +958,11 @@ MSIM_NOUNROLL
     ch_flags(d_rx) &= ~CH_RX_ALIVE;  // UnboundedReceiver dropped: the peer's send fails
     if (!((ch_flags(d_tx) | ch_flags(d_rx)) & (CH_TX_ALIVE | CH_RX_ALIVE))) b(L::B_CONN_USED, c) = 0;
   }
+  /// Sender::is_closed / the ready state of Sender::closed() (endpoint.rs:247-253): the peer dropped its Receiver
+  MSIM_HD bool conn_tx_closed(int t) const {
+    int e = t_conn(t);
+    return !(ch_flags(e) & CH_RX_ALIVE);  // direction 2*conn+side is the one this end sends on
+  }
   /// Timer callback of NetSim::send -> EndpointSocket::deliver -> Mailbox::deliver
   /// (endpoint.rs:310-351).  The target socket OBJECT was captured at send time: if it has
   /// been closed/reset since, the message lands in a mailbox nobody can read (dropped here).

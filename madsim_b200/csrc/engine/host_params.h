@@ -44,6 +44,11 @@ inline int workload_defaults(uint32_t workload, msim_workload_desc* d) {
       d->p[1] = 50 * NS_PER_MS;
       d->p[4] = 1;
       return 0;
+    case MSIM_WL_TONIC:
+      d->n_nodes = 7;
+      d->p[0] = 10;
+      d->p[1] = 100 * NS_PER_MS;
+      return 0;
     case MSIM_WL_CHAOS:
       d->n_nodes = 1;
       d->p[0] = 8;
@@ -154,6 +159,13 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
       P.p[6] = rate == 1.0f ? 0 : (u64)((double)rate * 18446744073709551616.0);
       break;
     }
+    case MSIM_WL_TONIC:
+      if (P.n_nodes == 0) P.n_nodes = 7;
+      if (P.n_nodes < 2 || P.n_nodes > 7 || wl.p[2] > 1) {
+        if (err) *err = "tonic: need 1..6 client nodes, flags <= 1";
+        return MSIM_EINVAL;
+      }
+      break;
     case MSIM_WL_CHAOS:
       if (wl.p[1] == 0) {
         if (err) *err = "chaos: period must be > 0";

@@ -5,4 +5,5 @@
 #include "sleep.h"
 #include "stream.h"
 #include "etcd.h"
+#include "tonic.h"
 #define MSIM_HAVE_RAFT 1

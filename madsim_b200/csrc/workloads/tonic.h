@@ -1,0 +1,220 @@
+// MSIM_WL_TONIC — BASELINE config 5 / SURVEY §8(f) row 3: the tonic-example Greeter service under
+// madsim-tonic while a supervisor kills / restarts the client nodes
+// (tonic-example/tests/test.rs:155-202 client_crash, widened to six client nodes; unary calls).
+//
+//   Server::serve_with_shutdown    madsim-tonic/src/transport/server.rs:217-336
+//   Endpoint::connect / connect_ep madsim-tonic/src/transport/channel.rs:75-111  (fresh endpoint + handshake per call)
+//   MultiEndpoint::connect1        channel.rs:294-307
+//   Grpc::unary                    madsim-tonic/src/client.rs:52-78
+//   MyGreeter::say_hello           tonic-example/src/lib.rs:48-63
+//   Handle::{kill,restart}         madsim/src/sim/task/mod.rs:356-401: a restarted node's old sockets
+//                                  stay bound (BindGuard::drop skips killed incarnations, net/mod.rs:483-493)
+//
+// Oracle twin: oracle/workloads_tonic.hpp.
+#pragma once
+#include "../engine/engine.h"
+
+namespace msim {
+
+struct WL_Tonic {
+  enum : int { S_HANDLED = 0, S_CNT, S_ROUND, S_C, S_END };  // wl_s scalars
+  enum : int { F_REPLIES = 0, F_STARTS, F_NFIELD };           // wl_w per client node
+  struct Caps {
+    static constexpr int NT = 24, TQ = 64, NMSG = 2, NSOCK = 24, NREG = 1, NMBOX = 1, NNODE = 8, NPARK = 1;
+    static constexpr int WQ = 0, WW = F_NFIELD, WS = S_END;
+    static constexpr bool USES_JOIN = false;
+    static constexpr bool USES_KILL = true;
+    static constexpr int NCONN = 16, NCQ = 2, NACC = 16;
+  };
+  enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT };
+  enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u };
+  enum : u32 { ST_OK = 0, ST_INVALID_ARGUMENT = 1 };
+  static constexpr u32 MAIN_KIND = K_MAIN;
+  static constexpr u32 SERVER_ADDR = (IPK_NODE << 24) | (1u << 16) | 50051u;  // 10.0.0.1:50051
+  /// NodeBuilder::init(|| tonic_client(c)) — what Handle::restart re-runs
+  static MSIM_HD int init_kind(int) { return K_CLIENT; }
+  static MSIM_HD u32 reply_for(u32 name, u32 remote_addr) { return name * 31u + addr_node(remote_addr); }
+  template <class E>
+  static MSIM_HD int panic(E& e, u32 code) {
+    e.ya = code;
+    return RQ_PANIC;
+  }
+
+  template <class E>
+  static MSIM_HD int fsm(E& e, int t) {
+    using L = typename E::L;
+    const Params& P = *e.P;
+    const u32 n_clients = P.n_nodes - 1;
+    for (;;) switch (e.t_kind(t) * 16 + e.t_pc(t)) {
+        // ---- wl_tonic_main ----
+        case K_MAIN * 16 + 0:
+          e.t_pc(t) = 1;
+          e.ya = NODE_IP;
+          return RQ_CREATE_NODE;
+        case K_MAIN * 16 + 1:  // node0.spawn(tonic_serve)
+          e.t_pc(t) = 2;
+          e.ya = K_SERVE, e.yb = 1, e.yc = e.yd = 0, e.xa = e.xb = 0;
+          return RQ_SPAWN;
+        case K_MAIN * 16 + 2:
+          e.t_pc(t) = 3;
+          e.xa = NS_PER_SEC;
+          return RQ_SLEEP_FOR;
+        case K_MAIN * 16 + 3:  // client nodes: create_node().ip().init(tonic_client).build()
+          if (e.wl_s(S_CNT) < n_clients) {
+            e.wl_s(S_CNT)++;
+            e.ya = NODE_IP | NODE_INIT;
+            return RQ_CREATE_NODE;
+          }
+          e.t_pc(t) = 4;
+          // fallthrough
+        case K_MAIN * 16 + 4:  // for i in 0..rounds { sleep(gen_range(0 s..5 s))
+          if ((u64)e.wl_s(S_ROUND) >= P.p[0]) {
+            e.t_pc(t) = 8;
+            e.xa = NS_PER_SEC;
+            return RQ_SLEEP_FOR;
+          }
+          e.t_pc(t) = 5;
+          e.xa = e.sample_inclusive_u64(0, 5 * NS_PER_SEC - 1);  // UniformDuration Medium
+          return RQ_SLEEP_FOR;
+        case K_MAIN * 16 + 5:  // c = gen_range(0..n_clients)
+          e.t_pc(t) = 6;
+          e.xa = 0, e.xb = n_clients;
+          return RQ_GEN_RANGE;
+        case K_MAIN * 16 + 6:  // k = gen_range(0..4)
+          e.wl_s(S_C) = (u32)e.ret64;
+          e.t_pc(t) = 7;
+          e.xa = 0, e.xb = 4;
+          return RQ_GEN_RANGE;
+        case K_MAIN * 16 + 7: {
+          int id = 2 + (int)e.wl_s(S_C);
+          if (e.ret64 == 3 && !(P.p[2] & 1))
+            e.kill(id);
+          else
+            e.restart(id);
+          e.wl_s(S_ROUND)++;
+          e.t_pc(t) = 4;
+          continue;
+        }
+        case K_MAIN * 16 + 8: {
+          u32 replies = 0, starts = 0;
+          for (u32 c = 0; c < n_clients; c++) replies += e.wl_w(F_REPLIES, 2 + c), starts += e.wl_w(F_STARTS, 2 + c);
+          if (e.wl_s(S_HANDLED) < replies) return panic(e, 74);
+          e.w(L::W_USER0) = replies;
+          e.w(L::W_USER1) = starts;
+          e.w(L::W_USER2) = e.wl_s(S_HANDLED);
+          e.w(L::W_USER3) = e.w(L::W_MSG_COUNT);
+          return RQ_READY;
+        }
+
+        // ---- tonic_serve ----
+        case K_SERVE * 16 + 0:
+          e.t_pc(t) = 1;
+          e.ya = SERVER_ADDR;
+          return RQ_BIND;
+        case K_SERVE * 16 + 1:
+          if (e.ret < 0) return panic(e, 0);
+          e.t_pc(t) = 2;
+          // fallthrough
+        case K_SERVE * 16 + 2:
+          e.t_pc(t) = 3;
+          return RQ_ACCEPT1;
+        case K_SERVE * 16 + 3:  // the connection's first message, awaited inline
+          if (e.ret < 0) return panic(e, 0);
+          e.t_b(t) = e.rfrom;
+          e.t_pc(t) = 4;
+          return RQ_CH_RECV;
+        case K_SERVE * 16 + 4:
+          if (e.ret < 0) {  // Err(_) => continue: a handshake (or a killed client); tx, rx drop
+            e.conn_drop_end(t);
+            e.t_pc(t) = 2;
+            continue;
+          }
+          e.t_pc(t) = 2;  // spawn the response task with tx (and the request)
+          e.ya = K_RSP | SPAWN_CONN, e.yb = e.t_node(t), e.yc = e.rv0, e.yd = e.t_b(t), e.xa = e.rv1, e.xb = 0;
+          return RQ_SPAWN;
+
+        // ---- tonic_response_task ----
+        case K_RSP * 16 + 0:
+          e.wl_s(S_HANDLED)++;
+          e.t_pc(t) = 1;
+          if (e.t_a(t) == ERROR_NAME) {
+            e.yb = ST_INVALID_ARGUMENT, e.yc = 0;
+            return RQ_CH_SEND;
+          }
+          if (e.conn_tx_closed(t)) return RQ_READY;  // select_biased!{ tx.closed() => return, .. }
+          e.yb = ST_OK, e.yc = reply_for(e.t_a(t), e.t_b(t));
+          return RQ_CH_SEND;
+        case K_RSP * 16 + 1:
+          return RQ_READY;
+
+        // ---- tonic_client: the client node's init task ----
+        case K_CLIENT * 16 + 0:  // GreeterClient::connect: connect_ep, then drop it
+          e.wl_w(F_STARTS, e.t_node(t))++;
+          e.t_pc(t) = 1;
+          e.ya = mk_addr(IPK_UNSPEC, 0, 0);
+          return RQ_BIND;
+        case K_CLIENT * 16 + 1:
+          if (e.ret < 0) return panic(e, 70);
+          e.t_pc(t) = 2;
+          e.ya = SERVER_ADDR;
+          return RQ_CONNECT1;
+        case K_CLIENT * 16 + 2:
+          if (e.ret < 0) return panic(e, 70);
+          e.conn_drop_end(t);
+          e.sock_unref(t);
+          e.t_b(t) = 0;  // seq
+          e.t_pc(t) = 3;
+          // fallthrough
+        case K_CLIENT * 16 + 3:  // loop { name = gen_range(0..10) == 0 ? "error" : "Tonic"
+          e.t_pc(t) = 4;
+          e.xa = 0, e.xb = 10;
+          return RQ_GEN_RANGE;
+        case K_CLIENT * 16 + 4:  // Grpc::unary -> connect_ep: Endpoint::connect
+          e.t_a(t) = e.ret64 == 0 ? (u32)ERROR_NAME : (u32)NAME;
+          e.t_pc(t) = 5;
+          e.ya = mk_addr(IPK_UNSPEC, 0, 0);
+          return RQ_BIND;
+        case K_CLIENT * 16 + 5:  // the handshake connection
+          if (e.ret < 0) return panic(e, 71);
+          e.t_pc(t) = 6;
+          e.ya = SERVER_ADDR;
+          return RQ_CONNECT1;
+        case K_CLIENT * 16 + 6:  // the request's connection
+          if (e.ret < 0) return panic(e, 71);
+          e.conn_drop_end(t);
+          e.t_pc(t) = 7;
+          e.ya = SERVER_ADDR;
+          return RQ_CONNECT1;
+        case K_CLIENT * 16 + 7:
+          if (e.ret < 0) return panic(e, 71);
+          e.t_pc(t) = 8;
+          e.yb = e.t_a(t), e.yc = e.t_b(t);
+          return RQ_CH_SEND;
+        case K_CLIENT * 16 + 8:
+          if (e.ret < 0) return panic(e, 71);
+          e.t_pc(t) = 9;
+          return RQ_CH_RECV;
+        case K_CLIENT * 16 + 9: {
+          if (e.ret < 0) return panic(e, 71);
+          u32 node = e.t_node(t);
+          u32 st = e.rv0, reply = e.rv1;
+          e.conn_drop_end(t);  // rx, tx, then the last BindGuard reference
+          e.sock_unref(t);
+          if (e.t_a(t) == ERROR_NAME) {
+            if (st != ST_INVALID_ARGUMENT) return panic(e, 72);
+          } else if (st != ST_OK || reply != NAME * 31u + node) {
+            return panic(e, 73);
+          }
+          e.wl_w(F_REPLIES, node)++;
+          e.t_b(t)++;
+          e.t_pc(t) = 3;
+          e.xa = P.p[1];
+          return RQ_SLEEP_FOR;
+        }
+        default:
+          return panic(e, 0xbad);
+      }
+  }
+};
+
+}  // namespace msim

@@ -92,6 +92,17 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
         rt.teardown();
         break;
       }
+      case MSIM_WL_TONIC: {
+        TonicParams tp;
+        tp.n_clients = (wl->n_nodes ? wl->n_nodes : 7) - 1;
+        tp.rounds = wl->p[0];
+        tp.think_ns = wl->p[1];
+        tp.flags = u32(wl->p[2]);
+        if (tp.n_clients < 1 || tp.n_clients > 6) return MSIM_EINVAL;
+        rt.block_on(wl_tonic_main(tp, &user));
+        rt.teardown();
+        break;
+      }
       case MSIM_WL_CHAOS:
         rt.block_on(wl_chaos_main(wl->p[0], wl->p[1], u32(wl->p[2]), &user));
         break;

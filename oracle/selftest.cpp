@@ -378,6 +378,28 @@ static void etcd_case(F client) {
   rt.teardown();
 }
 
+// ---- tonic-example/tests/test.rs:22-70 basic() (unary part), :139-151 invalid_address() ----
+static Async<Unit> tonic_basic_client(SocketAddr server) {
+  co_await sleep(1 * SEC);
+  auto ep = co_await tonic_connect_ep(server);  // GreeterClient::connect
+  CHECK(ep.is_ok());
+  ep.ok.reset();
+  Payload q;
+  q.v[0] = TONIC_NAME;
+  auto r = co_await tonic_unary(server, q);
+  CHECK(r.is_ok() && r.ok->v[0] == TONIC_OK);
+  CHECK(r.ok->v[1] == tonic_reply_for(TONIC_NAME, SocketAddr{ip4(10, 0, 0, 2), 0}));  // "Hello Tonic! (10.0.0.2)"
+  q.v[0] = TONIC_ERROR;
+  r = co_await tonic_unary(server, q);
+  CHECK(r.is_ok() && r.ok->v[0] == TONIC_INVALID_ARGUMENT);  // Status::invalid_argument("error!")
+  co_return {};
+}
+static Async<Unit> tonic_invalid_address_client(SocketAddr server) {
+  auto ep = co_await tonic_connect_ep(server);  // nobody listens on 10.0.0.1:50051
+  CHECK(ep.is_err());
+  co_return {};
+}
+
 int main() {
   run_case("task::spawn_in_block_on", [] {
     Runtime rt;
@@ -560,6 +582,37 @@ int main() {
   });
   run_case("etcd::kv (madsim-etcd-client/tests/test.rs:9-62)", [] { etcd_case(etcd_kv_client); });
   run_case("etcd::lease expiry + lease not found (tests/test.rs:64-128)", [] { etcd_case(etcd_lease_client); });
+  run_case("tonic::basic unary + invalid_argument (tonic-example/tests/test.rs:22-70)", [] {
+    Runtime rt;
+    SocketAddr a{ip4(10, 0, 0, 1), 50051};
+    auto server = rt.create_node().ip(a.ip).build();
+    auto cl = rt.create_node().ip(ip4(10, 0, 0, 2)).build();
+    auto st = std::make_shared<TonicStats>();
+    server.spawn(tonic_serve(a, st));
+    auto h = cl.spawn(tonic_basic_client(a));
+    rt.block_on(join_unwrap(std::move(h)));
+    CHECK(st->handled == 2);
+    rt.teardown();
+  });
+  run_case("tonic::invalid_address (tests/test.rs:139-151)", [] {
+    Runtime rt;
+    SocketAddr a{ip4(10, 0, 0, 1), 50051};
+    rt.create_node().ip(a.ip).build();
+    auto cl = rt.create_node().ip(ip4(10, 0, 0, 2)).build();
+    auto h = cl.spawn(tonic_invalid_address_client(a));
+    rt.block_on(join_unwrap(std::move(h)));
+  });
+  run_case("tonic::client_crash (tests/test.rs:155-202): 10 random restarts of the client node", [] {
+    for (u64 seed = 0; seed < 8; seed++) {
+      Runtime rt(seed);
+      TonicParams p;
+      p.n_clients = 1, p.flags = 1;
+      std::array<u32, 4> user{};
+      rt.block_on(wl_tonic_main(p, &user));
+      CHECK(user[1] == 11 && user[0] > 0);  // the init task ran once per restart + once at build
+      rt.teardown();
+    }
+  });
   run_case("workload::raft elects exactly one leader", [] {
     for (u64 seed = 0; seed < 20; seed++) {
       Runtime rt(seed);

@@ -62,6 +62,7 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
     case MSIM_WL_CHAOS: return run_wl<WL_Chaos>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_STREAM: return run_wl<WL_Stream>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_ETCD: return run_wl<WL_Etcd>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
+    case MSIM_WL_TONIC: return run_wl<WL_Tonic>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
   }
   return MSIM_EINVAL;
 }
@@ -74,6 +75,7 @@ extern "C" int enginecheck_state_bytes(uint32_t workload) {
     case MSIM_WL_CHAOS: return Layout<WL_Chaos::Caps>::BYTES;
     case MSIM_WL_STREAM: return Layout<WL_Stream::Caps>::BYTES;
     case MSIM_WL_ETCD: return Layout<WL_Etcd::Caps>::BYTES;
+    case MSIM_WL_TONIC: return Layout<WL_Tonic::Caps>::BYTES;
   }
   return -1;
 }

@@ -55,6 +55,11 @@ CASES = [
     ("etcd-stale-read-bug", m.Config(packet_loss_rate=0.05), m.Workload.etcd(bug=1), 0, 64),
     ("etcd-reference-no-lease-panic", m.Config(), m.Workload.etcd(bug=2), 0, 64),
     ("etcd-always-timeout", m.Config(), m.Workload.etcd(ops=3, timeout_rate=1.0), 0, 16),
+    # tonic-example Greeter under madsim-tonic + kill/restart chaos (BASELINE config 5)
+    ("tonic", m.Config(), m.Workload.tonic(), 0, 32),
+    ("tonic-restart-only-1client", m.Config(), m.Workload.tonic(clients=1, restart_only=True), 0, 32),
+    ("tonic-loss1-client-panics", m.Config(packet_loss_rate=0.01), m.Workload.tonic(), 0, 32),
+    ("tonic-buggify-slow-server", m.Config(buggify=True), m.Workload.tonic(clients=3, rounds=5), 0, 32),
     # Handle::{kill,restart,pause,resume} + restart_on_panic (task/mod.rs:356-424,289-317)
     ("chaos", m.Config(), m.Workload.chaos(), 0, 200),
     ("chaos-long-panics", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 200),

@@ -89,6 +89,11 @@ CASES = [
     ("etcd-stale-read-bug", m.Config(packet_loss_rate=0.05), m.Workload.etcd(bug=1), 0, 300),
     ("etcd-reference-no-lease-panic", m.Config(), m.Workload.etcd(bug=2), 0, 300),
     ("etcd-always-timeout-buggify", m.Config(buggify=True), m.Workload.etcd(ops=3, timeout_rate=1.0), 0, 64),
+    ("tonic-kill-restart-chaos", m.Config(), m.Workload.tonic(), 0, 300),
+    ("tonic-restart-only-1client", m.Config(), m.Workload.tonic(clients=1, restart_only=True), 0, 200),
+    ("tonic-loss1-client-panics", m.Config(packet_loss_rate=0.01), m.Workload.tonic(), 0, 200),
+    ("tonic-buggify-slow-server", m.Config(buggify=True), m.Workload.tonic(clients=3, rounds=5), 0, 200),
+    ("tonic-16-rounds-slow-links", m.Config(send_latency_ns=(1 * m.MS, 400 * m.MS)), m.Workload.tonic(rounds=16, think_ns=0), 0, 200),
     ("chaos-kill-restart-pause", m.Config(), m.Workload.chaos(), 0, 500),
     ("chaos-restart-on-panic", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 500),
     ("chaos-always-panicking", m.Config(), m.Workload.chaos(rounds=4, period_ms=3000, panics=50), 0, 200),
@@ -166,6 +171,22 @@ def test_config4_seeds_to_first_bug(oracle):
     first = int(st["first_fail_seed"])
     ref = oracle.run_many(cfg, wl, 0, first + 1)
     assert (ref["status"][:first] == m.ST_PASS).all() and ref["status"][first] == m.ST_FAIL_ASSERT
+
+
+def test_config5_tonic_32768_seeds_kill_restart_chaos(oracle):
+    """BASELINE config 5: tonic-example Greeter under madsim-tonic, 7 nodes, 32768 seeds, kill/restart
+    chaos.  A 384-seed window bit-exact against the oracle; at full size: every seed passes (no reply
+    ever mismatches, the server survives every client crash), every client start is accounted for
+    (6 builds + one per restart), and the batch is deterministic across launch geometries."""
+    cfg, wl = m.Config(), m.Workload.tonic()
+    got, bm, st = run_gpu(cfg, wl, 0, 32768)
+    assert st["n_unfinished"] == 0 and st["n_pass"] == 32768 and not bm.any()
+    ref = oracle.run_many(cfg, wl, 20000, 384)
+    assert_same(ref, got[20000:20384], "config 5")
+    starts, replies, handled = got["user"][:, 1], got["user"][:, 0], got["user"][:, 2]
+    assert (starts >= 6).all() and (starts <= 16).all() and (handled >= replies).all() and (replies > 0).all()
+    again, _, _ = run_gpu(cfg, wl, 0, 32768, S=9, L=2)
+    assert np.array_equal(got, again)
 
 
 def test_burst_checkpoint_resume_equals_run_to_completion():

@@ -24,7 +24,7 @@ struct WL_Tonic {
     static constexpr int WQ = 0, WW = F_NFIELD, WS = S_END;
     static constexpr bool USES_JOIN = false;
     static constexpr bool USES_KILL = true;
-    static constexpr int NCONN = 16, NCQ = 2, NACC = 16;
+    static constexpr int NCONN = 32, NCQ = 2, NACC = 32;
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT };
   enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u };

@@ -106,6 +106,7 @@ typedef struct msim_config {
 #define MSIM_WL_CHAOS 3     /* kill/restart/pause supervisor schedule (task/mod.rs:852-1016)   */
 #define MSIM_WL_STREAM 4    /* reliable connect1/accept1 echo stream under partitions (net/mod.rs:337-430) */
 #define MSIM_WL_TONIC 6     /* tonic-example Greeter under madsim-tonic + kill/restart chaos, BASELINE config 5 */
+#define MSIM_WL_SIGNAL 7    /* time::interval + MissedTickBehavior, signal::ctrl_c, Handle::send_ctrl_c (interval.rs, signal.rs) */
 #define MSIM_WL_ETCD 5      /* madsim-etcd-client SimServer + KV clients + linearizability check, BASELINE config 4 */
 
 /* parameter slots p[] per workload
@@ -121,6 +122,8 @@ typedef struct msim_config {
  *           2 = clients also delete the leased key: reaches the crate's own expect("no lease")), p4 = lease ttl s (default 1)
  *  TONIC    n_nodes = 1 server + (n_nodes-1) client nodes (default 7); p0 = chaos rounds (default 10),
  *           p1 = think time ns between unary calls (default 100 ms), p2 = flags (1 = restart only, never kill)
+ *  SIGNAL   p0 = supervisor rounds (default 8), p1 = interval period ms (default 100),
+ *           p2 = MissedTickBehavior (0 Burst, 1 Delay, 2 Skip), p3 = flags (1 = the worker installs a ctrl-c handler; default 1)
  *  CHAOS    p0 = rounds, p1 = period ms, p2 = worker panics on its first p2 starts (restart_on_panic)
  *                                                         */
 #define MSIM_RAFT_FAULT_CLOG_NODE 1u

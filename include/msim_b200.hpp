@@ -108,6 +108,13 @@ struct Workload {
     w.desc.n_nodes = clients + 1, w.desc.p[0] = ops, w.desc.p[2] = bits, w.desc.p[3] = bug;
     return w;
   }
+  /// time::interval + MissedTickBehavior (0 Burst, 1 Delay, 2 Skip), signal::ctrl_c, Handle::send_ctrl_c
+  static Workload signal(uint64_t rounds = 8, uint64_t period_ms = 100, uint32_t behavior = 0, bool catch_ctrl_c = true) {
+    Workload w;
+    check(msim_workload_default(MSIM_WL_SIGNAL, &w.desc));
+    w.desc.p[0] = rounds, w.desc.p[1] = period_ms, w.desc.p[2] = behavior, w.desc.p[3] = catch_ctrl_c ? 1 : 0;
+    return w;
+  }
   /// tonic-example Greeter under madsim-tonic + kill/restart chaos of the client nodes
   static Workload tonic(uint32_t clients = 6, uint64_t rounds = 10, uint64_t think_ns = 100000000, bool restart_only = false) {
     Workload w;

@@ -37,6 +37,7 @@ from ._native import (  # noqa: F401
     WL_STREAM,
     WL_ETCD,
     WL_TONIC,
+    WL_SIGNAL,
     MsimError,
 )
 

@@ -120,11 +120,17 @@ class Workload:
         unary call) while a supervisor kills / restarts the client nodes (BASELINE config 5)."""
         return Workload(N.WL_TONIC, clients + 1, [rounds, think_ns, int(restart_only), 0, 0, 0, 0, 0])
 
+    @staticmethod
+    def signal(rounds: int = 8, period_ms: int = 100, behavior: int = 0, catch: bool = True) -> "Workload":
+        """time::interval with a MissedTickBehavior (0 Burst, 1 Delay, 2 Skip) on a worker node that a
+        supervisor sends ctrl-c to / restarts (time/interval.rs, signal.rs, Handle::send_ctrl_c)."""
+        return Workload(N.WL_SIGNAL, 1, [rounds, period_ms, behavior, int(catch), 0, 0, 0, 0])
+
     def to_c(self) -> N.MsimWorkloadDesc:
         return N.MsimWorkloadDesc(self.workload, self.n_nodes, (C.c_uint64 * 8)(*[int(x) for x in self.p]))
 
     def name(self) -> str:
-        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos", 4: "stream", 5: "etcd", 6: "tonic"}.get(self.workload, "?")
+        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos", 4: "stream", 5: "etcd", 6: "tonic", 7: "signal"}.get(self.workload, "?")
 
 
 class SimulationFailure(AssertionError):

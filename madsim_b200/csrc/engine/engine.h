@@ -48,6 +48,7 @@ enum : u8 {
   W_CONNECT = 10,    // connect1: rand_delay, then the connection request (net/mod.rs:337-364)
   W_ACCEPT = 11,     // accept1: rand_delay FIRST, then the next incoming connection (endpoint.rs:197-211)
   W_CH_RECV = 12,    // Receiver::recv: the channel's delay/back-off stream (net/mod.rs:385-402)
+  W_CTRLC = 13,      // signal::ctrl_c: watch::Receiver::changed() on the node's channel (signal.rs:4-8)
   WF_RD = 0x10,      // rand_delay not drawn yet: draw it now, then sleep on dl0
   WF_SLEEP = 0x20,   // sleeping on dl0
 };
@@ -73,6 +74,8 @@ enum : int {
   RQ_ACCEPT1,       // ep.accept1()                    -> ret 0, rfrom = peer address
   RQ_CH_SEND,       // conn.tx.send({yb, yc})          -> ret 0 / -1 ConnectionReset   (no await point)
   RQ_CH_RECV,       // conn.rx.recv()                  -> ret 0, rv0, rv1 / -1 ConnectionReset
+  RQ_SLEEP_RAW,     // Sleep::reset(xa) + await: the deadline is NOT clamped to now + 1 ms (time/sleep.rs:40-42, interval.rs:156)
+  RQ_CTRL_C,        // signal::ctrl_c().await (installs the node's handler on first use)
 };
 enum : u32 { SPAWN_EP = 0x100, SPAWN_JOINABLE = 0x200, SPAWN_CONN = 0x400 };  // clone the Endpoint / keep a JoinHandle / move the connection end
 enum : u32 { NODE_IP = 1, NODE_INIT = 2, NODE_RESTART_ON_PANIC = 4 };
@@ -136,7 +139,10 @@ struct Layout {
   static constexpr int W_CONN_SRC = W_CH_WAITER + ND;           // [NCONN] connector's source address
   static constexpr int NSA = C::NCONN ? C::NSOCK : 0;           // accept state exists only with connections
   static constexpr int W_ACC_WAITER = W_CONN_SRC + C::NCONN;    // [NSA] task waiting in accept1
-  static constexpr int NW = W_ACC_WAITER + NSA;
+  static constexpr int NCC = C::USES_CTRLC ? C::NNODE : 0;     // ctrl-c state exists only where it is awaited
+  static constexpr int W_N_CTRLC = W_ACC_WAITER + NSA;          // [NCC] NodeInfo::ctrl_c: installed<<31 | watch version
+  static constexpr int W_N_CTRLC_WAITER = W_N_CTRLC + NCC;      // [NCC] the receiver parked in changed() (slot<<20|gen) or NONE32
+  static constexpr int NW = W_N_CTRLC_WAITER + NCC;
   // ---- u8 section ----
   static constexpr int B_RQ = 0;                        // [NT] ready "queue": a Vec popped at a random index
   static constexpr int B_T_KIND = B_RQ + C::NT;
@@ -646,6 +652,7 @@ MSIM_NOUNROLL
     info_kill(n, n_epoch(n));  // old_info.kill()
     n_epoch(n) = n_epoch(n) + 1;
     n_flags(n) = n_flags(n) & ~(NF_KILLED | NF_PAUSED);
+    if (C::USES_CTRLC) w(L::W_N_CTRLC, n) = 0, w(L::W_N_CTRLC_WAITER, n) = NONE32;  // the new NodeInfo has no handler
     int kind = WL::init_kind(n);
     if (kind >= 0) spawn((u32)kind, n, TF_INIT);
   }
@@ -662,6 +669,35 @@ MSIM_NOUNROLL
   MSIM_HD void restart(int n) {
     store();
     restart_cold(sb, P, now, n);
+    load();
+  }
+  /// Handle::send_ctrl_c (task/mod.rs:427-441): watch::Sender::send if a handler was ever installed
+  /// on this NodeInfo (an error for "no receiver" is ignored), otherwise the node is killed
+  MSIM_HD void send_ctrl_c_inl(int n) {
+    if (!C::USES_CTRLC) {
+      kill_inl(n);
+      return;
+    }
+    u32 c = w(L::W_N_CTRLC, n);
+    if (c >> 31) {
+      w(L::W_N_CTRLC, n) = 0x80000000u | ((c + 1) & 0x7fffffffu);
+      wake_waiter(w(L::W_N_CTRLC_WAITER, n));
+    } else {
+      kill_inl(n);
+    }
+  }
+  static MSIM_NI void send_ctrl_c_cold(unsigned char* sb_, const Params* P_, u64 now_, int n) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.load();
+    e_.now = now_;
+    e_.send_ctrl_c_inl(n);
+    e_.store();
+  }
+  MSIM_HD void send_ctrl_c(int n) {
+    store();
+    send_ctrl_c_cold(sb, P, now, n);
     load();
   }
   MSIM_HD void pause(int n) { n_flags(n) = n_flags(n) | NF_PAUSED; }
@@ -705,6 +741,7 @@ MSIM_NOUNROLL
     w(L::W_NEXT_NODE) = n + 1;
     n_flags(n) = NF_EXISTS | ((flags & NODE_IP) ? NF_HAS_IP : 0) | ((flags & NODE_RESTART_ON_PANIC) ? NF_RESTART_ON_PANIC : 0);
     n_epoch(n) = 0;
+    if (C::USES_CTRLC) w(L::W_N_CTRLC, n) = 0, w(L::W_N_CTRLC_WAITER, n) = NONE32;
     int kind = (flags & NODE_INIT) ? WL::init_kind((int)n) : -1;
     if (kind >= 0) spawn((u32)kind, n, TF_INIT);
     return (int)n;
@@ -1296,6 +1333,22 @@ MSIM_NOUNROLL
               }
               break;
             }
+            case W_CTRLC: {  // rx.changed(): ready once the version moved past the one seen at subscribe()
+              if (!C::USES_CTRLC) break;
+              int n = t_node(t);
+              if ((w(L::W_N_CTRLC, n) & 0x7fffffffu) != (u32)t_dl1(t)) {
+                ret = 0;
+                wt = W_NONE;
+              } else {
+                u32 me = ((u32)t << 20) | t_gen(t);
+                u32 cur = w(L::W_N_CTRLC_WAITER, n);
+                if (cur != NONE32 && cur != me && t_gen(cur >> 20) == (cur & 0xfffffu) && t_wait(cur >> 20) == W_CTRLC)
+                  fail_cap(MSIM_CAP_REGISTERED);  // one parked receiver per node in this build
+                w(L::W_N_CTRLC_WAITER, n) = me;
+                pend = true;
+              }
+              break;
+            }
             case W_JOIN: {
               if (!C::USES_JOIN) break;
               int target = (int)t_c(t);
@@ -1351,6 +1404,19 @@ MSIM_NOUNROLL
           t_dl0(t) = sleep_deadline(xa);
           t_wait(t) = W_SLEEP | WF_SLEEP;
           break;
+        case RQ_SLEEP_RAW:
+          t_dl0(t) = xa;
+          t_wait(t) = W_SLEEP | WF_SLEEP;
+          break;
+        case RQ_CTRL_C: {  // NodeInfo::ctrl_c(): get_or_insert the watch channel, subscribe at the current version
+          if (!C::USES_CTRLC) break;
+          int n = t_node(t);
+          u32 c = w(L::W_N_CTRLC, n) | 0x80000000u;
+          w(L::W_N_CTRLC, n) = c;
+          t_dl1(t) = c & 0x7fffffffu;
+          t_wait(t) = W_CTRLC;
+          break;
+        }
         case RQ_RAND_DELAY:
           t_wait(t) = W_SLEEP | WF_RD;
           break;

@@ -49,6 +49,12 @@ inline int workload_defaults(uint32_t workload, msim_workload_desc* d) {
       d->p[0] = 10;
       d->p[1] = 100 * NS_PER_MS;
       return 0;
+    case MSIM_WL_SIGNAL:
+      d->n_nodes = 1;
+      d->p[0] = 8;
+      d->p[1] = 100;
+      d->p[3] = 1;
+      return 0;
     case MSIM_WL_CHAOS:
       d->n_nodes = 1;
       d->p[0] = 8;
@@ -163,6 +169,12 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
       if (P.n_nodes == 0) P.n_nodes = 7;
       if (P.n_nodes < 2 || P.n_nodes > 7 || wl.p[2] > 1) {
         if (err) *err = "tonic: need 1..6 client nodes, flags <= 1";
+        return MSIM_EINVAL;
+      }
+      break;
+    case MSIM_WL_SIGNAL:
+      if (wl.p[1] == 0 || wl.p[2] > 2 || wl.p[3] > 1) {
+        if (err) *err = "signal: period must be > 0, behavior 0..2, flags <= 1";
         return MSIM_EINVAL;
       }
       break;

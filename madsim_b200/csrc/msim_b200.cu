@@ -252,6 +252,7 @@ int state_bytes_of(uint32_t workload) {
     case MSIM_WL_STREAM: return Layout<WL_Stream::Caps>::BYTES;
     case MSIM_WL_ETCD: return Layout<WL_Etcd::Caps>::BYTES;
     case MSIM_WL_TONIC: return Layout<WL_Tonic::Caps>::BYTES;
+    case MSIM_WL_SIGNAL: return Layout<WL_Signal::Caps>::BYTES;
   }
   return -1;
 }
@@ -350,6 +351,7 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
     case MSIM_WL_STREAM: e = launch_wl<WL_Stream>(a, grid, block, b->smem, b->stream); break;
     case MSIM_WL_ETCD: e = launch_wl<WL_Etcd>(a, grid, block, b->smem, b->stream); break;
     case MSIM_WL_TONIC: e = launch_wl<WL_Tonic>(a, grid, block, b->smem, b->stream); break;
+    case MSIM_WL_SIGNAL: e = launch_wl<WL_Signal>(a, grid, block, b->smem, b->stream); break;
     default: return set_err(MSIM_EINVAL, "unknown workload");
   }
   if (e != cudaSuccess) return set_err(MSIM_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));

@@ -6,4 +6,5 @@
 #include "stream.h"
 #include "etcd.h"
 #include "tonic.h"
+#include "signal.h"
 #define MSIM_HAVE_RAFT 1

@@ -16,6 +16,7 @@ struct WL_Chaos {
     // USES_KILL: can a task be dropped while queued (kill / restart / pause / abort / a returning init task)?
     static constexpr bool USES_JOIN = false;  // does any task await a JoinHandle?
     static constexpr bool USES_KILL = true;
+    static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
     static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 { K_MAIN = 0, K_WORKER = 1 };

@@ -31,6 +31,7 @@ struct WL_Etcd {
     static constexpr int WQ = 0, WW = F_NFIELD, WS = S_END;
     static constexpr bool USES_JOIN = true;
     static constexpr bool USES_KILL = false;
+    static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
     static constexpr int NCONN = 6, NCQ = 2, NACC = 4;
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_TICK, K_REQ, K_CLIENT };

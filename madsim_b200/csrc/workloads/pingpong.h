@@ -15,6 +15,7 @@ struct WL_PingPong {
     // USES_KILL: can a task be dropped while queued (kill / restart / pause / abort / a returning init task)?
     static constexpr bool USES_JOIN = true;  // does any task await a JoinHandle?
     static constexpr bool USES_KILL = false;
+    static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
     static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 { K_MAIN = 0, K_SERVER = 1, K_CLIENT = 2 };

@@ -16,6 +16,7 @@ struct WL_Stream {
     // USES_KILL: can a task be dropped while queued (kill / restart / pause / abort / a returning init task)?
     static constexpr bool USES_JOIN = true;  // does any task await a JoinHandle?
     static constexpr bool USES_KILL = false;
+    static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
     static constexpr int NCONN = 2, NCQ = 4, NACC = 2;
   };
   enum : u32 { K_MAIN = 0, K_SERVER, K_ECHO, K_CLIENT, K_FAULT };

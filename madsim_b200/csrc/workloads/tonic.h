@@ -24,6 +24,7 @@ struct WL_Tonic {
     static constexpr int WQ = 0, WW = F_NFIELD, WS = S_END;
     static constexpr bool USES_JOIN = false;
     static constexpr bool USES_KILL = true;
+    static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
     static constexpr int NCONN = 32, NCQ = 2, NACC = 32;
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT };

@@ -103,6 +103,17 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
         rt.teardown();
         break;
       }
+      case MSIM_WL_SIGNAL: {
+        SignalParams sp;
+        sp.rounds = wl->p[0];
+        sp.period_ms = wl->p[1];
+        sp.behavior = u32(wl->p[2]);
+        sp.flags = u32(wl->p[3]);
+        if (sp.period_ms == 0 || sp.behavior > 2) return MSIM_EINVAL;
+        rt.block_on(wl_signal_main(sp, &user));
+        rt.teardown();
+        break;
+      }
       case MSIM_WL_CHAOS:
         rt.block_on(wl_chaos_main(wl->p[0], wl->p[1], u32(wl->p[2]), &user));
         break;

@@ -61,6 +61,7 @@ struct Runtime {
   void pause(u64 id) { task.handle.pause(id); }
   void resume(u64 id) { task.handle.resume(id); }
   bool is_exit(u64 id) { return task.handle.is_exit(id); }
+  void send_ctrl_c(u64 id) { task.handle.send_ctrl_c(id); }
 
   struct NodeHandle {
     Spawner task;
@@ -149,6 +150,81 @@ Timeout<F> timeout(u64 dur_ns, F fut) {  // time/mod.rs:128-140: the Sleep is cr
   return Timeout<F>{std::move(fut), sleep(dur_ns)};
 }
 constexpr u64 MS = 1000000ull, SEC = 1000000000ull, US = 1000ull;
+
+// ---- time/interval.rs:39-169 ----
+enum class MissedTickBehavior { Burst, Delay, Skip };
+struct Interval {
+  Sleep delay;
+  u64 period;
+  MissedTickBehavior missed_tick_behavior = MissedTickBehavior::Burst;
+  /// MissedTickBehavior::next_timeout (:73-100)
+  u64 next_timeout(u64 timeout, u64 now_, u64 period_) const {
+    switch (missed_tick_behavior) {
+      case MissedTickBehavior::Burst: return timeout + period_;
+      case MissedTickBehavior::Delay: return now_ + period_;
+      case MissedTickBehavior::Skip: return now_ + period_ - ((now_ - timeout) % period_);
+    }
+    return 0;
+  }
+  /// poll_tick (:134-160): the Sleep, then re-arm it; yields the instant the tick was scheduled for
+  Poll<u64> poll(Context& cx) {
+    if (!delay.poll(cx).ready()) return Poll<u64>::pending();
+    u64 timeout = delay.deadline;
+    u64 now_ = now();
+    u64 next = now_ > timeout + 5 * MS ? next_timeout(timeout, now_, period) : timeout + period;
+    delay.reset(next);
+    return Poll<u64>::done(timeout);
+  }
+  struct Tick {
+    Interval* iv;
+    Poll<u64> poll(Context& cx) { return iv->poll(cx); }
+  };
+  Tick tick() { return Tick{this}; }
+  void set_missed_tick_behavior(MissedTickBehavior b) { missed_tick_behavior = b; }
+};
+inline Interval interval(u64 period_ns) {  // :39-42
+  if (period_ns == 0) panic("`period` must be non-zero.");
+  return Interval{sleep_until(now()), period_ns};
+}
+
+// ---- signal.rs:4-8 ctrl_c(): subscribe to the node's watch channel, then rx.changed() ----
+struct CtrlC {
+  std::shared_ptr<CtrlCChannel> ch;
+  u64 seen;
+  u64 key = 0;
+  CtrlC(std::shared_ptr<CtrlCChannel> c) : ch(std::move(c)), seen(ch->version) {}
+  CtrlC(CtrlC&& o) noexcept : ch(std::move(o.ch)), seen(o.seen), key(std::exchange(o.key, 0)) {}
+  CtrlC(const CtrlC&) = delete;
+  ~CtrlC() { unregister(); }
+  void unregister() {
+    if (!key || !ch) return;
+    for (size_t i = 0; i < ch->waiters.size(); i++)
+      if (ch->waiters[i].first == key) {
+        ch->waiters.erase(ch->waiters.begin() + long(i));
+        break;
+      }
+    key = 0;
+  }
+  Poll<Unit> poll(Context& cx) {
+    if (ch->version != seen) {
+      unregister();
+      return Poll<Unit>::done({});
+    }
+    if (key) {
+      for (auto& kv : ch->waiters)
+        if (kv.first == key) kv.second = cx.waker;
+    } else {
+      key = ch->next_key++;
+      ch->waiters.emplace_back(key, cx.waker);
+    }
+    return Poll<Unit>::pending();
+  }
+};
+inline CtrlC ctrl_c() {
+  auto node = current_task()->node;
+  if (!node->ctrl_c) node->ctrl_c = std::make_shared<CtrlCChannel>();  // "ctrl-c signal handler installed"
+  return CtrlC(node->ctrl_c);
+}
 
 // ---- rpc.rs:96-105, 134-166 ----
 inline Async<Result<Payload>> Endpoint::call_timeout(SocketAddr dst, u64 req_tag, Payload request,

@@ -32,6 +32,22 @@ struct TaskInfo {
   }
 };
 
+/// tokio::sync::watch<()> as NodeInfo::ctrl_c uses it (task/mod.rs:105-112,167-176): a version
+/// counter + the wakers of the receivers parked in `changed()` (Notify::notify_waiters order =
+/// registration order).
+struct CtrlCChannel {
+  u64 version = 0;
+  u64 next_key = 1;
+  std::vector<std::pair<u64, Waker>> waiters;
+  /// watch::Sender::send(()): Err when no receiver is alive — the caller ignores it
+  void send() {
+    version++;
+    auto ws = std::move(waiters);
+    waiters.clear();
+    for (auto& kv : ws) kv.second.wake();
+  }
+};
+
 /// task/mod.rs:87-112
 struct NodeInfo {
   u64 id;
@@ -42,6 +58,7 @@ struct NodeInfo {
   bool paused = false;
   bool killed = false;
   std::vector<std::weak_ptr<TaskInfo>> tasks;  // spawn order
+  std::shared_ptr<CtrlCChannel> ctrl_c;        // None until signal::ctrl_c() is first called on the node
   /// task/mod.rs:133-140
   void kill() {
     killed = true;
@@ -339,6 +356,15 @@ struct TaskHandle {
     for (auto& r : parked) r->drop_runnable();
     old->kill();
     if (n.init) n.init(spawner_for(n.info));
+  }
+  /// :427-441: delivered if a handler was ever installed on this NodeInfo, else the node is killed
+  void send_ctrl_c(u64 id) {
+    Node& n = node(id);
+    if (n.info->ctrl_c) {
+      n.info->ctrl_c->send();
+      return;
+    }
+    kill(id);
   }
   void pause(u64 id) { node(id).info->paused = true; }
   void resume(u64 id) {

@@ -400,6 +400,47 @@ static Async<Unit> tonic_invalid_address_client(SocketAddr server) {
   co_return {};
 }
 
+// ---- signal.rs:23-66 ctrl_c_kill / ctrl_c_catch; interval.rs:73-160 ----
+static Async<Unit> pending_task() {
+  co_await PendingForever<Unit>{};
+  co_return {};
+}
+static Async<Unit> ctrl_c_kill_main(Runtime* rt, Runtime::NodeHandle node) {
+  auto h = node.spawn(pending_task());
+  CHECK(!h.is_finished());
+  rt->send_ctrl_c(node.id());  // no handler was ever installed: ctrl-c kills the node
+  co_await sleep(1 * SEC);
+  CHECK(h.is_finished());
+  co_return {};
+}
+static Async<Unit> ctrl_c_catch_task(Flag flag) {
+  co_await ctrl_c();
+  *flag = 1;
+  co_await PendingForever<Unit>{};
+  co_return {};
+}
+static Async<Unit> ctrl_c_catch_main(Runtime* rt, Runtime::NodeHandle node) {
+  for (int i = 0; i < 2; i++) {
+    Flag flag = std::make_shared<u32>(0);
+    auto h = node.spawn(ctrl_c_catch_task(flag));
+    co_await sleep(1 * SEC);
+    CHECK(*flag == 0 && !h.is_finished());
+    rt->send_ctrl_c(node.id());  // caught: the node survives
+    co_await sleep(1 * SEC);
+    CHECK(*flag == 1 && !h.is_finished());
+  }
+  co_return {};
+}
+static Async<Unit> interval_main(MissedTickBehavior b, std::shared_ptr<std::vector<u64>> out) {
+  u64 t0 = now();
+  Interval iv = interval(100 * MS);
+  iv.set_missed_tick_behavior(b);
+  out->push_back(co_await iv.tick() - t0);  // the first tick: sleep_until(now) = now + 1 ms
+  co_await sleep(350 * MS);                 // miss three ticks
+  for (int i = 0; i < 4; i++) out->push_back(co_await iv.tick() - t0);
+  co_return {};
+}
+
 int main() {
   run_case("task::spawn_in_block_on", [] {
     Runtime rt;
@@ -612,6 +653,29 @@ int main() {
       CHECK(user[1] == 11 && user[0] > 0);  // the init task ran once per restart + once at build
       rt.teardown();
     }
+  });
+  run_case("signal::ctrl_c_kill (signal.rs:23-40)", [] {
+    Runtime rt;
+    auto node = rt.create_node().build();
+    rt.block_on(ctrl_c_kill_main(&rt, node));
+  });
+  run_case("signal::ctrl_c_catch (signal.rs:42-66)", [] {
+    Runtime rt;
+    auto node = rt.create_node().build();
+    rt.block_on(ctrl_c_catch_main(&rt, node));
+  });
+  run_case("time::interval MissedTickBehavior Burst / Delay / Skip (interval.rs:73-160)", [] {
+    auto run = [](MissedTickBehavior b) {
+      Runtime rt;
+      auto out = std::make_shared<std::vector<u64>>();
+      rt.block_on(interval_main(b, out));
+      for (auto& v : *out) v /= MS;  // whole ms: the 50-100 ns poll jitter only matters for Delay's `now`
+      return *out;
+    };
+    // scheduled instants: 1 ms, then after ~351 ms of work three ticks (101, 201, 301) are overdue
+    CHECK((run(MissedTickBehavior::Burst) == std::vector<u64>{1, 101, 201, 301, 401}));
+    CHECK((run(MissedTickBehavior::Delay) == std::vector<u64>{1, 101, 451, 551, 651}));
+    CHECK((run(MissedTickBehavior::Skip) == std::vector<u64>{1, 101, 401, 501, 601}));
   });
   run_case("workload::raft elects exactly one leader", [] {
     for (u64 seed = 0; seed < 20; seed++) {

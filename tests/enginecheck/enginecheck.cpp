@@ -63,6 +63,7 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
     case MSIM_WL_STREAM: return run_wl<WL_Stream>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_ETCD: return run_wl<WL_Etcd>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_TONIC: return run_wl<WL_Tonic>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
+    case MSIM_WL_SIGNAL: return run_wl<WL_Signal>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
   }
   return MSIM_EINVAL;
 }
@@ -76,6 +77,7 @@ extern "C" int enginecheck_state_bytes(uint32_t workload) {
     case MSIM_WL_STREAM: return Layout<WL_Stream::Caps>::BYTES;
     case MSIM_WL_ETCD: return Layout<WL_Etcd::Caps>::BYTES;
     case MSIM_WL_TONIC: return Layout<WL_Tonic::Caps>::BYTES;
+    case MSIM_WL_SIGNAL: return Layout<WL_Signal::Caps>::BYTES;
   }
   return -1;
 }

@@ -32,6 +32,9 @@ CASES = {
     "etcd_cfg4_timeouts_bug": (dict(packet_loss_rate=0.1), dict(kind="etcd", timeout_rate=0.125, bug=3), list(range(8))),
     "tonic_cfg5": (dict(), dict(kind="tonic"), list(range(6)) + [32767]),  # BASELINE config 5
     "tonic_cfg5_restart_only": (dict(), dict(kind="tonic", clients=1, restart_only=True), list(range(4))),
+    "signal_burst": (dict(), dict(kind="signal", behavior=0), list(range(4))),
+    "signal_delay": (dict(), dict(kind="signal", behavior=1), list(range(4))),
+    "signal_skip_no_handler": (dict(), dict(kind="signal", behavior=2, catch=False), list(range(4))),
     "raft_cfg3_loss5": (dict(packet_loss_rate=0.05), dict(kind="raft", faults=7), list(range(4))),
 }
 

@@ -48,6 +48,7 @@ def test_defaults_and_validation_need_no_device():
     assert (d.n_nodes, list(d.p)[:5]) == (3, [32, 50_000_000, 0, 0, 1])
     assert m.Workload.etcd().p == list(d.p) and m.Workload.etcd().n_nodes == 3
     assert m.Workload.etcd(timeout_rate=0.5).p[2] == 0x3F000000  # SimServer::timeout_rate is an f32
+    assert lib.msim_workload_default(N.WL_SIGNAL, C.byref(d)) == 0 and m.Workload.signal().p == list(d.p)
     assert lib.msim_workload_default(N.WL_TONIC, C.byref(d)) == 0
     assert (d.n_nodes, list(d.p)[:3]) == (7, [10, 100_000_000, 0]) and m.Workload.tonic().p == list(d.p)
 

@@ -60,6 +60,11 @@ CASES = [
     ("tonic-restart-only-1client", m.Config(), m.Workload.tonic(clients=1, restart_only=True), 0, 32),
     ("tonic-loss1-client-panics", m.Config(packet_loss_rate=0.01), m.Workload.tonic(), 0, 32),
     ("tonic-buggify-slow-server", m.Config(buggify=True), m.Workload.tonic(clients=3, rounds=5), 0, 160),
+    # time::interval + MissedTickBehavior, signal::ctrl_c, Handle::send_ctrl_c
+    ("signal-burst-catch", m.Config(), m.Workload.signal(behavior=0, rounds=12), 0, 100),
+    ("signal-delay-catch", m.Config(), m.Workload.signal(behavior=1, rounds=12), 0, 100),
+    ("signal-skip-catch", m.Config(), m.Workload.signal(behavior=2, rounds=12), 0, 100),
+    ("signal-skip-ctrlc-kills", m.Config(), m.Workload.signal(behavior=2, rounds=12, catch=False), 0, 100),
     # Handle::{kill,restart,pause,resume} + restart_on_panic (task/mod.rs:356-424,289-317)
     ("chaos", m.Config(), m.Workload.chaos(), 0, 200),
     ("chaos-long-panics", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 200),

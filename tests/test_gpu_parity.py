@@ -94,6 +94,11 @@ CASES = [
     ("tonic-loss1-client-panics", m.Config(packet_loss_rate=0.01), m.Workload.tonic(), 0, 200),
     ("tonic-buggify-slow-server", m.Config(buggify=True), m.Workload.tonic(clients=3, rounds=5), 0, 200),
     ("tonic-16-rounds-slow-links", m.Config(send_latency_ns=(1 * m.MS, 400 * m.MS)), m.Workload.tonic(rounds=16, think_ns=0), 0, 200),
+    ("signal-interval-burst-ctrlc-caught", m.Config(), m.Workload.signal(behavior=0, rounds=12), 0, 500),
+    ("signal-interval-delay-ctrlc-caught", m.Config(), m.Workload.signal(behavior=1, rounds=12), 0, 500),
+    ("signal-interval-skip-ctrlc-caught", m.Config(), m.Workload.signal(behavior=2, rounds=12), 0, 500),
+    ("signal-interval-skip-ctrlc-kills", m.Config(), m.Workload.signal(behavior=2, rounds=12, catch=False), 0, 500),
+    ("signal-interval-1ms-period", m.Config(), m.Workload.signal(behavior=0, rounds=6, period_ms=1), 0, 300),
     ("chaos-kill-restart-pause", m.Config(), m.Workload.chaos(), 0, 500),
     ("chaos-restart-on-panic", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 500),
     ("chaos-always-panicking", m.Config(), m.Workload.chaos(rounds=4, period_ms=3000, panics=50), 0, 200),

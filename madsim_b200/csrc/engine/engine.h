@@ -835,8 +835,11 @@ MSIM_NOUNROLL
     for (u32 i = 0; i < ml; i++) msg_free(b(L::B_MB, k * C::NMBOX + i));
     b(L::B_SK_MBLEN, k) = 0;
     b(L::B_SK_REGLEN, k) = 0;
-    if (C::NCONN) {
-      b(L::B_ACC_LEN, k) = 0;  // pending incoming connections die with the socket object
+    if (C::NCONN) {  // pending incoming connections die with the socket object: their (tx, rx) drop, FIFO
+      u32 al = b(L::B_ACC_LEN, k);
+MSIM_NOUNROLL
+      for (u32 i = 0; i < al; i++) conn_drop(2 * b(L::B_ACC, k * C::NACC + i) + 1);
+      b(L::B_ACC_LEN, k) = 0;
       w(L::W_ACC_WAITER, k) = NONE32;
     }
     sk_state(k) = 0;
@@ -845,7 +848,13 @@ MSIM_NOUNROLL
   MSIM_HD void reset_node_sockets(int n) {
 MSIM_NOUNROLL
     for (int k = 0; k < C::NSOCK; k++)
-      if (sk_state(k) && b(L::B_SK_NODE, k) == n) sock_release_storage(k);
+      if (sk_state(k) && b(L::B_SK_NODE, k) == n) {
+        // The reference frees the socket OBJECT (and with it the un-accepted connections) only when the
+        // killed listener's future is dropped; this build frees it here.  Unobservable unless connections
+        // are waiting to be accepted — that case is reported, not approximated.
+        if (C::NCONN && b(L::B_ACC_LEN, k) != 0) fail_cap(MSIM_CAP_SOCKETS);
+        sock_release_storage(k);
+      }
   }
   /// A future takes / drops a clone of the Endpoint (Arc<BindGuard>)
   MSIM_HD void sock_ref(int t, int k) {
@@ -988,6 +997,9 @@ MSIM_NOUNROLL
     int e = t_conn(t);
     if (e == NONE8) return;
     t_conn(t) = NONE8;
+    conn_drop(e);
+  }
+  MSIM_HD void conn_drop(int e) {
     int c = e >> 1, side = e & 1;
     int d_tx = 2 * c + side, d_rx = 2 * c + (side ^ 1);
     ch_flags(d_tx) &= ~CH_TX_ALIVE;  // last UnboundedSender dropped: the peer's recv wakes and drains

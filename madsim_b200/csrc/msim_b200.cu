@@ -51,6 +51,8 @@ struct KernelArgs {
   uint32_t L;               // populated lanes per warp
   uint32_t resume;          // 0: init from seed, 1: load checkpoint
   uint32_t* unfinished;     // device counter: seeds still RUNNING after this launch
+  uint32_t* next_seed;      // device counter of the seed queue (dynamic mode)
+  uint32_t dynamic;         // 1: run-to-completion launch, every warp slot pulls the next seed when its own finishes
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t col = warp * a.L + lane;  // this thread's seed column
   const uint64_t first = (uint64_t)blockIdx.x * S;
-  const bool active = lane < a.L && col < S && first + col < a.n_seeds;
+  const bool active = lane < a.L && col < S && (a.dynamic || first + col < a.n_seeds);
   const uint32_t block_bytes = S * (uint32_t)E::L::BYTES;
   unsigned char* gblob = a.blob ? a.blob + (size_t)blockIdx.x * block_bytes : nullptr;
 
@@ -139,28 +141,41 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
       e.tr = a.trace;
       e.tr_cap = a.trace_cap;
     }
-    if (a.resume) {
-      e.load();
-      if (a.trace) e.tr_n = *a.trace_n;
-    } else {
-      e.init(a.seed_base + first + col);
-    }
-    // ---- the event loop: up to max_events steps out of shared memory / registers ----
-    if (e.status == MSIM_ST_RUNNING) {
-      uint64_t budget = a.max_events ? a.max_events : ~0ull;
-      while (budget-- && e.step()) {
+    // Static launches (bursts, resume, replay): seed = first + col, once.  Dynamic launches
+    // (run to completion): seeds finish at very different event counts (a chaos schedule may last 10
+    // or 50 virtual seconds), so CTAs are persistent (one per SM) and a slot whose seed is done takes
+    // the next one from the queue (SURVEY §8e "handle load imbalance inside a GPU").  Seeds are
+    // independent: the assignment cannot change any result.  One event-loop site for both.
+    uint64_t idx = first + col;
+    for (;;) {
+      if (a.dynamic) {
+        idx = atomicAdd(a.next_seed, 1u);
+        if (idx >= a.n_seeds) break;
       }
+      if (a.resume) {
+        e.load();
+        if (a.trace) e.tr_n = *a.trace_n;
+      } else {
+        e.init(a.seed_base + idx);
+      }
+      // ---- the event loop: up to max_events steps out of shared memory / registers ----
+      if (e.status == MSIM_ST_RUNNING) {
+        uint64_t budget = a.max_events ? a.max_events : ~0ull;
+        while (budget-- && e.step()) {
+        }
+      }
+      e.store();
+      SeedResult r;
+      e.result(r);
+      a.results[idx] = r;
+      if (!a.dynamic) break;
     }
-    e.store();
-    SeedResult r;
-    e.result(r);
-    a.results[first + col] = r;
     if (a.trace) *a.trace_n = e.tr_n;
   }
   // ---- stage out: in burst mode (a checkpoint buffer exists) the block always goes back to HBM,
   // finished seeds included, so that a later resume reloads a consistent image ----
-  if (active && e.status == MSIM_ST_RUNNING) atomicAdd(a.unfinished, 1u);
-  if (gblob) {
+  if (active && !a.dynamic && e.status == MSIM_ST_RUNNING) atomicAdd(a.unfinished, 1u);
+  if (gblob && !a.dynamic) {
     fence_proxy_async();  // generic-proxy smem writes → visible to the async proxy
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -272,7 +287,7 @@ struct msim_batch {
   uint32_t user_S = 0, user_L = 0;
   // current run
   uint64_t seed_base = 0, n_seeds = 0;
-  uint32_t S = 0, L = 0, n_blocks = 0, threads = 0;
+  uint32_t S = 0, L = 0, n_blocks = 0, threads = 0, grid_launched = 0;
   size_t smem = 0;
   bool ran = false, pending = false;
   SeedResult* d_results = nullptr;
@@ -303,7 +318,15 @@ int choose_geometry(msim_batch* b, uint64_t n) {
     uint64_t per_sm = (n + b->sm_count - 1) / b->sm_count;
     S = (uint32_t)(per_sm < s_max ? per_sm : s_max);
     if (S == 0) S = 1;
-    if (S > (uint32_t)MAX_THREADS) S = MAX_THREADS;
+    // Lanes of a warp run different seeds, i.e. mostly diverged: populating 2-4 lanes per warp pays
+    // only for the small programs (measured, profiles/r1j_geometry_sweeps.txt): STREAM / CHAOS / SIGNAL
+    // gain 1.4-1.6x at 4 lanes, RAFT / ETCD / TONIC lose 20-25 % at 2.
+    uint32_t lanes = 1;
+    switch (b->wl.workload) {
+      case MSIM_WL_SLEEP: case MSIM_WL_PINGPONG: case MSIM_WL_STREAM: case MSIM_WL_CHAOS: case MSIM_WL_SIGNAL: lanes = 4; break;
+      default: break;
+    }
+    if (S > lanes * (MAX_THREADS / 32)) S = lanes * (MAX_THREADS / 32);
   }
   if (S > s_max) return set_err(MSIM_EINVAL, "seeds_per_cta exceeds shared memory (" + std::to_string(s_max) + " max)");
   uint32_t L = b->user_L ? b->user_L : 1;  // one seed per warp: lanes never run converged (profiles/), warps do overlap
@@ -340,8 +363,14 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
   a.L = b->L;
   a.resume = resume ? 1 : 0;
   a.unfinished = b->d_unfinished;
-  CUDA_TRY(cudaMemsetAsync(b->d_unfinished, 0, sizeof(uint32_t), b->stream));
-  dim3 grid(b->n_blocks), block(b->threads);
+  a.next_seed = b->d_unfinished + 1;
+  // run-to-completion launches balance the load dynamically; bursts keep seed i in block i / S (the checkpoint layout)
+  a.dynamic = (max_events == 0 && !resume && !d_trace && b->n_seeds < 0xffffffffull) ? 1 : 0;
+  CUDA_TRY(cudaMemsetAsync(b->d_unfinished, 0, 2 * sizeof(uint32_t), b->stream));
+  uint32_t n_grid = b->n_blocks;
+  if (a.dynamic && n_grid > (uint32_t)b->sm_count) n_grid = (uint32_t)b->sm_count;  // 1 CTA per SM (shared memory)
+  b->grid_launched = n_grid;
+  dim3 grid(n_grid), block(b->threads);
   cudaError_t e;
   switch (b->wl.workload) {
     case MSIM_WL_SLEEP: e = launch_wl<WL_Sleep>(a, grid, block, b->smem, b->stream); break;
@@ -467,7 +496,7 @@ int msim_batch_create(const msim_config* cfg, int device, msim_batch** out) {
   b->own_stream = true;
   CUDA_TRY(cudaEventCreate(&b->ev0));
   CUDA_TRY(cudaEventCreate(&b->ev1));
-  CUDA_TRY(cudaMalloc(&b->d_unfinished, sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&b->d_unfinished, 2 * sizeof(uint32_t)));
   CUDA_TRY(cudaMallocHost(&b->h_unfinished, sizeof(uint32_t)));
   *out = b;
   return MSIM_OK;
@@ -619,7 +648,7 @@ int msim_batch_results(msim_batch* b, msim_seed_result* out, uint32_t* fail_bitm
     stats->launches = b->launches;
     stats->seeds_per_cta = b->S;
     stats->lanes_per_warp = b->L;
-    stats->ctas = b->n_blocks;
+    stats->ctas = b->grid_launched ? b->grid_launched : b->n_blocks;
     stats->smem_bytes = (uint32_t)b->smem;
   }
   return MSIM_OK;

@@ -15,7 +15,8 @@ import madsim_b200 as m
 def main():
     n = int(os.environ.get("N", 4096))
     faults = int(os.environ.get("FAULTS", 0))
-    wl = m.Workload.raft(faults=faults)
+    kind = os.environ.get("WL", "raft")
+    wl = m.Workload.raft(faults=faults) if kind == "raft" else getattr(m.Workload, kind)()
     out = []
     geos = [tuple(int(x) for x in g.split(":")) for g in os.environ.get("GEOS", "0:1,0:2,0:4,0:8").split(",")]
     for S, L in geos:
@@ -31,9 +32,10 @@ def main():
                    kernel_ms=st["kernel_ms"], e2e_ms=dt * 1e3, events=ev, mev_s=ev / st["kernel_ms"] / 1e3,
                    n_fail=st["n_fail"], unfinished=st["n_unfinished"],
                    status=np.bincount(res["status"], minlength=6).tolist())
+        rec["wl"] = kind
         print(json.dumps(rec), flush=True)
         out.append(rec)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"sweep_n{n}_f{faults}_{os.environ.get('TAG','x')}.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"sweep_{kind}_n{n}_f{faults}_{os.environ.get('TAG','x')}.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

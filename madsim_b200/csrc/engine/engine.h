@@ -27,6 +27,7 @@
 //    instruction stream, and lanes of a warp that wait in the same primitive execute it together.
 //  * Every bounded table reports overflow as MSIM_ST_FAIL_CAPACITY — never silently.
 #pragma once
+#include <type_traits>
 #include "defs.h"
 
 namespace msim {
@@ -230,6 +231,42 @@ struct Engine {
   MSIM_HD u64& wl_q(int f, int n) const { return q(L::Q_WL, f * C::NNODE + n); }
   MSIM_HD u32& wl_w(int f, int n) const { return w(L::W_WL, f * C::NNODE + n); }
   MSIM_HD u32& wl_s(int i) const { return w(L::W_WLS, i); }
+
+  // ---------------- rarely executed runtime paths ----------------
+  /// kill / restart / create_node / bind / panic handling ... run OUT OF LINE: one copy per kernel keeps
+  /// them off the hot loop's instruction-cache footprint.  The hot loop's registers are spilled to the
+  /// state block around the call (store / load); the callee works on an Engine of its own.
+  template <class F>
+  static MSIM_NI auto cold_run(unsigned char* sb_, const Params* P_, u64 now_, F f) {
+    Engine e_;
+    e_.sb = sb_;
+    e_.P = P_;
+    e_.tr = nullptr;  // nothing on these paths appends trace records
+    e_.tr_cap = 0;
+    e_.tr_n = 0;
+    e_.load();
+    e_.now = now_;
+    if constexpr (std::is_void<decltype(f(e_))>::value) {
+      f(e_);
+      e_.store();
+    } else {
+      auto r_ = f(e_);
+      e_.store();
+      return r_;
+    }
+  }
+  template <class F>
+  MSIM_HD auto cold(F f) {
+    store();
+    if constexpr (std::is_void<decltype(cold_run(sb, P, now, f))>::value) {
+      cold_run(sb, P, now, f);
+      load();
+    } else {
+      auto r_ = cold_run(sb, P, now, f);
+      load();
+      return r_;
+    }
+  }
 
   // ---------------- failure ----------------
   MSIM_HD void fail(u32 st, u32 code) {
@@ -481,20 +518,8 @@ struct Engine {
     notify_awaiter(t);
     maybe_free(t);
   }
-  static MSIM_NI void drop_runnable_cold(unsigned char* sb_, const Params* P_, u64 now_, int t) {
-    Engine e_;
-    e_.sb = sb_;
-    e_.P = P_;
-    e_.load();
-    e_.now = now_;
-    e_.drop_runnable_inl(t);
-    e_.store();
-  }
-  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
   MSIM_HD void drop_runnable(int t) {
-    store();
-    drop_runnable_cold(sb, P, now, t);
-    load();
+    cold([t](Engine& e_) { e_.drop_runnable_inl(t); });
   }
   /// Spawner::spawn_inner (task/mod.rs:627-654): returns the slot or -1
   MSIM_HD int spawn(u32 kind, u32 node, u8 extra_flags) {
@@ -612,40 +637,16 @@ MSIM_NOUNROLL
     info_kill(n, n_epoch(n));
     reset_node_sockets(n);  // NetSim::reset_node: all sockets of the node closed (network.rs:142-147)
   }
-  static MSIM_NI void kill_cold(unsigned char* sb_, const Params* P_, u64 now_, int n) {
-    Engine e_;
-    e_.sb = sb_;
-    e_.P = P_;
-    e_.load();
-    e_.now = now_;
-    e_.kill_inl(n);
-    e_.store();
-  }
-  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
   MSIM_HD void kill(int n) {
-    store();
-    kill_cold(sb, P, now, n);
-    load();
+    cold([n](Engine& e_) { e_.kill_inl(n); });
   }
   /// Spawner::exit (task/mod.rs:656-661): info.kill() only — no reset_node, paused list kept
   MSIM_HD void node_exit_inl(int n, u8 epoch) {
     if (n_epoch(n) == epoch) n_flags(n) = n_flags(n) | NF_KILLED;
     info_kill(n, epoch);
   }
-  static MSIM_NI void node_exit_cold(unsigned char* sb_, const Params* P_, u64 now_, int n, u8 epoch) {
-    Engine e_;
-    e_.sb = sb_;
-    e_.P = P_;
-    e_.load();
-    e_.now = now_;
-    e_.node_exit_inl(n, epoch);
-    e_.store();
-  }
-  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
   MSIM_HD void node_exit(int n, u8 epoch) {
-    store();
-    node_exit_cold(sb, P, now, n, epoch);
-    load();
+    cold([n, epoch](Engine& e_) { e_.node_exit_inl(n, epoch); });
   }
   MSIM_HD void restart_inl(int n) {
     drop_parked(n);
@@ -656,20 +657,8 @@ MSIM_NOUNROLL
     int kind = WL::init_kind(n);
     if (kind >= 0) spawn((u32)kind, n, TF_INIT);
   }
-  static MSIM_NI void restart_cold(unsigned char* sb_, const Params* P_, u64 now_, int n) {
-    Engine e_;
-    e_.sb = sb_;
-    e_.P = P_;
-    e_.load();
-    e_.now = now_;
-    e_.restart_inl(n);
-    e_.store();
-  }
-  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
   MSIM_HD void restart(int n) {
-    store();
-    restart_cold(sb, P, now, n);
-    load();
+    cold([n](Engine& e_) { e_.restart_inl(n); });
   }
   /// Handle::send_ctrl_c (task/mod.rs:427-441): watch::Sender::send if a handler was ever installed
   /// on this NodeInfo (an error for "no receiver" is ignored), otherwise the node is killed
@@ -686,19 +675,8 @@ MSIM_NOUNROLL
       kill_inl(n);
     }
   }
-  static MSIM_NI void send_ctrl_c_cold(unsigned char* sb_, const Params* P_, u64 now_, int n) {
-    Engine e_;
-    e_.sb = sb_;
-    e_.P = P_;
-    e_.load();
-    e_.now = now_;
-    e_.send_ctrl_c_inl(n);
-    e_.store();
-  }
   MSIM_HD void send_ctrl_c(int n) {
-    store();
-    send_ctrl_c_cold(sb, P, now, n);
-    load();
+    cold([n](Engine& e_) { e_.send_ctrl_c_inl(n); });
   }
   MSIM_HD void pause(int n) { n_flags(n) = n_flags(n) | NF_PAUSED; }
   MSIM_HD void resume_inl(int n) {
@@ -714,20 +692,8 @@ MSIM_NOUNROLL
     }
     w(L::W_PK_LEN) = keep;
   }
-  static MSIM_NI void resume_cold(unsigned char* sb_, const Params* P_, u64 now_, int n) {
-    Engine e_;
-    e_.sb = sb_;
-    e_.P = P_;
-    e_.load();
-    e_.now = now_;
-    e_.resume_inl(n);
-    e_.store();
-  }
-  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
   MSIM_HD void resume(int n) {
-    store();
-    resume_cold(sb, P, now, n);
-    load();
+    cold([n](Engine& e_) { e_.resume_inl(n); });
   }
   MSIM_HD bool is_exit(int n) const { return n_flags(n) & NF_KILLED; }
   /// Handle::create_node + NodeBuilder::build (runtime/mod.rs:405-418): ids start at 1; the init
@@ -746,22 +712,8 @@ MSIM_NOUNROLL
     if (kind >= 0) spawn((u32)kind, n, TF_INIT);
     return (int)n;
   }
-  static MSIM_NI int create_node_cold(unsigned char* sb_, const Params* P_, u64 now_, u32 flags) {
-    Engine e_;
-    e_.sb = sb_;
-    e_.P = P_;
-    e_.load();
-    e_.now = now_;
-    int r_ = e_.create_node_inl(flags);
-    e_.store();
-    return r_;
-  }
-  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
   MSIM_HD int create_node(u32 flags) {
-    store();
-    auto r_ = create_node_cold(sb, P, now, flags);
-    load();
-    return r_;
+    return cold([flags](Engine& e_) { return e_.create_node_inl(flags); });
   }
 
   // ---------------- network (net/network.rs, net/mod.rs, net/endpoint.rs) ----------------
@@ -812,22 +764,8 @@ MSIM_NOUNROLL
     w(L::W_SK_PORTGEN, k) = port | ((sk_gen(k) + 1) << 16);
     return k;
   }
-  static MSIM_NI int sock_bind_cold(unsigned char* sb_, const Params* P_, u64 now_, int node, u32 addr) {
-    Engine e_;
-    e_.sb = sb_;
-    e_.P = P_;
-    e_.load();
-    e_.now = now_;
-    int r_ = e_.sock_bind_inl(node, addr);
-    e_.store();
-    return r_;
-  }
-  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
   MSIM_HD int sock_bind(int node, u32 addr) {
-    store();
-    auto r_ = sock_bind_cold(sb, P, now, node, addr);
-    load();
-    return r_;
+    return cold([node, addr](Engine& e_) { return e_.sock_bind_inl(node, addr); });
   }
   MSIM_HD void sock_release_storage(int k) {
     u32 ml = b(L::B_SK_MBLEN, k);
@@ -1575,20 +1513,8 @@ MSIM_NOUNROLL
       fail(MSIM_ST_FAIL_ASSERT, w(L::W_PANIC_CODE));
     }
   }
-  static MSIM_NI void panicked_cold(unsigned char* sb_, const Params* P_, u64 now_, int n) {
-    Engine e_;
-    e_.sb = sb_;
-    e_.P = P_;
-    e_.load();
-    e_.now = now_;
-    e_.panicked_inl(n);
-    e_.store();
-  }
-  /// rarely executed: one out-of-line copy, registers spilled to / reloaded from the block around it
   MSIM_HD void panicked(int n) {
-    store();
-    panicked_cold(sb, P, now, n);
-    load();
+    cold([n](Engine& e_) { e_.panicked_inl(n); });
   }
   MSIM_HD int panic(u32 code) {
     w(L::W_PANIC_CODE) = code;

@@ -86,6 +86,18 @@ def test_burst_checkpoint_equals_run_to_completion(oracle):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("wl", [m.Workload.etcd(timeout_rate=0.1), m.Workload.tonic(rounds=4), m.Workload.signal(behavior=2),
+                                m.Workload.stream(messages=60)], ids=["etcd", "tonic", "signal", "stream"])
+def test_burst_checkpoint_covers_channel_and_signal_state(oracle, wl):
+    # connections, accept queues, leases, ctrl-c waiters all live in the state block: k-event bursts == one run
+    cfg = m.Config(packet_loss_rate=0.05) if wl.workload != m.WL_TONIC else m.Config()
+    a, _ = oracle.engine_host(cfg, wl, 0, 12, seeds_per_block=4)
+    assert np.array_equal(a, oracle.run_many(cfg, wl, 0, 12))
+    for k in (1, 13, 500):
+        b, _ = oracle.engine_host(cfg, wl, 0, 12, seeds_per_block=3, max_events=k)
+        assert np.array_equal(a, b)
+
+
 def test_full_trace_equal(oracle):
     cfg, wl = m.Config(), m.Workload.raft(duration_ms=2500, faults=7)
     for seed in (0, 5, 123456789012345):

@@ -194,6 +194,18 @@ def test_config5_tonic_32768_seeds_kill_restart_chaos(oracle):
     assert np.array_equal(got, again)
 
 
+@pytest.mark.parametrize("wl", [m.Workload.etcd(timeout_rate=0.1), m.Workload.tonic(rounds=4), m.Workload.signal(behavior=2),
+                                m.Workload.stream(messages=60)], ids=["etcd", "tonic", "signal", "stream"])
+def test_burst_checkpoint_covers_channel_and_signal_state(wl):
+    # static (burst) launches through the HBM checkpoint == the dynamic run-to-completion launch
+    cfg = m.Config(packet_loss_rate=0.05) if wl.workload != m.WL_TONIC else m.Config()
+    ref, _, _ = run_gpu(cfg, wl, 0, 600)
+    for k in (97, 2000):
+        got, _, st = run_gpu(cfg, wl, 0, 600, max_events=k)
+        assert st["n_unfinished"] == 0
+        assert np.array_equal(ref, got)
+
+
 def test_burst_checkpoint_resume_equals_run_to_completion():
     # bursts go through the HBM checkpoint: smem → TMA bulk store → TMA bulk load → smem
     cfg, wl = m.Config(), m.Workload.raft(duration_ms=3000, faults=7)

@@ -115,10 +115,12 @@ class Workload:
         return Workload(N.WL_ETCD, clients + 1, [ops, think_ns, bits, bug, lease_ttl_s, 0, 0, 0])
 
     @staticmethod
-    def tonic(clients: int = 6, rounds: int = 10, think_ns: int = 100 * MS, restart_only: bool = False) -> "Workload":
+    def tonic(clients: int = 6, rounds: int = 10, think_ns: int = 100 * MS, restart_only: bool = False,
+              streaming: bool = False) -> "Workload":
         """tonic-example Greeter service under madsim-tonic (a fresh endpoint + handshake + connection per
-        unary call) while a supervisor kills / restarts the client nodes (BASELINE config 5)."""
-        return Workload(N.WL_TONIC, clients + 1, [rounds, think_ns, int(restart_only), 0, 0, 0, 0, 0])
+        unary call) while a supervisor kills / restarts the client nodes (BASELINE config 5); with `streaming`
+        the clients also make server-streaming calls (lots_of_replies) and sometimes drop the response stream."""
+        return Workload(N.WL_TONIC, clients + 1, [rounds, think_ns, int(restart_only) | 2 * int(streaming), 0, 0, 0, 0, 0])
 
     @staticmethod
     def signal(rounds: int = 8, period_ms: int = 100, behavior: int = 0, catch: bool = True) -> "Workload":

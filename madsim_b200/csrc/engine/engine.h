@@ -49,6 +49,7 @@ enum : u8 {
   W_CONNECT = 10,    // connect1: rand_delay, then the connection request (net/mod.rs:337-364)
   W_ACCEPT = 11,     // accept1: rand_delay FIRST, then the next incoming connection (endpoint.rs:197-211)
   W_CH_RECV = 12,    // Receiver::recv: the channel's delay/back-off stream (net/mod.rs:385-402)
+  W_SLEEP_CLOSED = 14,  // select_biased!{ tx.closed(), sleep }: the connection's Sender::closed() first, then a Sleep
   W_CTRLC = 13,      // signal::ctrl_c: watch::Receiver::changed() on the node's channel (signal.rs:4-8)
   WF_RD = 0x10,      // rand_delay not drawn yet: draw it now, then sleep on dl0
   WF_SLEEP = 0x20,   // sleeping on dl0
@@ -77,6 +78,7 @@ enum : int {
   RQ_CH_RECV,       // conn.rx.recv()                  -> ret 0, rv0, rv1 / -1 ConnectionReset
   RQ_SLEEP_RAW,     // Sleep::reset(xa) + await: the deadline is NOT clamped to now + 1 ms (time/sleep.rs:40-42, interval.rs:156)
   RQ_CTRL_C,        // signal::ctrl_c().await (installs the node's handler on first use)
+  RQ_SLEEP_OR_CLOSED,  // select_biased!{ conn.tx.closed() => -1, sleep(xa ns) => 0 }  (madsim-tonic server.rs:289-300)
 };
 enum : u32 { SPAWN_EP = 0x100, SPAWN_JOINABLE = 0x200, SPAWN_CONN = 0x400 };  // clone the Endpoint / keep a JoinHandle / move the connection end
 enum : u32 { NODE_IP = 1, NODE_INIT = 2, NODE_RESTART_ON_PANIC = 4 };
@@ -137,7 +139,9 @@ struct Layout {
   static constexpr int W_CH_CUR_V1 = W_CH_CUR_V0 + ND;
   static constexpr int W_CH_DST = W_CH_CUR_V1 + ND;             // [ND] test_link destination address
   static constexpr int W_CH_WAITER = W_CH_DST + ND;             // [ND] mpsc rx_waker (slot<<20|gen) or NONE32
-  static constexpr int W_CONN_SRC = W_CH_WAITER + ND;           // [NCONN] connector's source address
+  static constexpr int NDC = C::USES_CLOSED ? ND : 0;
+  static constexpr int W_CH_CLOSED_WAITER = W_CH_WAITER + ND;   // [NDC] the task parked in Sender::closed() of this direction
+  static constexpr int W_CONN_SRC = W_CH_CLOSED_WAITER + NDC;   // [NCONN] connector's source address
   static constexpr int NSA = C::NCONN ? C::NSOCK : 0;           // accept state exists only with connections
   static constexpr int W_ACC_WAITER = W_CONN_SRC + C::NCONN;    // [NSA] task waiting in accept1
   static constexpr int NCC = C::USES_CTRLC ? C::NNODE : 0;     // ctrl-c state exists only where it is awaited
@@ -918,6 +922,7 @@ MSIM_NOUNROLL
       b(L::B_CH_PHASE, d) = 0;
       ch_flags(d) = CH_TX_ALIVE | CH_RX_ALIVE;
       w(L::W_CH_WAITER, d) = NONE32;
+      if (C::USES_CLOSED) w(L::W_CH_CLOSED_WAITER, d) = NONE32;
     }
     b(L::B_CH_SRC, 2 * c) = (u8)node;  // channel(node, dst)
     w(L::W_CH_DST, 2 * c) = dst;
@@ -940,9 +945,11 @@ MSIM_NOUNROLL
   MSIM_HD void conn_drop(int e) {
     int c = e >> 1, side = e & 1;
     int d_tx = 2 * c + side, d_rx = 2 * c + (side ^ 1);
+    // `(tx, rx)` bindings drop in reverse order: the Receiver first, then the Sender
+    ch_flags(d_rx) &= ~CH_RX_ALIVE;  // UnboundedReceiver dropped: the peer's send fails, its closed() completes
+    if (C::USES_CLOSED) wake_waiter(w(L::W_CH_CLOSED_WAITER, d_rx));
     ch_flags(d_tx) &= ~CH_TX_ALIVE;  // last UnboundedSender dropped: the peer's recv wakes and drains
     wake_waiter(w(L::W_CH_WAITER, d_tx));
-    ch_flags(d_rx) &= ~CH_RX_ALIVE;  // UnboundedReceiver dropped: the peer's send fails
     if (!((ch_flags(d_tx) | ch_flags(d_rx)) & (CH_TX_ALIVE | CH_RX_ALIVE))) b(L::B_CONN_USED, c) = 0;
   }
   /// Sender::is_closed / the ready state of Sender::closed() (endpoint.rs:247-253): the peer dropped its Receiver
@@ -1149,6 +1156,17 @@ MSIM_NOUNROLL
       if (wt != W_NONE) {
         u8 st = wt & 0x0f;
         bool pend = false;
+        if (C::USES_CLOSED && st == W_SLEEP_CLOSED) {  // select_biased!: tx.closed() is polled before the Sleep
+          int d = t_conn(t);
+          if (!(ch_flags(d) & CH_RX_ALIVE)) {
+            w(L::W_CH_CLOSED_WAITER, d) = NONE32;
+            ret = -1;
+            wt = W_NONE;  // the select is over; the Sleep is dropped unpolled
+            st = 15;      // (no case below)
+          } else {
+            w(L::W_CH_CLOSED_WAITER, d) = ((u32)t << 20) | t_gen(t);
+          }
+        }
         if (wt & WF_RD) {  // NetSim::rand_delay: draw, then `sleep(delay).await`
           t_dl0(t) = rand_delay_deadline();
           wt = (wt & ~WF_RD) | WF_SLEEP;
@@ -1283,6 +1301,11 @@ MSIM_NOUNROLL
               }
               break;
             }
+            case W_SLEEP_CLOSED:  // the Sleep won: the closed() future drops with the select
+              if (C::USES_CLOSED) w(L::W_CH_CLOSED_WAITER, t_conn(t)) = NONE32;
+              ret = 0;
+              wt = W_NONE;
+              break;
             case W_CTRLC: {  // rx.changed(): ready once the version moved past the one seen at subscribe()
               if (!C::USES_CTRLC) break;
               int n = t_node(t);
@@ -1353,6 +1376,10 @@ MSIM_NOUNROLL
         case RQ_SLEEP_UNTIL:
           t_dl0(t) = sleep_deadline(xa);
           t_wait(t) = W_SLEEP | WF_SLEEP;
+          break;
+        case RQ_SLEEP_OR_CLOSED:
+          t_dl0(t) = sleep_deadline(now + xa);
+          t_wait(t) = W_SLEEP_CLOSED | WF_SLEEP;
           break;
         case RQ_SLEEP_RAW:
           t_dl0(t) = xa;

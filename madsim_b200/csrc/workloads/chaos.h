@@ -17,6 +17,7 @@ struct WL_Chaos {
     static constexpr bool USES_JOIN = false;  // does any task await a JoinHandle?
     static constexpr bool USES_KILL = true;
     static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
+    static constexpr bool USES_CLOSED = false;  // does any task await Sender::closed()?
     static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 { K_MAIN = 0, K_WORKER = 1 };

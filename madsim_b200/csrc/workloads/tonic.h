@@ -25,11 +25,13 @@ struct WL_Tonic {
     static constexpr bool USES_JOIN = false;
     static constexpr bool USES_KILL = true;
     static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
+    static constexpr bool USES_CLOSED = true;   // does any task await Sender::closed()?
     static constexpr int NCONN = 32, NCQ = 2, NACC = 32;
   };
-  enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT };
+  enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_CLIENT_STREAM };
   enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u };
-  enum : u32 { ST_OK = 0, ST_INVALID_ARGUMENT = 1 };
+  enum : u32 { ST_OK = 0, ST_INVALID_ARGUMENT = 1, ST_EOF = 2, ST_TRAILER = 3 };
+  enum : u32 { SERVER_STREAMING = 1u << 31, FLAG_RESTART_ONLY = 1, FLAG_STREAMING_MIX = 2 };
   static constexpr u32 MAIN_KIND = K_MAIN;
   static constexpr u32 SERVER_ADDR = (IPK_NODE << 24) | (1u << 16) | 50051u;  // 10.0.0.1:50051
   /// NodeBuilder::init(|| tonic_client(c)) — what Handle::restart re-runs
@@ -88,7 +90,7 @@ struct WL_Tonic {
           return RQ_GEN_RANGE;
         case K_MAIN * 16 + 7: {
           int id = 2 + (int)e.wl_s(S_C);
-          if (e.ret64 == 3 && !(P.p[2] & 1))
+          if (e.ret64 == 3 && !(P.p[2] & FLAG_RESTART_ONLY))
             e.kill(id);
           else
             e.restart(id);
@@ -131,7 +133,7 @@ struct WL_Tonic {
             continue;
           }
           e.t_pc(t) = 2;  // spawn the response task with tx (and the request)
-          e.ya = K_RSP | SPAWN_CONN, e.yb = e.t_node(t), e.yc = e.rv0, e.yd = e.t_b(t), e.xa = e.rv1, e.xb = 0;
+          e.ya = ((e.rv1 & SERVER_STREAMING) ? (u32)K_RSP_STREAM : (u32)K_RSP) | SPAWN_CONN, e.yb = e.t_node(t), e.yc = e.rv0, e.yd = e.t_b(t), e.xa = e.rv1, e.xb = 0;
           return RQ_SPAWN;
 
         // ---- tonic_response_task ----
@@ -146,6 +148,47 @@ struct WL_Tonic {
           e.yb = ST_OK, e.yc = reply_for(e.t_a(t), e.t_b(t));
           return RQ_CH_SEND;
         case K_RSP * 16 + 1:
+          return RQ_READY;
+
+        // ---- tonic_stream_response_task: header, lots_of_replies' items, trailer (server.rs:274-313) ----
+        case K_RSP_STREAM * 16 + 0:
+          e.wl_s(S_HANDLED)++;
+          e.t_c(t) = 0;  // i
+          e.t_pc(t) = 1;
+          e.yb = ST_OK, e.yc = 0;
+          return RQ_CH_SEND;
+        case K_RSP_STREAM * 16 + 1:  // tx.send(header).await?
+          if (e.ret < 0) return RQ_READY;
+          e.t_pc(t) = 2;
+          // fallthrough
+        case K_RSP_STREAM * 16 + 2:  // select_biased!{ closed => return, stream.next() => reply i }
+          if (e.conn_tx_closed(t)) return RQ_READY;
+          e.t_pc(t) = 3;
+          e.yb = ST_OK, e.yc = reply_for(e.t_a(t), e.t_b(t)) + e.t_c(t);
+          return RQ_CH_SEND;
+        case K_RSP_STREAM * 16 + 3:  // the next select finds the generator in `sleep(1 s)`
+          if (e.ret < 0) return RQ_READY;
+          if (e.conn_tx_closed(t)) return RQ_READY;
+          e.t_pc(t) = 4;
+          e.xa = NS_PER_SEC;
+          return RQ_SLEEP_OR_CLOSED;
+        case K_RSP_STREAM * 16 + 4:
+          if (e.ret < 0) return RQ_READY;  // the client dropped the response stream
+          e.t_c(t)++;
+          if (e.t_c(t) < 3) {
+            e.t_pc(t) = 2;
+            continue;
+          }
+          e.t_pc(t) = 5;  // Err(Status::unknown("EOF"))?: the stream's last item
+          e.yb = ST_EOF, e.yc = 0;
+          return RQ_CH_SEND;
+        case K_RSP_STREAM * 16 + 5:  // stream.next() == None: break; the trailer
+          if (e.ret < 0) return RQ_READY;
+          if (e.conn_tx_closed(t)) return RQ_READY;
+          e.t_pc(t) = 6;
+          e.yb = ST_TRAILER, e.yc = 0;
+          return RQ_CH_SEND;
+        case K_RSP_STREAM * 16 + 6:
           return RQ_READY;
 
         // ---- tonic_client: the client node's init task ----
@@ -170,8 +213,9 @@ struct WL_Tonic {
           e.t_pc(t) = 4;
           e.xa = 0, e.xb = 10;
           return RQ_GEN_RANGE;
-        case K_CLIENT * 16 + 4:  // Grpc::unary -> connect_ep: Endpoint::connect
+        case K_CLIENT * 16 + 4:  // Grpc::unary / server_streaming -> connect_ep: Endpoint::connect
           e.t_a(t) = e.ret64 == 0 ? (u32)ERROR_NAME : (u32)NAME;
+          e.t_c(t) = ((P.p[2] & FLAG_STREAMING_MIX) && e.ret64 >= 1 && e.ret64 <= 3) ? (u32)e.ret64 : 0u;  // 1..3: lots_of_replies
           e.t_pc(t) = 5;
           e.ya = mk_addr(IPK_UNSPEC, 0, 0);
           return RQ_BIND;
@@ -189,7 +233,7 @@ struct WL_Tonic {
         case K_CLIENT * 16 + 7:
           if (e.ret < 0) return panic(e, 71);
           e.t_pc(t) = 8;
-          e.yb = e.t_a(t), e.yc = e.t_b(t);
+          e.yb = e.t_a(t), e.yc = e.t_b(t) | (e.t_c(t) ? (u32)SERVER_STREAMING : 0u);
           return RQ_CH_SEND;
         case K_CLIENT * 16 + 8:
           if (e.ret < 0) return panic(e, 71);
@@ -199,6 +243,21 @@ struct WL_Tonic {
           if (e.ret < 0) return panic(e, 71);
           u32 node = e.t_node(t);
           u32 st = e.rv0, reply = e.rv1;
+          if (e.t_c(t)) {  // the header of a server-streaming call
+            if (st != ST_OK) return panic(e, 75);
+            if (e.t_c(t) == 3) {  // drop the response stream at once (tests/test.rs:204-230)
+              e.conn_drop_end(t);
+              e.sock_unref(t);
+              e.wl_w(F_REPLIES, node)++;
+              e.t_b(t)++;
+              e.t_pc(t) = 3;
+              e.xa = P.p[1];
+              return RQ_SLEEP_FOR;
+            }
+            e.t_c(t) = 16;  // items read so far = t_c - 16
+            e.t_pc(t) = 10;
+            return RQ_CH_RECV;
+          }
           e.conn_drop_end(t);  // rx, tx, then the last BindGuard reference
           e.sock_unref(t);
           if (e.t_a(t) == ERROR_NAME) {
@@ -206,6 +265,23 @@ struct WL_Tonic {
           } else if (st != ST_OK || reply != NAME * 31u + node) {
             return panic(e, 73);
           }
+          e.wl_w(F_REPLIES, node)++;
+          e.t_b(t)++;
+          e.t_pc(t) = 3;
+          e.xa = P.p[1];
+          return RQ_SLEEP_FOR;
+        }
+        case K_CLIENT * 16 + 10: {  // Streaming::message(): three replies, then the EOF status
+          if (e.ret < 0) return panic(e, 71);
+          u32 node = e.t_node(t), i = e.t_c(t) - 16;
+          if (i < 3) {
+            if (e.rv0 != ST_OK || e.rv1 != NAME * 31u + node + i) return panic(e, 76);
+            e.t_c(t)++;
+            return RQ_CH_RECV;
+          }
+          if (e.rv0 != ST_EOF) return panic(e, 77);
+          e.conn_drop_end(t);
+          e.sock_unref(t);
           e.wl_w(F_REPLIES, node)++;
           e.t_b(t)++;
           e.t_pc(t) = 3;

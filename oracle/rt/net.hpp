@@ -7,6 +7,7 @@
 // Reliable channels: connect1 / accept1 / Sender / Receiver,
 // net/mod.rs:337-430 + net/endpoint.rs:178-274, over tokio's unbounded mpsc and an async stream.
 #pragma once
+#include <vector>
 #include <deque>
 #include <map>
 #include <set>
@@ -52,6 +53,15 @@ struct MpscState {
   std::optional<Waker> rx_waker;
   int tx_count = 0;
   bool rx_closed = false;
+  // Sender::closed() waiters (tokio: notify_rx_closed.notify_waiters() when the receiver closes)
+  std::vector<std::pair<u64, Waker>> closed_waiters;
+  u64 next_closed_key = 1;
+  void close_rx() {
+    rx_closed = true;
+    auto ws = std::move(closed_waiters);
+    closed_waiters.clear();
+    for (auto& kv : ws) kv.second.wake();
+  }
   void wake_rx() {
     if (rx_waker) {
       Waker w = std::move(*rx_waker);
@@ -85,6 +95,34 @@ struct UnboundedSender {
     return true;
   }
   bool is_closed() const { return st->rx_closed; }
+  /// `tx.closed()`: completes when the receiver is dropped
+  struct ClosedFut {
+    std::shared_ptr<MpscState<T>> st;
+    u64 key = 0;
+    explicit ClosedFut(std::shared_ptr<MpscState<T>> s) : st(std::move(s)) {}
+    ClosedFut(ClosedFut&& o) noexcept : st(std::move(o.st)), key(std::exchange(o.key, 0)) {}
+    ClosedFut(const ClosedFut&) = delete;
+    ~ClosedFut() {
+      if (!key || !st) return;
+      for (size_t i = 0; i < st->closed_waiters.size(); i++)
+        if (st->closed_waiters[i].first == key) {
+          st->closed_waiters.erase(st->closed_waiters.begin() + long(i));
+          break;
+        }
+    }
+    Poll<Unit> poll(Context& cx) {
+      if (st->rx_closed) return Poll<Unit>::done({});
+      if (key) {
+        for (auto& kv : st->closed_waiters)
+          if (kv.first == key) kv.second = cx.waker;
+      } else {
+        key = st->next_closed_key++;
+        st->closed_waiters.emplace_back(key, cx.waker);
+      }
+      return Poll<Unit>::pending();
+    }
+  };
+  ClosedFut closed() const { return ClosedFut(st); }
 };
 template <class T>
 struct UnboundedReceiver {
@@ -94,7 +132,7 @@ struct UnboundedReceiver {
   UnboundedReceiver(UnboundedReceiver&&) = default;
   UnboundedReceiver& operator=(UnboundedReceiver&&) = default;
   ~UnboundedReceiver() {
-    if (st) st->rx_closed = true;
+    if (st) st->close_rx();
   }
   /// `rx.recv().await`
   struct RecvFut {
@@ -130,6 +168,7 @@ struct PayloadSender {
     return tx.send({value, state});
   }
   bool is_closed() const { return tx.is_closed(); }
+  auto closed() const { return tx.closed(); }
 };
 using PayloadReceiver = Stream<Payload>;
 
@@ -485,6 +524,7 @@ struct ConnSender {
     return Result<Unit>::Ok({});
   }
   bool is_closed() const { return tx.is_closed(); }
+  auto closed() const { return tx.closed(); }  // endpoint.rs:251-253
 };
 struct ConnReceiver {
   std::shared_ptr<BindGuard> guard;

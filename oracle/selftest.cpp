@@ -441,6 +441,23 @@ static Async<Unit> interval_main(MissedTickBehavior b, std::shared_ptr<std::vect
   co_return {};
 }
 
+// ---- tonic-example/tests/test.rs:72-83 basic() server stream; :204-230 client_drops_response_stream ----
+static Async<Unit> tonic_server_stream_client(SocketAddr server, std::shared_ptr<TonicStats> st) {
+  co_await sleep(1 * SEC);
+  Payload q;
+  q.v[0] = TONIC_NAME;
+  u64 t0 = now();
+  auto r = co_await tonic_server_streaming(server, q, false, tonic_reply_for(TONIC_NAME, SocketAddr{ip4(10, 0, 0, 2), 0}));
+  CHECK(r.is_ok() && *r.ok == 3);             // "{i}: Hello Tonic! (10.0.0.2)" x3, then Status::unknown("EOF")
+  CHECK(now() - t0 > 3 * SEC);                // the generator sleeps 1 s after every item
+  // drop the response stream at once: the server's select sees tx.closed() and stops streaming
+  r = co_await tonic_server_streaming(server, q, true, 0);
+  CHECK(r.is_ok() && *r.ok == 0);
+  co_await sleep(10 * SEC);
+  CHECK(st->handled == 2);
+  co_return {};
+}
+
 int main() {
   run_case("task::spawn_in_block_on", [] {
     Runtime rt;
@@ -633,6 +650,17 @@ int main() {
     auto h = cl.spawn(tonic_basic_client(a));
     rt.block_on(join_unwrap(std::move(h)));
     CHECK(st->handled == 2);
+    rt.teardown();
+  });
+  run_case("tonic::basic server stream + client_drops_response_stream (tests/test.rs:72-83,204-230)", [] {
+    Runtime rt;
+    SocketAddr a{ip4(10, 0, 0, 1), 50051};
+    auto server = rt.create_node().ip(a.ip).build();
+    auto cl = rt.create_node().ip(ip4(10, 0, 0, 2)).build();
+    auto st = std::make_shared<TonicStats>();
+    server.spawn(tonic_serve(a, st));
+    auto h = cl.spawn(tonic_server_stream_client(a, st));
+    rt.block_on(join_unwrap(std::move(h)));
     rt.teardown();
   });
   run_case("tonic::invalid_address (tests/test.rs:139-151)", [] {

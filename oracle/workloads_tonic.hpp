@@ -21,13 +21,16 @@ namespace msim_oracle {
 
 constexpr u32 TONIC_NAME = 0x696e6f54u;   // "Toni"
 constexpr u32 TONIC_ERROR = 0x6f727265u;  // "erro"
-enum : u32 { TONIC_OK = 0, TONIC_INVALID_ARGUMENT = 1 };
+enum : u32 { TONIC_OK = 0, TONIC_INVALID_ARGUMENT = 1, TONIC_EOF = 2, TONIC_TRAILER = 3 };
+constexpr u32 TONIC_SERVER_STREAMING = 1u << 31;  // the `server_streaming: bool` of the first message (client.rs:128)
+enum : u32 { TONIC_RESTART_ONLY = 1, TONIC_STREAMING_MIX = 2 };
 
 struct TonicParams {
   u32 n_clients = 6;
   u64 rounds = 10;
   u64 think_ns = 100 * MS;
-  u32 flags = 0;  // 1: the supervisor never kills, only restarts (client_crash as written)
+  u32 flags = 0;  // 1: the supervisor never kills, only restarts (client_crash as written); 2: clients also make
+                  // server-streaming calls (lots_of_replies), sometimes dropping the response stream at once
 };
 struct TonicStats {
   std::array<u32, 8> replies{}, starts{};
@@ -50,13 +53,52 @@ inline Async<Unit> tonic_response_task(Connection conn, Payload request, std::sh
   (void)conn.tx.send(rsp);  // tx.send(..).await?
   co_return {};
 }
+/// select_biased!{ _ = tx.closed() => Closed, item = stream.next() => .. } where the stream is
+/// parked in `sleep(1 s)` (server.rs:289-300 around lots_of_replies' generator, lib.rs:72-81)
+struct ClosedOrSleep {
+  UnboundedSender<std::pair<Payload, LinkState>>::ClosedFut closed;
+  Sleep delay;
+  Poll<bool> poll(Context& cx) {  // true = the client closed
+    if (closed.poll(cx).ready()) return Poll<bool>::done(true);
+    if (delay.poll(cx).ready()) return Poll<bool>::done(false);
+    return Poll<bool>::pending();
+  }
+};
+/// the response task of a server-streaming call: header, then the stream's items, then the trailer
+inline Async<Unit> tonic_stream_response_task(Connection conn, Payload request, std::shared_ptr<TonicStats> st) {
+  st->handled++;
+  u32 name = request.v[0];
+  Payload header;
+  header.v[0] = TONIC_OK;
+  if (conn.tx.send(header).is_err()) co_return {};
+  for (u32 i = 0; i < 3; i++) {  // lots_of_replies: for i in 0..3 { yield reply; sleep(1 s).await }
+    if (conn.tx.is_closed()) co_return {};
+    Payload item;
+    item.v[0] = TONIC_OK;
+    item.v[1] = tonic_reply_for(name, conn.peer) + i;
+    if (conn.tx.send(item).is_err()) co_return {};
+    if (conn.tx.is_closed()) co_return {};
+    if (co_await ClosedOrSleep{conn.tx.closed(), sleep(1 * SEC)}) co_return {};
+  }
+  Payload eof;  // Err(Status::unknown("EOF"))?: the stream's last item
+  eof.v[0] = TONIC_EOF;
+  if (conn.tx.send(eof).is_err()) co_return {};
+  if (conn.tx.is_closed()) co_return {};
+  Payload trailer;
+  trailer.v[0] = TONIC_TRAILER;
+  (void)conn.tx.send(trailer);
+  co_return {};
+}
 inline Async<Unit> tonic_serve(SocketAddr addr, std::shared_ptr<TonicStats> st) {
   Endpoint ep = std::move((co_await Endpoint::bind(addr)).unwrap());
   for (;;) {
     Connection conn = std::move((co_await ep.accept1()).unwrap());
     auto msg = co_await conn.rx.recv();
     if (msg.is_err()) continue;  // maybe handshake or error
-    spawn(tonic_response_task(std::move(conn), *msg.ok, st));
+    if (msg.ok->v[1] & TONIC_SERVER_STREAMING)
+      spawn(tonic_stream_response_task(std::move(conn), *msg.ok, st));
+    else
+      spawn(tonic_response_task(std::move(conn), *msg.ok, st));
   }
 }
 
@@ -83,6 +125,34 @@ inline Async<Result<Payload>> tonic_unary(SocketAddr server, Payload request) {
   co_return R::Ok(*rsp.ok);
 }
 
+/// Grpc::server_streaming (client.rs:110-136) + Streaming::message (codec.rs:30-44): read all three
+/// replies and the EOF status, or drop the response stream right after the header
+/// (tests/test.rs:204-230 client_drops_response_stream)
+inline Async<Result<u32>> tonic_server_streaming(SocketAddr server, Payload request, bool drop_at_once, u32 expect0) {
+  using R = Result<u32>;
+  auto ep = co_await tonic_connect_ep(server);
+  if (ep.is_err()) co_return R::Error(Err::ConnectionRefused);
+  auto c = co_await ep.ok->connect1(server);
+  if (c.is_err()) co_return R::Error(c.err);
+  Connection conn = std::move(*c.ok);
+  ep.ok.reset();
+  request.v[1] |= TONIC_SERVER_STREAMING;
+  if (conn.tx.send(request).is_err()) co_return R::Error(Err::ConnectionReset);
+  auto header = co_await conn.rx.recv();
+  if (header.is_err()) co_return R::Error(header.err);
+  if (header.ok->v[0] != TONIC_OK) panic("bad streaming header", 75);
+  if (drop_at_once) co_return R::Ok(0);
+  for (u32 i = 0; i < 3; i++) {
+    auto m = co_await conn.rx.recv();
+    if (m.is_err()) co_return R::Error(m.err);
+    if (m.ok->v[0] != TONIC_OK || m.ok->v[1] != expect0 + i) panic("unexpected streamed reply", 76);
+  }
+  auto e = co_await conn.rx.recv();
+  if (e.is_err()) co_return R::Error(e.err);
+  if (e.ok->v[0] != TONIC_EOF) panic("expected the EOF status", 77);
+  co_return R::Ok(3);
+}
+
 /// the client node's init task (tests/test.rs:176-194, unary part)
 inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::shared_ptr<TonicStats> st) {
   st->starts[c]++;
@@ -94,8 +164,16 @@ inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::sh
   GlobalRng& rng = thread_rng();
   for (u32 seq = 0;; seq++) {
     Payload q;
-    q.v[0] = rng.gen_range_u64(0, 10) == 0 ? TONIC_ERROR : TONIC_NAME;
+    u64 pick = rng.gen_range_u64(0, 10);
+    q.v[0] = pick == 0 ? TONIC_ERROR : TONIC_NAME;
     q.v[1] = seq;
+    if ((p.flags & TONIC_STREAMING_MIX) && pick >= 1 && pick <= 3) {  // lots_of_replies; pick 3 drops the stream at once
+      auto sr = co_await tonic_server_streaming(server, q, pick == 3, tonic_reply_for(TONIC_NAME, me));
+      if (sr.is_err()) panic("lots_of_replies failed", 71);
+      st->replies[c]++;
+      co_await sleep(p.think_ns);
+      continue;
+    }
     auto r = co_await tonic_unary(server, q);
     if (r.is_err()) panic("say_hello failed", 71);
     if (q.v[0] == TONIC_ERROR) {
@@ -127,7 +205,7 @@ inline Async<u32> wl_tonic_main(TonicParams p, std::array<u32, 4>* user) {
     co_await sleep(rng.gen_range_duration(0, 5 * SEC));
     u64 c = rng.gen_range_u64(0, p.n_clients);
     u64 k = rng.gen_range_u64(0, 4);
-    if (k == 3 && !(p.flags & 1))
+    if (k == 3 && !(p.flags & TONIC_RESTART_ONLY))
       rt.kill(ids[c]);
     else
       rt.restart(ids[c]);

@@ -1302,7 +1302,8 @@ MSIM_NOUNROLL
               break;
             }
             case W_SLEEP_CLOSED:  // the Sleep won: the closed() future drops with the select
-              if (C::USES_CLOSED) w(L::W_CH_CLOSED_WAITER, t_conn(t)) = NONE32;
+              if (!C::USES_CLOSED) break;
+              w(L::W_CH_CLOSED_WAITER, t_conn(t)) = NONE32;
               ret = 0;
               wt = W_NONE;
               break;
@@ -1378,6 +1379,7 @@ MSIM_NOUNROLL
           t_wait(t) = W_SLEEP | WF_SLEEP;
           break;
         case RQ_SLEEP_OR_CLOSED:
+          if (!C::USES_CLOSED) break;
           t_dl0(t) = sleep_deadline(now + xa);
           t_wait(t) = W_SLEEP_CLOSED | WF_SLEEP;
           break;

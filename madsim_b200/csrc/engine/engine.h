@@ -187,8 +187,10 @@ struct Layout {
   static constexpr int BYTES = round_up(B_BASE + NB, 16);  // one seed; a CTA's block is S * BYTES
 };
 
-/// One lane's view of its seed.  `WL` supplies Caps + the state machines.
-template <class WL>
+/// One lane's view of its seed.  `WL` supplies Caps + the state machines; `TRACE` = the variant that
+/// also appends full trace records (single-seed replay, msim_batch_trace) — the batch kernels carry
+/// neither its registers nor its code.
+template <class WL, bool TRACE = true>
 struct Engine {
   using C = typename WL::Caps;
   using L = Layout<C>;
@@ -294,7 +296,7 @@ struct Engine {
     u32 d = (u32)draws;
     u64 kd = ((u64)kind_id << 32) | d;
     hash = mix(hash, t_now ^ rotl64(aux, 17) ^ rotl64(kd, 41));
-    if (tr) {
+    if (TRACE && tr) {
       if (tr_n < tr_cap) {
         tr[tr_n].now_ns = t_now;
         tr[tr_n].aux = aux;

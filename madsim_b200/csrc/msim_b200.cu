@@ -97,9 +97,9 @@ __device__ __forceinline__ void bulk_commit_wait() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <class WL>
+template <class WL, bool TRACE>
 __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_constant__ KernelArgs a) {
-  using E = Engine<WL>;
+  using E = Engine<WL, TRACE>;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* block = smem + SMEM_HDR;
@@ -251,7 +251,8 @@ int set_err(int code, const std::string& m) {
 
 template <class WL>
 cudaError_t launch_wl(const KernelArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
-  auto k = msim_step_kernel<WL>;
+  // two instantiations per program: the batch kernel, and the single-seed replay that also records the trace
+  auto k = a.trace ? msim_step_kernel<WL, true> : msim_step_kernel<WL, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<grid, block, smem, st>>>(a);

@@ -133,6 +133,7 @@ struct Params {
   u64 lat_range; // inclusive range size
   u64 lat_zone;  // acceptance zone
   u64 time_limit_ns;  // 0 = none
+  u64 time_limit_cmp; // time_limit_ns, or u64::MAX when there is none (one compare per event)
   u32 buggify;
   u32 reserved;
   u64 buggify_p10_int;  // (0.1 * 2^64) as u64, computed on the host in f64 like rand does

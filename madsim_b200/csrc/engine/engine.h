@@ -1636,7 +1636,7 @@ MSIM_NOUNROLL
     expire(limit);  // the one place timers fire from the event loop
     if (now != limit) {
       now = limit;
-      if (MSIM_UNLIKELY(P->time_limit_ns && now >= P->time_limit_ns)) {
+      if (MSIM_UNLIKELY(now >= P->time_limit_cmp)) {  // u64::MAX when there is no limit
         fail(MSIM_ST_FAIL_TIME_LIMIT, 0);
         return false;
       }

@@ -121,6 +121,7 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
     P.lat_zone = ~0ull - ((~0ull - range + 1) % range);
   }
   P.time_limit_ns = c.time_limit_ns;
+  P.time_limit_cmp = c.time_limit_ns ? c.time_limit_ns : ~0ull;
   P.buggify = c.buggify ? 1 : 0;
   P.buggify_p10_int = (u64)(0.1 * 18446744073709551616.0);
   // workload parameter validation

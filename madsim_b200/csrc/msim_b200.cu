@@ -97,9 +97,11 @@ __device__ __forceinline__ void bulk_commit_wait() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <class WL, bool TRACE>
+/// GENERAL = false: the batch kernel — run to completion, dynamic seed queue, no event budget, no
+/// checkpoint staging, no trace records.  GENERAL = true: bursts / resume / single-seed replay.
+template <class WL, bool GENERAL>
 __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_constant__ KernelArgs a) {
-  using E = Engine<WL, TRACE>;
+  using E = Engine<WL, GENERAL>;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   unsigned char* block = smem + SMEM_HDR;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
   unsigned char* gblob = a.blob ? a.blob + (size_t)blockIdx.x * block_bytes : nullptr;
 
   // ---- stage in: TMA bulk copy of the checkpoint (resume) ----
-  if (a.resume) {
+  if (GENERAL && a.resume) {
     if (threadIdx.x == 0) {
       mbar_init(bar, 1);
       fence_proxy_async();
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
   e.tr_n = 0;
   e.status = MSIM_ST_PASS;
   if (active) {
-    if (a.trace) {
+    if (GENERAL && a.trace) {
       e.tr = a.trace;
       e.tr_cap = a.trace_cap;
     }
@@ -148,11 +150,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
     // independent: the assignment cannot change any result.  One event-loop site for both.
     uint64_t idx = first + col;
     for (;;) {
-      if (a.dynamic) {
+      if (!GENERAL || a.dynamic) {
         idx = atomicAdd(a.next_seed, 1u);
         if (idx >= a.n_seeds) break;
       }
-      if (a.resume) {
+      if (GENERAL && a.resume) {
         e.load();
         if (a.trace) e.tr_n = *a.trace_n;
       } else {
@@ -160,22 +162,27 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
       }
       // ---- the event loop: up to max_events steps out of shared memory / registers ----
       if (e.status == MSIM_ST_RUNNING) {
-        uint64_t budget = a.max_events ? a.max_events : ~0ull;
-        while (budget-- && e.step()) {
+        if (GENERAL) {
+          uint64_t budget = a.max_events ? a.max_events : ~0ull;
+          while (budget-- && e.step()) {
+          }
+        } else {
+          while (e.step()) {
+          }
         }
       }
       e.store();
       SeedResult r;
       e.result(r);
       a.results[idx] = r;
-      if (!a.dynamic) break;
+      if (GENERAL && !a.dynamic) break;
     }
-    if (a.trace) *a.trace_n = e.tr_n;
+    if (GENERAL && a.trace) *a.trace_n = e.tr_n;
   }
   // ---- stage out: in burst mode (a checkpoint buffer exists) the block always goes back to HBM,
   // finished seeds included, so that a later resume reloads a consistent image ----
-  if (active && !a.dynamic && e.status == MSIM_ST_RUNNING) atomicAdd(a.unfinished, 1u);
-  if (gblob && !a.dynamic) {
+  if (GENERAL && active && !a.dynamic && e.status == MSIM_ST_RUNNING) atomicAdd(a.unfinished, 1u);
+  if (GENERAL && gblob && !a.dynamic) {
     fence_proxy_async();  // generic-proxy smem writes → visible to the async proxy
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -251,8 +258,9 @@ int set_err(int code, const std::string& m) {
 
 template <class WL>
 cudaError_t launch_wl(const KernelArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
-  // two instantiations per program: the batch kernel, and the single-seed replay that also records the trace
-  auto k = a.trace ? msim_step_kernel<WL, true> : msim_step_kernel<WL, false>;
+  // two instantiations per program: the batch kernel (dynamic run-to-completion launches), and the general
+  // one (bursts through the checkpoint, resume, single-seed replay with trace records)
+  auto k = a.dynamic ? msim_step_kernel<WL, false> : msim_step_kernel<WL, true>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<grid, block, smem, st>>>(a);

@@ -37,7 +37,7 @@ B_MSG = 40            # one datagram send/deliver
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the bench configuration,
 # from the `ncu --set full` capture summarised in profiles/r1c_step_kernel_v2_bench_config.json
-TRAFFIC_BYTES_PER_LAUNCH = {"raft": 69376}
+TRAFFIC_BYTES_PER_LAUNCH = {"raft": 67072}
 
 
 def algorithmic_bytes(ev_pop, ev_fire, msgs):
@@ -311,7 +311,7 @@ def main():
         "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.workload), "kernel": "msim_step_kernel<WL_Raft>", "peak_source": peak_src,
         "bytes_per_launch": alg_bytes / args.steps, "launch_ms": local_ms / args.steps,
         "note": "algorithmic bytes (SURVEY §8d model: 168 B/pop, 92+40*3.8 B/fire, 32 B/push, 40 B/msg). The kernel keeps "
-                "all per-seed state in shared memory: measured DRAM traffic is ~0.07 MB per launch (profiles/r1k), so the "
+                "all per-seed state in shared memory: measured DRAM traffic is ~0.07 MB per launch (profiles/r1l), so the "
                 "kernel is instruction-issue/latency bound, not HBM bound; frac is reported against HBM as the contract asks.",
     }
 

@@ -122,7 +122,8 @@ typedef struct msim_config {
  *           2 = clients also delete the leased key: reaches the crate's own expect("no lease")), p4 = lease ttl s (default 1)
  *  TONIC    n_nodes = 1 server + (n_nodes-1) client nodes (default 7); p0 = chaos rounds (default 10),
  *           p1 = think time ns between unary calls (default 100 ms), p2 = flags (1 = restart only, never kill;
- *           2 = clients also make server-streaming calls and sometimes drop the response stream at once)
+ *           2 = clients also make server-streaming calls, sometimes dropping the response stream at once,
+ *           and client-streaming calls)
  *  SIGNAL   p0 = supervisor rounds (default 8), p1 = interval period ms (default 100),
  *           p2 = MissedTickBehavior (0 Burst, 1 Delay, 2 Skip), p3 = flags (1 = the worker installs a ctrl-c handler; default 1)
  *  CHAOS    p0 = rounds, p1 = period ms, p2 = worker panics on its first p2 starts (restart_on_panic)
@@ -188,7 +189,9 @@ int msim_batch_set_geometry(msim_batch* b, uint32_t seeds_per_cta, uint32_t lane
 int msim_batch_set_stream(msim_batch* b, void* cuda_stream);
 
 /* Builder::run seed sweep (builder.rs:129-150): seeds seed_base..seed_base+n.
- * max_events_per_seed = 0 → run every seed to completion in one launch;
+ * max_events_per_seed = 0 → run every seed to completion in one launch (at most one
+ * persistent CTA per SM; a slot whose seed has finished pulls the next seed index from a
+ * device-side queue, so seeds of very different lengths do not idle the GPU);
  * otherwise each launch advances every unfinished seed by at most that many
  * events, checkpoints the per-seed state to HBM and msim_batch_resume continues. */
 int msim_batch_run(msim_batch* b, uint64_t seed_base, uint64_t n_seeds, uint64_t max_events_per_seed);

@@ -119,7 +119,8 @@ class Workload:
               streaming: bool = False) -> "Workload":
         """tonic-example Greeter service under madsim-tonic (a fresh endpoint + handshake + connection per
         unary call) while a supervisor kills / restarts the client nodes (BASELINE config 5); with `streaming`
-        the clients also make server-streaming calls (lots_of_replies) and sometimes drop the response stream."""
+        the clients also make server-streaming (lots_of_replies, sometimes dropping the response stream) and
+        client-streaming (lots_of_greetings) calls."""
         return Workload(N.WL_TONIC, clients + 1, [rounds, think_ns, int(restart_only) | 2 * int(streaming), 0, 0, 0, 0, 0])
 
     @staticmethod

@@ -944,6 +944,12 @@ MSIM_NOUNROLL
     t_conn(t) = NONE8;
     conn_drop(e);
   }
+  /// Dropping only the Sender of the end a task holds (a request stream that ended: client.rs:171-196)
+  MSIM_HD void conn_drop_tx(int t) {
+    int e = t_conn(t);  // direction 2*conn+side is the one this end sends on
+    ch_flags(e) &= ~CH_TX_ALIVE;
+    wake_waiter(w(L::W_CH_WAITER, e));
+  }
   MSIM_HD void conn_drop(int e) {
     int c = e >> 1, side = e & 1;
     int d_tx = 2 * c + side, d_rx = 2 * c + (side ^ 1);

@@ -1,6 +1,7 @@
 // MSIM_WL_TONIC — BASELINE config 5 / SURVEY §8(f) row 3: the tonic-example Greeter service under
 // madsim-tonic while a supervisor kills / restarts the client nodes
-// (tonic-example/tests/test.rs:155-202 client_crash, widened to six client nodes; unary calls).
+// (tonic-example/tests/test.rs:155-202 client_crash, widened to six client nodes; unary calls and, with
+// flag 2, server-streaming lots_of_replies and client-streaming lots_of_greetings).
 //
 //   Server::serve_with_shutdown    madsim-tonic/src/transport/server.rs:217-336
 //   Endpoint::connect / connect_ep madsim-tonic/src/transport/channel.rs:75-111  (fresh endpoint + handshake per call)
@@ -26,12 +27,12 @@ struct WL_Tonic {
     static constexpr bool USES_KILL = true;
     static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
     static constexpr bool USES_CLOSED = true;   // does any task await Sender::closed()?
-    static constexpr int NCONN = 32, NCQ = 2, NACC = 32;
+    static constexpr int NCONN = 32, NCQ = 4, NACC = 32;  // a client-streaming call queues header + 3 items at a slow server
   };
-  enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_CLIENT_STREAM };
+  enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_CLIENT2 };
   enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u };
   enum : u32 { ST_OK = 0, ST_INVALID_ARGUMENT = 1, ST_EOF = 2, ST_TRAILER = 3 };
-  enum : u32 { SERVER_STREAMING = 1u << 31, FLAG_RESTART_ONLY = 1, FLAG_STREAMING_MIX = 2 };
+  enum : u32 { SERVER_STREAMING = 1u << 31, CLIENT_STREAMING = 1u << 30, FLAG_RESTART_ONLY = 1, FLAG_STREAMING_MIX = 2 };
   static constexpr u32 MAIN_KIND = K_MAIN;
   static constexpr u32 SERVER_ADDR = (IPK_NODE << 24) | (1u << 16) | 50051u;  // 10.0.0.1:50051
   /// NodeBuilder::init(|| tonic_client(c)) — what Handle::restart re-runs
@@ -133,7 +134,7 @@ struct WL_Tonic {
             continue;
           }
           e.t_pc(t) = 2;  // spawn the response task with tx (and the request)
-          e.ya = ((e.rv1 & SERVER_STREAMING) ? (u32)K_RSP_STREAM : (u32)K_RSP) | SPAWN_CONN, e.yb = e.t_node(t), e.yc = e.rv0, e.yd = e.t_b(t), e.xa = e.rv1, e.xb = 0;
+          e.ya = ((e.rv1 & CLIENT_STREAMING) ? (u32)K_RSP_CSTREAM : (e.rv1 & SERVER_STREAMING) ? (u32)K_RSP_STREAM : (u32)K_RSP) | SPAWN_CONN, e.yb = e.t_node(t), e.yc = e.rv0, e.yd = e.t_b(t), e.xa = e.rv1, e.xb = 0;
           return RQ_SPAWN;
 
         // ---- tonic_response_task ----
@@ -191,6 +192,24 @@ struct WL_Tonic {
         case K_RSP_STREAM * 16 + 6:
           return RQ_READY;
 
+        // ---- tonic_client_stream_response_task: lots_of_greetings reads the request stream to its end ----
+        case K_RSP_CSTREAM * 16 + 0:
+          e.wl_s(S_HANDLED)++;
+          e.t_c(t) = 0;  // fold of the names
+          e.t_pc(t) = 1;
+          return RQ_CH_RECV;
+        case K_RSP_CSTREAM * 16 + 1:
+          if (e.ret >= 0) {  // while let Some(request) = stream.message().await?
+            e.t_c(t) = e.t_c(t) * 33u + e.rv0;
+            return RQ_CH_RECV;
+          }
+          if (e.conn_tx_closed(t)) return RQ_READY;  // select_biased!{ tx.closed() => return, .. }
+          e.t_pc(t) = 2;
+          e.yb = ST_OK, e.yc = reply_for(e.t_c(t), e.t_b(t));
+          return RQ_CH_SEND;
+        case K_RSP_CSTREAM * 16 + 2:
+          return RQ_READY;
+
         // ---- tonic_client: the client node's init task ----
         case K_CLIENT * 16 + 0:  // GreeterClient::connect: connect_ep, then drop it
           e.wl_w(F_STARTS, e.t_node(t))++;
@@ -215,7 +234,7 @@ struct WL_Tonic {
           return RQ_GEN_RANGE;
         case K_CLIENT * 16 + 4:  // Grpc::unary / server_streaming -> connect_ep: Endpoint::connect
           e.t_a(t) = e.ret64 == 0 ? (u32)ERROR_NAME : (u32)NAME;
-          e.t_c(t) = ((P.p[2] & FLAG_STREAMING_MIX) && e.ret64 >= 1 && e.ret64 <= 3) ? (u32)e.ret64 : 0u;  // 1..3: lots_of_replies
+          e.t_c(t) = ((P.p[2] & FLAG_STREAMING_MIX) && e.ret64 >= 1 && e.ret64 <= 4) ? (u32)e.ret64 : 0u;  // 1..3: lots_of_replies, 4: lots_of_greetings
           e.t_pc(t) = 5;
           e.ya = mk_addr(IPK_UNSPEC, 0, 0);
           return RQ_BIND;
@@ -232,6 +251,13 @@ struct WL_Tonic {
           return RQ_CONNECT1;
         case K_CLIENT * 16 + 7:
           if (e.ret < 0) return panic(e, 71);
+          if (e.t_c(t) == 4) {  // client streaming: the stream-start header, then hello_stream's items
+            e.t_c(t) = 32;      // 32 + items sent
+            e.t_a(t) = 0;       // fold of the names sent
+            e.t_pc(t) = 11;
+            e.yb = 0, e.yc = e.t_b(t) | CLIENT_STREAMING;
+            return RQ_CH_SEND;
+          }
           e.t_pc(t) = 8;
           e.yb = e.t_a(t), e.yc = e.t_b(t) | (e.t_c(t) ? (u32)SERVER_STREAMING : 0u);
           return RQ_CH_SEND;
@@ -280,6 +306,43 @@ struct WL_Tonic {
             return RQ_CH_RECV;
           }
           if (e.rv0 != ST_EOF) return panic(e, 77);
+          e.conn_drop_end(t);
+          e.sock_unref(t);
+          e.wl_w(F_REPLIES, node)++;
+          e.t_b(t)++;
+          e.t_pc(t) = 3;
+          e.xa = P.p[1];
+          return RQ_SLEEP_FOR;
+        }
+        case K_CLIENT * 16 + 11:  // header sent (tx.send(..).await?), then: yield item i; sleep(1 s)
+          if (e.ret < 0) return panic(e, 71);
+          // fallthrough
+        case K_CLIENT * 16 + 12: {
+          u32 i = e.t_c(t) - 32;
+          if (i >= 3) {  // the request stream ended: send_request_stream returns, its Sender drops
+            e.conn_drop_tx(t);
+            e.t_pc(t) = 14;
+            return RQ_CH_RECV;
+          }
+          e.t_a(t) = e.t_a(t) * 33u + (NAME + i);
+          e.t_pc(t) = 13;
+          e.yb = NAME + i, e.yc = 0;
+          return RQ_CH_SEND;
+        }
+        case K_CLIENT * 16 + 13:
+          if (e.ret < 0) {  // the server closed the stream prematurely: stop sending
+            e.t_c(t) = 35;
+            e.t_pc(t) = 12;
+            continue;
+          }
+          e.t_c(t)++;
+          e.t_pc(t) = 12;
+          e.xa = NS_PER_SEC;
+          return RQ_SLEEP_FOR;
+        case K_CLIENT * 16 + 14: {
+          if (e.ret < 0) return panic(e, 71);
+          u32 node = e.t_node(t);
+          if (e.rv0 != ST_OK || e.rv1 != e.t_a(t) * 31u + node) return panic(e, 78);
           e.conn_drop_end(t);
           e.sock_unref(t);
           e.wl_w(F_REPLIES, node)++;

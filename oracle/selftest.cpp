@@ -455,6 +455,11 @@ static Async<Unit> tonic_server_stream_client(SocketAddr server, std::shared_ptr
   CHECK(r.is_ok() && *r.ok == 0);
   co_await sleep(10 * SEC);
   CHECK(st->handled == 2);
+  // client stream (tests/test.rs:85-94): "Hello Tonic0 Tonic1 Tonic2! (10.0.0.2)" after the three requests, 1 s apart
+  t0 = now();
+  r = co_await tonic_client_streaming(server, 0, SocketAddr{ip4(10, 0, 0, 2), 0});
+  CHECK(r.is_ok() && *r.ok == 3 && now() - t0 > 3 * SEC);
+  CHECK(st->handled == 3);
   co_return {};
 }
 
@@ -652,7 +657,7 @@ int main() {
     CHECK(st->handled == 2);
     rt.teardown();
   });
-  run_case("tonic::basic server stream + client_drops_response_stream (tests/test.rs:72-83,204-230)", [] {
+  run_case("tonic::basic server stream, client stream + client_drops_response_stream (tests/test.rs:72-94,204-230)", [] {
     Runtime rt;
     SocketAddr a{ip4(10, 0, 0, 1), 50051};
     auto server = rt.create_node().ip(a.ip).build();

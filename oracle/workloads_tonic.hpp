@@ -2,7 +2,8 @@
 //
 // MSIM_WL_TONIC — BASELINE config 5 / SURVEY §8(f) row 3: the tonic-example Greeter service under
 // madsim-tonic with a kill/restart chaos schedule (tonic-example/tests/test.rs:155-202
-// client_crash, widened from one client node to six; unary calls only).
+// client_crash, widened from one client node to six; unary calls and, with flag 2, server- and
+// client-streaming calls).
 //
 //   Server::serve_with_shutdown   madsim-tonic/src/transport/server.rs:217-336
 //       bind; loop { accept1; first message INLINE (Err = handshake: continue); spawn the
@@ -23,6 +24,7 @@ constexpr u32 TONIC_NAME = 0x696e6f54u;   // "Toni"
 constexpr u32 TONIC_ERROR = 0x6f727265u;  // "erro"
 enum : u32 { TONIC_OK = 0, TONIC_INVALID_ARGUMENT = 1, TONIC_EOF = 2, TONIC_TRAILER = 3 };
 constexpr u32 TONIC_SERVER_STREAMING = 1u << 31;  // the `server_streaming: bool` of the first message (client.rs:128)
+constexpr u32 TONIC_CLIENT_STREAMING = 1u << 30;  // the first message is the stream-start header Box<()> (client.rs:170-176)
 enum : u32 { TONIC_RESTART_ONLY = 1, TONIC_STREAMING_MIX = 2 };
 
 struct TonicParams {
@@ -89,13 +91,33 @@ inline Async<Unit> tonic_stream_response_task(Connection conn, Payload request, 
   (void)conn.tx.send(trailer);
   co_return {};
 }
+/// the response task of a client-streaming call (lots_of_greetings, lib.rs:85-103): the service reads the
+/// request stream until the client's Sender drops, then answers like a unary call
+inline u32 tonic_fold_names(u32 acc, u32 name) { return acc * 33u + name; }
+inline Async<Unit> tonic_client_stream_response_task(Connection conn, std::shared_ptr<TonicStats> st) {
+  st->handled++;
+  u32 acc = 0;
+  for (;;) {  // while let Some(request) = stream.message().await?
+    auto m = co_await conn.rx.recv();
+    if (m.is_err()) break;
+    acc = tonic_fold_names(acc, m.ok->v[0]);
+  }
+  if (conn.tx.is_closed()) co_return {};
+  Payload rsp;
+  rsp.v[0] = TONIC_OK;
+  rsp.v[1] = tonic_reply_for(acc, conn.peer);
+  (void)conn.tx.send(rsp);
+  co_return {};
+}
 inline Async<Unit> tonic_serve(SocketAddr addr, std::shared_ptr<TonicStats> st) {
   Endpoint ep = std::move((co_await Endpoint::bind(addr)).unwrap());
   for (;;) {
     Connection conn = std::move((co_await ep.accept1()).unwrap());
     auto msg = co_await conn.rx.recv();
     if (msg.is_err()) continue;  // maybe handshake or error
-    if (msg.ok->v[1] & TONIC_SERVER_STREAMING)
+    if (msg.ok->v[1] & TONIC_CLIENT_STREAMING)
+      spawn(tonic_client_stream_response_task(std::move(conn), st));
+    else if (msg.ok->v[1] & TONIC_SERVER_STREAMING)
       spawn(tonic_stream_response_task(std::move(conn), *msg.ok, st));
     else
       spawn(tonic_response_task(std::move(conn), *msg.ok, st));
@@ -153,6 +175,36 @@ inline Async<Result<u32>> tonic_server_streaming(SocketAddr server, Payload requ
   co_return R::Ok(3);
 }
 
+/// Grpc::client_streaming (client.rs:82-108) + send_request_stream (:171-196) over hello_stream
+/// (tests/test.rs:119-129: three requests, 1 s apart); the Sender drops when the stream ends
+inline Async<Result<u32>> tonic_client_streaming(SocketAddr server, u32 seq, SocketAddr me) {
+  using R = Result<u32>;
+  auto ep = co_await tonic_connect_ep(server);
+  if (ep.is_err()) co_return R::Error(Err::ConnectionRefused);
+  auto c = co_await ep.ok->connect1(server);
+  if (c.is_err()) co_return R::Error(c.err);
+  Connection conn = std::move(*c.ok);
+  ep.ok.reset();
+  u32 acc = 0;
+  {
+    ConnSender tx = std::move(conn.tx);  // moved into send_request_stream
+    Payload header;
+    header.v[1] = seq | TONIC_CLIENT_STREAMING;
+    if (tx.send(header).is_err()) co_return R::Error(Err::ConnectionReset);
+    for (u32 i = 0; i < 3; i++) {
+      Payload item;
+      item.v[0] = TONIC_NAME + i;
+      acc = tonic_fold_names(acc, item.v[0]);
+      if (tx.send(item).is_err()) break;  // "allows the server to prematurely close the stream"
+      co_await sleep(1 * SEC);
+    }
+  }
+  auto rsp = co_await conn.rx.recv();
+  if (rsp.is_err()) co_return R::Error(rsp.err);
+  if (rsp.ok->v[0] != TONIC_OK || rsp.ok->v[1] != tonic_reply_for(acc, me)) panic("unexpected client-streaming reply", 78);
+  co_return R::Ok(3);
+}
+
 /// the client node's init task (tests/test.rs:176-194, unary part)
 inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::shared_ptr<TonicStats> st) {
   st->starts[c]++;
@@ -170,6 +222,13 @@ inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::sh
     if ((p.flags & TONIC_STREAMING_MIX) && pick >= 1 && pick <= 3) {  // lots_of_replies; pick 3 drops the stream at once
       auto sr = co_await tonic_server_streaming(server, q, pick == 3, tonic_reply_for(TONIC_NAME, me));
       if (sr.is_err()) panic("lots_of_replies failed", 71);
+      st->replies[c]++;
+      co_await sleep(p.think_ns);
+      continue;
+    }
+    if ((p.flags & TONIC_STREAMING_MIX) && pick == 4) {  // lots_of_greetings
+      auto sr = co_await tonic_client_streaming(server, seq, me);
+      if (sr.is_err()) panic("lots_of_greetings failed", 71);
       st->replies[c]++;
       co_await sleep(p.think_ns);
       continue;

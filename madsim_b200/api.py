@@ -120,7 +120,7 @@ class Workload:
         """tonic-example Greeter service under madsim-tonic (a fresh endpoint + handshake + connection per
         unary call) while a supervisor kills / restarts the client nodes (BASELINE config 5); with `streaming`
         the clients also make server-streaming (lots_of_replies, sometimes dropping the response stream) and
-        client-streaming (lots_of_greetings) calls."""
+        client-streaming (lots_of_greetings) and bidi (bidi_hello, sometimes dropped after one reply) calls."""
         return Workload(N.WL_TONIC, clients + 1, [rounds, think_ns, int(restart_only) | 2 * int(streaming), 0, 0, 0, 0, 0])
 
     @staticmethod

@@ -49,10 +49,10 @@ enum : u8 {
   W_CONNECT = 10,    // connect1: rand_delay, then the connection request (net/mod.rs:337-364)
   W_ACCEPT = 11,     // accept1: rand_delay FIRST, then the next incoming connection (endpoint.rs:197-211)
   W_CH_RECV = 12,    // Receiver::recv: the channel's delay/back-off stream (net/mod.rs:385-402)
-  W_SLEEP_CLOSED = 14,  // select_biased!{ tx.closed(), sleep }: the connection's Sender::closed() first, then a Sleep
   W_CTRLC = 13,      // signal::ctrl_c: watch::Receiver::changed() on the node's channel (signal.rs:4-8)
   WF_RD = 0x10,      // rand_delay not drawn yet: draw it now, then sleep on dl0
   WF_SLEEP = 0x20,   // sleeping on dl0
+  WF_CLOSED = 0x40,  // select_biased!{ conn.tx.closed() => .., <the wait> }: closed() is polled first (W_SLEEP, W_CH_RECV)
 };
 
 // ---- requests a state machine returns to the engine ----
@@ -78,9 +78,10 @@ enum : int {
   RQ_CH_RECV,       // conn.rx.recv()                  -> ret 0, rv0, rv1 / -1 ConnectionReset
   RQ_SLEEP_RAW,     // Sleep::reset(xa) + await: the deadline is NOT clamped to now + 1 ms (time/sleep.rs:40-42, interval.rs:156)
   RQ_CTRL_C,        // signal::ctrl_c().await (installs the node's handler on first use)
-  RQ_SLEEP_OR_CLOSED,  // select_biased!{ conn.tx.closed() => -1, sleep(xa ns) => 0 }  (madsim-tonic server.rs:289-300)
+  RQ_SLEEP_OR_CLOSED,  // select_biased!{ conn.tx.closed() => -2, sleep(xa ns) => 0 }  (madsim-tonic server.rs:289-300)
+  RQ_CH_RECV_OR_CLOSED,  // select_biased!{ conn.tx.closed() => -2, conn.rx.recv() => 0 / -1 }
 };
-enum : u32 { SPAWN_EP = 0x100, SPAWN_JOINABLE = 0x200, SPAWN_CONN = 0x400 };  // clone the Endpoint / keep a JoinHandle / move the connection end
+enum : u32 { SPAWN_EP = 0x100, SPAWN_JOINABLE = 0x200, SPAWN_CONN = 0x400, SPAWN_CONN_TX = 0x800 };  // clone the Endpoint / keep a JoinHandle / move the connection end / move only its Sender
 enum : u32 { NODE_IP = 1, NODE_INIT = 2, NODE_RESTART_ON_PANIC = 4 };
 enum : int { CALL_OK = 1, CALL_TIMEOUT = 2 };
 
@@ -172,7 +173,10 @@ struct Layout {
   static constexpr int B_N_EPOCH = B_N_FLAGS + C::NNODE;
   static constexpr int B_PK = B_N_EPOCH + C::NNODE;        // [NPARK] parked runnables, park order
   static constexpr int B_T_CONN = B_PK + C::NPARK;         // [NT] connection end the future holds: conn<<1|side, or NONE8
-  static constexpr int B_CH_HEAD = B_T_CONN + (C::NCONN ? C::NT : 0);  // [ND] FIFO head / length
+  static constexpr int NTS = C::USES_SPLIT ? C::NT : 0;
+  static constexpr int B_T_CONNHALF = B_T_CONN + (C::NCONN ? C::NT : 0);  // [NTS] halves of the end this future owns: 1 Sender, 2 Receiver
+  static constexpr int B_T_HANDLE = B_T_CONNHALF + NTS;    // [NTS] task whose FallibleTask (cancel_on_drop) this future holds, or NONE8
+  static constexpr int B_CH_HEAD = B_T_HANDLE + NTS;       // [ND] FIFO head / length
   static constexpr int B_CH_LEN = B_CH_HEAD + ND;
   static constexpr int B_CH_PHASE = B_CH_LEN + ND;         // [ND] 0 idle, 1 back-off sleep, 2 arrival sleep
   static constexpr int B_CH_SRC = B_CH_PHASE + ND;         // [ND] test_link source node
@@ -224,6 +228,8 @@ struct Engine {
   MSIM_HD u8& t_sockgen(int t) const { return b(L::B_T_SOCKGEN, t); }
   MSIM_HD u8& t_msg(int t) const { return b(L::B_T_MSG, t); }
   MSIM_HD u8& t_conn(int t) const { return b(L::B_T_CONN, t); }
+  MSIM_HD u8& t_connhalf(int t) const { return b(L::B_T_CONNHALF, t); }
+  MSIM_HD u8& t_handle(int t) const { return b(L::B_T_HANDLE, t); }
   MSIM_HD u32& t_spawn(int t) const { return w(L::W_T_SPAWN, t); }
   MSIM_HD u32& t_aw(int t) const { return w(L::W_T_AW, t); }
   MSIM_HD u32& t_a(int t) const { return w(L::W_T_A, t); }
@@ -508,6 +514,13 @@ struct Engine {
         t_msg(t) = NONE8;
       }
       if (C::USES_JOIN && st == W_JOIN) join_detach((int)t_c(t));
+      if (C::USES_SPLIT && t_handle(t) != NONE8) {  // `_task` drops before the stream's Receiver
+        if (t_handle(t) & 0x80)
+          join_detach(t_handle(t) & 0x7f);  // still a plain JoinHandle (the stream was never polled): detach
+        else
+          task_cancel_detach(t_handle(t));
+        t_handle(t) = NONE8;
+      }
       if (C::NCONN) conn_drop_end(t);
       sock_unref(t);
       t_wait(t) = W_NONE;
@@ -556,6 +569,7 @@ MSIM_NOUNROLL
     t_sock(t) = NONE8;
     t_msg(t) = NONE8;
     if (C::NCONN) t_conn(t) = NONE8;
+    if (C::USES_SPLIT) t_connhalf(t) = 3, t_handle(t) = NONE8;
     t_spawn(t) = idx;
     t_aw(t) = NONE32;
     u32 live = ++w(L::W_LIVE_TASKS);
@@ -586,6 +600,21 @@ MSIM_NOUNROLL
     t_flags(target) = t_flags(target) & ~TF_JOINABLE;
     t_aw(target) = NONE32;
     maybe_free(target);
+  }
+  /// Drop of the FallibleTask made by JoinHandle::cancel_on_drop (task/join.rs:54-56; async-task Task::drop):
+  /// close the task; if it is neither scheduled nor running, schedule it so that the executor drops its future
+  MSIM_HD void task_cancel_detach(int x) {
+    u8 f = t_flags(x);
+    if (!(f & (TF_COMPLETED | TF_CLOSED))) {
+      f |= TF_CLOSED;
+      if (!(f & (TF_SCHEDULED | TF_RUNNING))) {
+        t_flags(x) = f | TF_SCHEDULED;
+        rq_push(x);
+      } else {
+        t_flags(x) = f;
+      }
+    }
+    join_detach(x);
   }
   /// AbortHandle::abort (task/join.rs:158-163)
   MSIM_HD void abort_task(int t) {
@@ -935,29 +964,34 @@ MSIM_NOUNROLL
     b(L::B_ACC_LEN, k) = (u8)(al + 1);
     wake_waiter(w(L::W_ACC_WAITER, k));
     t_conn(t) = (u8)(2 * c);
+    if (C::USES_SPLIT) t_connhalf(t) = 3;
     return 0;
   }
-  /// Dropping a Sender + Receiver pair (one end of a connection)
+  /// Dropping the halves a future owns of one end of a connection (both, unless the Sender was moved away)
   MSIM_HD void conn_drop_end(int t) {
     int e = t_conn(t);
     if (e == NONE8) return;
     t_conn(t) = NONE8;
-    conn_drop(e);
+    conn_drop_half(e, C::USES_SPLIT ? t_connhalf(t) : 3);
   }
   /// Dropping only the Sender of the end a task holds (a request stream that ended: client.rs:171-196)
   MSIM_HD void conn_drop_tx(int t) {
-    int e = t_conn(t);  // direction 2*conn+side is the one this end sends on
-    ch_flags(e) &= ~CH_TX_ALIVE;
-    wake_waiter(w(L::W_CH_WAITER, e));
+    if (C::USES_SPLIT) t_connhalf(t) = t_connhalf(t) & ~1;
+    conn_drop_half(t_conn(t), 1);
   }
-  MSIM_HD void conn_drop(int e) {
-    int c = e >> 1, side = e & 1;
-    int d_tx = 2 * c + side, d_rx = 2 * c + (side ^ 1);
+  MSIM_HD void conn_drop(int e) { conn_drop_half(e, 3); }
+  /// halves: 1 = the Sender, 2 = the Receiver of end `e` (direction e is the one this end sends on)
+  MSIM_HD void conn_drop_half(int e, int halves) {
+    int c = e >> 1, d_tx = e, d_rx = e ^ 1;
     // `(tx, rx)` bindings drop in reverse order: the Receiver first, then the Sender
-    ch_flags(d_rx) &= ~CH_RX_ALIVE;  // UnboundedReceiver dropped: the peer's send fails, its closed() completes
-    if (C::USES_CLOSED) wake_waiter(w(L::W_CH_CLOSED_WAITER, d_rx));
-    ch_flags(d_tx) &= ~CH_TX_ALIVE;  // last UnboundedSender dropped: the peer's recv wakes and drains
-    wake_waiter(w(L::W_CH_WAITER, d_tx));
+    if (halves & 2) {
+      ch_flags(d_rx) &= ~CH_RX_ALIVE;  // UnboundedReceiver dropped: the peer's send fails, its closed() completes
+      if (C::USES_CLOSED) wake_waiter(w(L::W_CH_CLOSED_WAITER, d_rx));
+    }
+    if (halves & 1) {
+      ch_flags(d_tx) &= ~CH_TX_ALIVE;  // last UnboundedSender dropped: the peer's recv wakes and drains
+      wake_waiter(w(L::W_CH_WAITER, d_tx));
+    }
     if (!((ch_flags(d_tx) | ch_flags(d_rx)) & (CH_TX_ALIVE | CH_RX_ALIVE))) b(L::B_CONN_USED, c) = 0;
   }
   /// Sender::is_closed / the ready state of Sender::closed() (endpoint.rs:247-253): the peer dropped its Receiver
@@ -1164,12 +1198,12 @@ MSIM_NOUNROLL
       if (wt != W_NONE) {
         u8 st = wt & 0x0f;
         bool pend = false;
-        if (C::USES_CLOSED && st == W_SLEEP_CLOSED) {  // select_biased!: tx.closed() is polled before the Sleep
+        const bool sel_closed = C::USES_CLOSED && (wt & WF_CLOSED);
+        if (sel_closed) {  // select_biased!: tx.closed() is polled before the other branch
           int d = t_conn(t);
           if (!(ch_flags(d) & CH_RX_ALIVE)) {
-            w(L::W_CH_CLOSED_WAITER, d) = NONE32;
-            ret = -1;
-            wt = W_NONE;  // the select is over; the Sleep is dropped unpolled
+            ret = -2;
+            wt = W_NONE;  // the select is over; the other future is dropped where it stands
             st = 15;      // (no case below)
           } else {
             w(L::W_CH_CLOSED_WAITER, d) = ((u32)t << 20) | t_gen(t);
@@ -1247,6 +1281,7 @@ MSIM_NOUNROLL
                 for (u32 i = 1; i < al; i++) b(L::B_ACC, k * C::NACC + i - 1) = b(L::B_ACC, k * C::NACC + i);
                 b(L::B_ACC_LEN, k) = (u8)(al - 1);
                 t_conn(t) = (u8)(2 * c + 1);
+                if (C::USES_SPLIT) t_connhalf(t) = 3;
                 rfrom = w(L::W_CONN_SRC, c);
                 ret = 0;
                 wt = W_NONE;
@@ -1309,12 +1344,6 @@ MSIM_NOUNROLL
               }
               break;
             }
-            case W_SLEEP_CLOSED:  // the Sleep won: the closed() future drops with the select
-              if (!C::USES_CLOSED) break;
-              w(L::W_CH_CLOSED_WAITER, t_conn(t)) = NONE32;
-              ret = 0;
-              wt = W_NONE;
-              break;
             case W_CTRLC: {  // rx.changed(): ready once the version moved past the one seen at subscribe()
               if (!C::USES_CTRLC) break;
               int n = t_node(t);
@@ -1346,6 +1375,10 @@ MSIM_NOUNROLL
               break;
             }
           }
+        }
+        if (sel_closed && wt == W_NONE) {  // the select completed: its closed() future (and waker) is gone
+          w(L::W_CH_CLOSED_WAITER, t_conn(t)) = NONE32;
+          if (st == W_SLEEP) ret = 0;
         }
         t_wait(t) = wt;
         if (pend) {
@@ -1389,7 +1422,11 @@ MSIM_NOUNROLL
         case RQ_SLEEP_OR_CLOSED:
           if (!C::USES_CLOSED) break;
           t_dl0(t) = sleep_deadline(now + xa);
-          t_wait(t) = W_SLEEP_CLOSED | WF_SLEEP;
+          t_wait(t) = W_SLEEP | WF_SLEEP | WF_CLOSED;
+          break;
+        case RQ_CH_RECV_OR_CLOSED:
+          if (!C::USES_CLOSED) break;
+          t_wait(t) = W_CH_RECV | WF_CLOSED;
           break;
         case RQ_SLEEP_RAW:
           t_dl0(t) = xa;
@@ -1446,6 +1483,11 @@ MSIM_NOUNROLL
           if (C::NCONN && (ya & SPAWN_CONN)) {
             t_conn(c) = t_conn(t);
             t_conn(t) = NONE8;
+          }
+          if (C::USES_SPLIT && (ya & SPAWN_CONN_TX)) {  // the child takes the Sender, this future keeps the Receiver
+            t_conn(c) = t_conn(t);
+            t_connhalf(c) = 1;
+            t_connhalf(t) = 2;
           }
           break;
         }

@@ -1,7 +1,7 @@
 // MSIM_WL_TONIC — BASELINE config 5 / SURVEY §8(f) row 3: the tonic-example Greeter service under
 // madsim-tonic while a supervisor kills / restarts the client nodes
 // (tonic-example/tests/test.rs:155-202 client_crash, widened to six client nodes; unary calls and, with
-// flag 2, server-streaming lots_of_replies and client-streaming lots_of_greetings).
+// flag 2, server-streaming lots_of_replies, client-streaming lots_of_greetings and bidi bidi_hello).
 //
 //   Server::serve_with_shutdown    madsim-tonic/src/transport/server.rs:217-336
 //   Endpoint::connect / connect_ep madsim-tonic/src/transport/channel.rs:75-111  (fresh endpoint + handshake per call)
@@ -21,15 +21,16 @@ struct WL_Tonic {
   enum : int { S_HANDLED = 0, S_CNT, S_ROUND, S_C, S_END };  // wl_s scalars
   enum : int { F_REPLIES = 0, F_STARTS, F_NFIELD };           // wl_w per client node
   struct Caps {
-    static constexpr int NT = 24, TQ = 64, NMSG = 2, NSOCK = 24, NREG = 1, NMBOX = 1, NNODE = 8, NPARK = 1;
+    static constexpr int NT = 32, TQ = 64, NMSG = 2, NSOCK = 24, NREG = 1, NMBOX = 1, NNODE = 8, NPARK = 1;
     static constexpr int WQ = 0, WW = F_NFIELD, WS = S_END;
     static constexpr bool USES_JOIN = false;
     static constexpr bool USES_KILL = true;
     static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
     static constexpr bool USES_CLOSED = true;   // does any task await Sender::closed()?
+    static constexpr bool USES_SPLIT = true;    // does any task give the Sender half of its connection to another task?
     static constexpr int NCONN = 32, NCQ = 4, NACC = 32;  // a client-streaming call queues header + 3 items at a slow server
   };
-  enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_CLIENT2 };
+  enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_RSP_BIDI, K_SENDER };
   enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u };
   enum : u32 { ST_OK = 0, ST_INVALID_ARGUMENT = 1, ST_EOF = 2, ST_TRAILER = 3 };
   enum : u32 { SERVER_STREAMING = 1u << 31, CLIENT_STREAMING = 1u << 30, FLAG_RESTART_ONLY = 1, FLAG_STREAMING_MIX = 2 };
@@ -49,21 +50,21 @@ struct WL_Tonic {
     using L = typename E::L;
     const Params& P = *e.P;
     const u32 n_clients = P.n_nodes - 1;
-    for (;;) switch (e.t_kind(t) * 16 + e.t_pc(t)) {
+    for (;;) switch (e.t_kind(t) * 32 + e.t_pc(t)) {
         // ---- wl_tonic_main ----
-        case K_MAIN * 16 + 0:
+        case K_MAIN * 32 + 0:
           e.t_pc(t) = 1;
           e.ya = NODE_IP;
           return RQ_CREATE_NODE;
-        case K_MAIN * 16 + 1:  // node0.spawn(tonic_serve)
+        case K_MAIN * 32 + 1:  // node0.spawn(tonic_serve)
           e.t_pc(t) = 2;
           e.ya = K_SERVE, e.yb = 1, e.yc = e.yd = 0, e.xa = e.xb = 0;
           return RQ_SPAWN;
-        case K_MAIN * 16 + 2:
+        case K_MAIN * 32 + 2:
           e.t_pc(t) = 3;
           e.xa = NS_PER_SEC;
           return RQ_SLEEP_FOR;
-        case K_MAIN * 16 + 3:  // client nodes: create_node().ip().init(tonic_client).build()
+        case K_MAIN * 32 + 3:  // client nodes: create_node().ip().init(tonic_client).build()
           if (e.wl_s(S_CNT) < n_clients) {
             e.wl_s(S_CNT)++;
             e.ya = NODE_IP | NODE_INIT;
@@ -71,7 +72,7 @@ struct WL_Tonic {
           }
           e.t_pc(t) = 4;
           // fallthrough
-        case K_MAIN * 16 + 4:  // for i in 0..rounds { sleep(gen_range(0 s..5 s))
+        case K_MAIN * 32 + 4:  // for i in 0..rounds { sleep(gen_range(0 s..5 s))
           if ((u64)e.wl_s(S_ROUND) >= P.p[0]) {
             e.t_pc(t) = 8;
             e.xa = NS_PER_SEC;
@@ -80,16 +81,16 @@ struct WL_Tonic {
           e.t_pc(t) = 5;
           e.xa = e.sample_inclusive_u64(0, 5 * NS_PER_SEC - 1);  // UniformDuration Medium
           return RQ_SLEEP_FOR;
-        case K_MAIN * 16 + 5:  // c = gen_range(0..n_clients)
+        case K_MAIN * 32 + 5:  // c = gen_range(0..n_clients)
           e.t_pc(t) = 6;
           e.xa = 0, e.xb = n_clients;
           return RQ_GEN_RANGE;
-        case K_MAIN * 16 + 6:  // k = gen_range(0..4)
+        case K_MAIN * 32 + 6:  // k = gen_range(0..4)
           e.wl_s(S_C) = (u32)e.ret64;
           e.t_pc(t) = 7;
           e.xa = 0, e.xb = 4;
           return RQ_GEN_RANGE;
-        case K_MAIN * 16 + 7: {
+        case K_MAIN * 32 + 7: {
           int id = 2 + (int)e.wl_s(S_C);
           if (e.ret64 == 3 && !(P.p[2] & FLAG_RESTART_ONLY))
             e.kill(id);
@@ -99,7 +100,7 @@ struct WL_Tonic {
           e.t_pc(t) = 4;
           continue;
         }
-        case K_MAIN * 16 + 8: {
+        case K_MAIN * 32 + 8: {
           u32 replies = 0, starts = 0;
           for (u32 c = 0; c < n_clients; c++) replies += e.wl_w(F_REPLIES, 2 + c), starts += e.wl_w(F_STARTS, 2 + c);
           if (e.wl_s(S_HANDLED) < replies) return panic(e, 74);
@@ -111,34 +112,37 @@ struct WL_Tonic {
         }
 
         // ---- tonic_serve ----
-        case K_SERVE * 16 + 0:
+        case K_SERVE * 32 + 0:
           e.t_pc(t) = 1;
           e.ya = SERVER_ADDR;
           return RQ_BIND;
-        case K_SERVE * 16 + 1:
+        case K_SERVE * 32 + 1:
           if (e.ret < 0) return panic(e, 0);
           e.t_pc(t) = 2;
           // fallthrough
-        case K_SERVE * 16 + 2:
+        case K_SERVE * 32 + 2:
           e.t_pc(t) = 3;
           return RQ_ACCEPT1;
-        case K_SERVE * 16 + 3:  // the connection's first message, awaited inline
+        case K_SERVE * 32 + 3:  // the connection's first message, awaited inline
           if (e.ret < 0) return panic(e, 0);
           e.t_b(t) = e.rfrom;
           e.t_pc(t) = 4;
           return RQ_CH_RECV;
-        case K_SERVE * 16 + 4:
+        case K_SERVE * 32 + 4:
           if (e.ret < 0) {  // Err(_) => continue: a handshake (or a killed client); tx, rx drop
             e.conn_drop_end(t);
             e.t_pc(t) = 2;
             continue;
           }
           e.t_pc(t) = 2;  // spawn the response task with tx (and the request)
-          e.ya = ((e.rv1 & CLIENT_STREAMING) ? (u32)K_RSP_CSTREAM : (e.rv1 & SERVER_STREAMING) ? (u32)K_RSP_STREAM : (u32)K_RSP) | SPAWN_CONN, e.yb = e.t_node(t), e.yc = e.rv0, e.yd = e.t_b(t), e.xa = e.rv1, e.xb = 0;
+          e.ya = (((e.rv1 & CLIENT_STREAMING) && (e.rv1 & SERVER_STREAMING)) ? (u32)K_RSP_BIDI
+                  : (e.rv1 & CLIENT_STREAMING) ? (u32)K_RSP_CSTREAM
+                  : (e.rv1 & SERVER_STREAMING) ? (u32)K_RSP_STREAM
+                                               : (u32)K_RSP) | SPAWN_CONN, e.yb = e.t_node(t), e.yc = e.rv0, e.yd = e.t_b(t), e.xa = e.rv1, e.xb = 0;
           return RQ_SPAWN;
 
         // ---- tonic_response_task ----
-        case K_RSP * 16 + 0:
+        case K_RSP * 32 + 0:
           e.wl_s(S_HANDLED)++;
           e.t_pc(t) = 1;
           if (e.t_a(t) == ERROR_NAME) {
@@ -148,32 +152,32 @@ struct WL_Tonic {
           if (e.conn_tx_closed(t)) return RQ_READY;  // select_biased!{ tx.closed() => return, .. }
           e.yb = ST_OK, e.yc = reply_for(e.t_a(t), e.t_b(t));
           return RQ_CH_SEND;
-        case K_RSP * 16 + 1:
+        case K_RSP * 32 + 1:
           return RQ_READY;
 
         // ---- tonic_stream_response_task: header, lots_of_replies' items, trailer (server.rs:274-313) ----
-        case K_RSP_STREAM * 16 + 0:
+        case K_RSP_STREAM * 32 + 0:
           e.wl_s(S_HANDLED)++;
           e.t_c(t) = 0;  // i
           e.t_pc(t) = 1;
           e.yb = ST_OK, e.yc = 0;
           return RQ_CH_SEND;
-        case K_RSP_STREAM * 16 + 1:  // tx.send(header).await?
+        case K_RSP_STREAM * 32 + 1:  // tx.send(header).await?
           if (e.ret < 0) return RQ_READY;
           e.t_pc(t) = 2;
           // fallthrough
-        case K_RSP_STREAM * 16 + 2:  // select_biased!{ closed => return, stream.next() => reply i }
+        case K_RSP_STREAM * 32 + 2:  // select_biased!{ closed => return, stream.next() => reply i }
           if (e.conn_tx_closed(t)) return RQ_READY;
           e.t_pc(t) = 3;
           e.yb = ST_OK, e.yc = reply_for(e.t_a(t), e.t_b(t)) + e.t_c(t);
           return RQ_CH_SEND;
-        case K_RSP_STREAM * 16 + 3:  // the next select finds the generator in `sleep(1 s)`
+        case K_RSP_STREAM * 32 + 3:  // the next select finds the generator in `sleep(1 s)`
           if (e.ret < 0) return RQ_READY;
           if (e.conn_tx_closed(t)) return RQ_READY;
           e.t_pc(t) = 4;
           e.xa = NS_PER_SEC;
           return RQ_SLEEP_OR_CLOSED;
-        case K_RSP_STREAM * 16 + 4:
+        case K_RSP_STREAM * 32 + 4:
           if (e.ret < 0) return RQ_READY;  // the client dropped the response stream
           e.t_c(t)++;
           if (e.t_c(t) < 3) {
@@ -183,22 +187,22 @@ struct WL_Tonic {
           e.t_pc(t) = 5;  // Err(Status::unknown("EOF"))?: the stream's last item
           e.yb = ST_EOF, e.yc = 0;
           return RQ_CH_SEND;
-        case K_RSP_STREAM * 16 + 5:  // stream.next() == None: break; the trailer
+        case K_RSP_STREAM * 32 + 5:  // stream.next() == None: break; the trailer
           if (e.ret < 0) return RQ_READY;
           if (e.conn_tx_closed(t)) return RQ_READY;
           e.t_pc(t) = 6;
           e.yb = ST_TRAILER, e.yc = 0;
           return RQ_CH_SEND;
-        case K_RSP_STREAM * 16 + 6:
+        case K_RSP_STREAM * 32 + 6:
           return RQ_READY;
 
         // ---- tonic_client_stream_response_task: lots_of_greetings reads the request stream to its end ----
-        case K_RSP_CSTREAM * 16 + 0:
+        case K_RSP_CSTREAM * 32 + 0:
           e.wl_s(S_HANDLED)++;
           e.t_c(t) = 0;  // fold of the names
           e.t_pc(t) = 1;
           return RQ_CH_RECV;
-        case K_RSP_CSTREAM * 16 + 1:
+        case K_RSP_CSTREAM * 32 + 1:
           if (e.ret >= 0) {  // while let Some(request) = stream.message().await?
             e.t_c(t) = e.t_c(t) * 33u + e.rv0;
             return RQ_CH_RECV;
@@ -207,50 +211,107 @@ struct WL_Tonic {
           e.t_pc(t) = 2;
           e.yb = ST_OK, e.yc = reply_for(e.t_c(t), e.t_b(t));
           return RQ_CH_SEND;
-        case K_RSP_CSTREAM * 16 + 2:
+        case K_RSP_CSTREAM * 32 + 2:
           return RQ_READY;
 
+        // ---- tonic_bidi_response_task: bidi_hello answers every request until the request stream ends ----
+        case K_RSP_BIDI * 32 + 0:
+          e.wl_s(S_HANDLED)++;
+          e.t_pc(t) = 1;
+          e.yb = ST_OK, e.yc = 0;
+          return RQ_CH_SEND;
+        case K_RSP_BIDI * 32 + 1:
+          if (e.ret < 0) return RQ_READY;
+          e.t_pc(t) = 2;
+          // fallthrough
+        case K_RSP_BIDI * 32 + 2:  // select_biased!{ tx.closed() => return, stream.next() => .. } parked in rx.recv()
+          e.t_pc(t) = 3;
+          return RQ_CH_RECV_OR_CLOSED;
+        case K_RSP_BIDI * 32 + 3:
+          if (e.ret == -2) return RQ_READY;
+          if (e.ret < 0) {  // the request stream ended: None => break; the trailer
+            e.t_pc(t) = 5;
+            e.yb = ST_TRAILER, e.yc = 0;
+            return RQ_CH_SEND;
+          }
+          e.t_pc(t) = 4;
+          e.yb = ST_OK, e.yc = reply_for(e.rv0, e.t_b(t));
+          return RQ_CH_SEND;
+        case K_RSP_BIDI * 32 + 4:
+          if (e.ret < 0) return RQ_READY;
+          e.t_pc(t) = 2;
+          continue;
+        case K_RSP_BIDI * 32 + 5:
+          return RQ_READY;
+
+        // ---- tonic_bidi_sender: the background task that owns the Sender (client.rs:152-155) ----
+        case K_SENDER * 32 + 0:
+          e.t_c(t) = 0;
+          e.t_pc(t) = 1;
+          e.yb = 0, e.yc = e.t_a(t) | CLIENT_STREAMING | SERVER_STREAMING;
+          return RQ_CH_SEND;
+        case K_SENDER * 32 + 1:
+          if (e.ret < 0) return RQ_READY;
+          e.t_pc(t) = 2;
+          // fallthrough
+        case K_SENDER * 32 + 2:
+          if (e.t_c(t) >= 3) return RQ_READY;  // the Sender drops with the future
+          e.t_pc(t) = 3;
+          e.yb = NAME + e.t_c(t), e.yc = 0;
+          return RQ_CH_SEND;
+        case K_SENDER * 32 + 3:
+          if (e.ret < 0) return RQ_READY;
+          e.t_c(t)++;
+          e.t_pc(t) = 2;
+          e.xa = NS_PER_SEC;
+          return RQ_SLEEP_FOR;
+
         // ---- tonic_client: the client node's init task ----
-        case K_CLIENT * 16 + 0:  // GreeterClient::connect: connect_ep, then drop it
+        case K_CLIENT * 32 + 0:  // GreeterClient::connect: connect_ep, then drop it
           e.wl_w(F_STARTS, e.t_node(t))++;
           e.t_pc(t) = 1;
           e.ya = mk_addr(IPK_UNSPEC, 0, 0);
           return RQ_BIND;
-        case K_CLIENT * 16 + 1:
+        case K_CLIENT * 32 + 1:
           if (e.ret < 0) return panic(e, 70);
           e.t_pc(t) = 2;
           e.ya = SERVER_ADDR;
           return RQ_CONNECT1;
-        case K_CLIENT * 16 + 2:
+        case K_CLIENT * 32 + 2:
           if (e.ret < 0) return panic(e, 70);
           e.conn_drop_end(t);
           e.sock_unref(t);
           e.t_b(t) = 0;  // seq
           e.t_pc(t) = 3;
           // fallthrough
-        case K_CLIENT * 16 + 3:  // loop { name = gen_range(0..10) == 0 ? "error" : "Tonic"
+        case K_CLIENT * 32 + 3:  // loop { name = gen_range(0..10) == 0 ? "error" : "Tonic"
           e.t_pc(t) = 4;
           e.xa = 0, e.xb = 10;
           return RQ_GEN_RANGE;
-        case K_CLIENT * 16 + 4:  // Grpc::unary / server_streaming -> connect_ep: Endpoint::connect
+        case K_CLIENT * 32 + 4:  // Grpc::unary / server_streaming -> connect_ep: Endpoint::connect
           e.t_a(t) = e.ret64 == 0 ? (u32)ERROR_NAME : (u32)NAME;
-          e.t_c(t) = ((P.p[2] & FLAG_STREAMING_MIX) && e.ret64 >= 1 && e.ret64 <= 4) ? (u32)e.ret64 : 0u;  // 1..3: lots_of_replies, 4: lots_of_greetings
+          e.t_c(t) = ((P.p[2] & FLAG_STREAMING_MIX) && e.ret64 >= 1 && e.ret64 <= 6) ? (u32)e.ret64 : 0u;  // 1..3: lots_of_replies, 4: lots_of_greetings, 5..6: bidi_hello
           e.t_pc(t) = 5;
           e.ya = mk_addr(IPK_UNSPEC, 0, 0);
           return RQ_BIND;
-        case K_CLIENT * 16 + 5:  // the handshake connection
+        case K_CLIENT * 32 + 5:  // the handshake connection
           if (e.ret < 0) return panic(e, 71);
           e.t_pc(t) = 6;
           e.ya = SERVER_ADDR;
           return RQ_CONNECT1;
-        case K_CLIENT * 16 + 6:  // the request's connection
+        case K_CLIENT * 32 + 6:  // the request's connection
           if (e.ret < 0) return panic(e, 71);
           e.conn_drop_end(t);
           e.t_pc(t) = 7;
           e.ya = SERVER_ADDR;
           return RQ_CONNECT1;
-        case K_CLIENT * 16 + 7:
+        case K_CLIENT * 32 + 7:
           if (e.ret < 0) return panic(e, 71);
+          if (e.t_c(t) >= 5) {  // bidi: spawn the task that sends the requests; it takes the Sender
+            e.t_pc(t) = 15;
+            e.ya = K_SENDER | SPAWN_CONN_TX | SPAWN_JOINABLE, e.yb = e.t_node(t), e.yc = e.t_b(t), e.yd = 0, e.xa = e.xb = 0;
+            return RQ_SPAWN;
+          }
           if (e.t_c(t) == 4) {  // client streaming: the stream-start header, then hello_stream's items
             e.t_c(t) = 32;      // 32 + items sent
             e.t_a(t) = 0;       // fold of the names sent
@@ -261,11 +322,11 @@ struct WL_Tonic {
           e.t_pc(t) = 8;
           e.yb = e.t_a(t), e.yc = e.t_b(t) | (e.t_c(t) ? (u32)SERVER_STREAMING : 0u);
           return RQ_CH_SEND;
-        case K_CLIENT * 16 + 8:
+        case K_CLIENT * 32 + 8:
           if (e.ret < 0) return panic(e, 71);
           e.t_pc(t) = 9;
           return RQ_CH_RECV;
-        case K_CLIENT * 16 + 9: {
+        case K_CLIENT * 32 + 9: {
           if (e.ret < 0) return panic(e, 71);
           u32 node = e.t_node(t);
           u32 st = e.rv0, reply = e.rv1;
@@ -297,7 +358,7 @@ struct WL_Tonic {
           e.xa = P.p[1];
           return RQ_SLEEP_FOR;
         }
-        case K_CLIENT * 16 + 10: {  // Streaming::message(): three replies, then the EOF status
+        case K_CLIENT * 32 + 10: {  // Streaming::message(): three replies, then the EOF status
           if (e.ret < 0) return panic(e, 71);
           u32 node = e.t_node(t), i = e.t_c(t) - 16;
           if (i < 3) {
@@ -314,10 +375,10 @@ struct WL_Tonic {
           e.xa = P.p[1];
           return RQ_SLEEP_FOR;
         }
-        case K_CLIENT * 16 + 11:  // header sent (tx.send(..).await?), then: yield item i; sleep(1 s)
+        case K_CLIENT * 32 + 11:  // header sent (tx.send(..).await?), then: yield item i; sleep(1 s)
           if (e.ret < 0) return panic(e, 71);
           // fallthrough
-        case K_CLIENT * 16 + 12: {
+        case K_CLIENT * 32 + 12: {
           u32 i = e.t_c(t) - 32;
           if (i >= 3) {  // the request stream ended: send_request_stream returns, its Sender drops
             e.conn_drop_tx(t);
@@ -329,7 +390,7 @@ struct WL_Tonic {
           e.yb = NAME + i, e.yc = 0;
           return RQ_CH_SEND;
         }
-        case K_CLIENT * 16 + 13:
+        case K_CLIENT * 32 + 13:
           if (e.ret < 0) {  // the server closed the stream prematurely: stop sending
             e.t_c(t) = 35;
             e.t_pc(t) = 12;
@@ -339,10 +400,45 @@ struct WL_Tonic {
           e.t_pc(t) = 12;
           e.xa = NS_PER_SEC;
           return RQ_SLEEP_FOR;
-        case K_CLIENT * 16 + 14: {
+        case K_CLIENT * 32 + 14: {
           if (e.ret < 0) return panic(e, 71);
           u32 node = e.t_node(t);
           if (e.rv0 != ST_OK || e.rv1 != e.t_a(t) * 31u + node) return panic(e, 78);
+          e.conn_drop_end(t);
+          e.sock_unref(t);
+          e.wl_w(F_REPLIES, node)++;
+          e.t_b(t)++;
+          e.t_pc(t) = 3;
+          e.xa = P.p[1];
+          return RQ_SLEEP_FOR;
+        }
+        case K_CLIENT * 32 + 15:  // a plain JoinHandle until the response stream is first polled
+          e.t_handle(t) = (u8)((u32)e.ret | 0x80u);
+          e.t_a(t) = e.t_c(t);  // 5, or 6 = drop the stream after the first reply
+          e.t_c(t) = 0;         // replies read
+          e.t_pc(t) = 16;
+          return RQ_CH_RECV;
+        case K_CLIENT * 32 + 16:  // the header: Result<Response<()>>
+          if (e.ret < 0) return panic(e, 71);
+          if (e.rv0 != ST_OK) return panic(e, 75);
+          e.t_handle(t) = e.t_handle(t) & 0x7f;  // first poll of the response stream: `_task = task.cancel_on_drop()`
+          e.t_pc(t) = 17;
+          return RQ_CH_RECV;
+        case K_CLIENT * 32 + 17: {  // while let Some(reply) = stream.message().await.unwrap()
+          if (e.ret < 0) return panic(e, 71);
+          u32 node = e.t_node(t);
+          bool done = false;
+          if (e.rv0 == ST_TRAILER) {
+            if (e.t_c(t) != 3) return panic(e, 79);
+            done = true;
+          } else {
+            if (e.rv0 != ST_OK || e.rv1 != (NAME + e.t_c(t)) * 31u + node) return panic(e, 79);
+            e.t_c(t)++;
+            if (e.t_a(t) == 6) done = true;  // drop the response stream after the first reply
+          }
+          if (!done) return RQ_CH_RECV;
+          e.task_cancel_detach(e.t_handle(t));  // `_task` drops (a no-op on a finished task) before the Receiver
+          e.t_handle(t) = NONE8;
           e.conn_drop_end(t);
           e.sock_unref(t);
           e.wl_w(F_REPLIES, node)++;

@@ -460,6 +460,16 @@ static Async<Unit> tonic_server_stream_client(SocketAddr server, std::shared_ptr
   r = co_await tonic_client_streaming(server, 0, SocketAddr{ip4(10, 0, 0, 2), 0});
   CHECK(r.is_ok() && *r.ok == 3 && now() - t0 > 3 * SEC);
   CHECK(st->handled == 3);
+  // bi-directional stream (tests/test.rs:96-107): "Hello Tonic{i}! (10.0.0.2)" x3, then the trailer
+  t0 = now();
+  r = co_await tonic_bidi(server, 0, SocketAddr{ip4(10, 0, 0, 2), 0}, false);
+  CHECK(r.is_ok() && *r.ok == 3 && now() - t0 > 3 * SEC);
+  // dropping the response stream after one reply cancels the background sender (codec.rs:29, cancel_on_drop)
+  t0 = now();
+  r = co_await tonic_bidi(server, 1, SocketAddr{ip4(10, 0, 0, 2), 0}, true);
+  CHECK(r.is_ok() && *r.ok == 1 && now() - t0 < 1 * SEC);
+  co_await sleep(5 * SEC);
+  CHECK(st->handled == 5);
   co_return {};
 }
 
@@ -657,7 +667,7 @@ int main() {
     CHECK(st->handled == 2);
     rt.teardown();
   });
-  run_case("tonic::basic server stream, client stream + client_drops_response_stream (tests/test.rs:72-94,204-230)", [] {
+  run_case("tonic::basic server / client / bidi streams + client_drops_response_stream (tests/test.rs:72-107,204-230)", [] {
     Runtime rt;
     SocketAddr a{ip4(10, 0, 0, 1), 50051};
     auto server = rt.create_node().ip(a.ip).build();

@@ -3,7 +3,7 @@
 // MSIM_WL_TONIC — BASELINE config 5 / SURVEY §8(f) row 3: the tonic-example Greeter service under
 // madsim-tonic with a kill/restart chaos schedule (tonic-example/tests/test.rs:155-202
 // client_crash, widened from one client node to six; unary calls and, with flag 2, server- and
-// client-streaming calls).
+// client-streaming and bidi calls).
 //
 //   Server::serve_with_shutdown   madsim-tonic/src/transport/server.rs:217-336
 //       bind; loop { accept1; first message INLINE (Err = handshake: continue); spawn the
@@ -109,13 +109,51 @@ inline Async<Unit> tonic_client_stream_response_task(Connection conn, std::share
   (void)conn.tx.send(rsp);
   co_return {};
 }
+/// select_biased!{ _ = tx.closed() => Closed, item = stream.next() => .. } where the response stream is
+/// parked in the REQUEST stream's rx.recv() (bidi_hello, lib.rs:106-124)
+struct ClosedOrRecv {
+  UnboundedSender<std::pair<Payload, LinkState>>::ClosedFut closed;
+  Async<Result<Payload>> recv;
+  Poll<int> poll(Context& cx) {  // 2 = the client closed, 1 = a request (in *out), 0 = the request stream ended
+    if (closed.poll(cx).ready()) return Poll<int>::done(2);
+    auto r = recv.poll(cx);
+    if (!r.ready()) return Poll<int>::pending();
+    if (r.v->is_err()) return Poll<int>::done(0);
+    *out = *r.v->ok;
+    return Poll<int>::done(1);
+  }
+  Payload* out;
+};
+/// the response task of a bidi call: header, one reply per request, trailer when the request stream ends
+inline Async<Unit> tonic_bidi_response_task(Connection conn, std::shared_ptr<TonicStats> st) {
+  st->handled++;
+  Payload header;
+  header.v[0] = TONIC_OK;
+  if (conn.tx.send(header).is_err()) co_return {};
+  for (;;) {
+    Payload req;
+    int k = co_await ClosedOrRecv{conn.tx.closed(), conn.rx.recv(), &req};
+    if (k == 2) co_return {};
+    if (k == 0) break;
+    Payload item;
+    item.v[0] = TONIC_OK;
+    item.v[1] = tonic_reply_for(req.v[0], conn.peer);
+    if (conn.tx.send(item).is_err()) co_return {};
+  }
+  Payload trailer;
+  trailer.v[0] = TONIC_TRAILER;
+  (void)conn.tx.send(trailer);
+  co_return {};
+}
 inline Async<Unit> tonic_serve(SocketAddr addr, std::shared_ptr<TonicStats> st) {
   Endpoint ep = std::move((co_await Endpoint::bind(addr)).unwrap());
   for (;;) {
     Connection conn = std::move((co_await ep.accept1()).unwrap());
     auto msg = co_await conn.rx.recv();
     if (msg.is_err()) continue;  // maybe handshake or error
-    if (msg.ok->v[1] & TONIC_CLIENT_STREAMING)
+    if ((msg.ok->v[1] & TONIC_CLIENT_STREAMING) && (msg.ok->v[1] & TONIC_SERVER_STREAMING))
+      spawn(tonic_bidi_response_task(std::move(conn), st));
+    else if (msg.ok->v[1] & TONIC_CLIENT_STREAMING)
       spawn(tonic_client_stream_response_task(std::move(conn), st));
     else if (msg.ok->v[1] & TONIC_SERVER_STREAMING)
       spawn(tonic_stream_response_task(std::move(conn), *msg.ok, st));
@@ -205,6 +243,63 @@ inline Async<Result<u32>> tonic_client_streaming(SocketAddr server, u32 seq, Soc
   co_return R::Ok(3);
 }
 
+/// Grpc::streaming (client.rs:139-166): the requests go out from a BACKGROUND task that owns the Sender;
+/// Streaming::new(rx, Some(task)) (codec.rs:19-47) cancels that task when the response stream is dropped
+/// after its first poll (`let _task = task.cancel_on_drop()` is the generator's first statement).
+inline Async<Unit> tonic_bidi_sender(ConnSender tx, u32 seq) {
+  Payload header;
+  header.v[1] = seq | TONIC_CLIENT_STREAMING | TONIC_SERVER_STREAMING;
+  if (tx.send(header).is_err()) co_return {};
+  for (u32 i = 0; i < 3; i++) {  // hello_stream (tests/test.rs:119-129)
+    Payload item;
+    item.v[0] = TONIC_NAME + i;
+    if (tx.send(item).is_err()) break;
+    co_await sleep(1 * SEC);
+  }
+  co_return {};
+}
+struct TonicBidiStream {
+  ConnReceiver rx;  // destroyed AFTER the body below ran: `_task` drops before the captured Receiver
+  std::optional<JoinHandle<Unit>> task;
+  bool armed = false;
+  TonicBidiStream(ConnReceiver r, JoinHandle<Unit> t) : rx(std::move(r)), task(std::move(t)) {}
+  TonicBidiStream(const TonicBidiStream&) = delete;
+  void end_of_stream() {  // the generator returns: `_task` drops (cancel is a no-op on a finished task)
+    if (armed && task) task->task->cancel();
+    task.reset();
+  }
+  ~TonicBidiStream() { end_of_stream(); }
+};
+inline Async<Result<u32>> tonic_bidi(SocketAddr server, u32 seq, SocketAddr me, bool drop_after_first) {
+  using R = Result<u32>;
+  auto ep = co_await tonic_connect_ep(server);
+  if (ep.is_err()) co_return R::Error(Err::ConnectionRefused);
+  auto c = co_await ep.ok->connect1(server);
+  if (c.is_err()) co_return R::Error(c.err);
+  Connection conn = std::move(*c.ok);
+  ep.ok.reset();
+  auto task = spawn(tonic_bidi_sender(std::move(conn.tx), seq));
+  auto header = co_await conn.rx.recv();
+  if (header.is_err()) co_return R::Error(header.err);
+  if (header.ok->v[0] != TONIC_OK) panic("bad bidi header", 75);
+  TonicBidiStream stream(std::move(conn.rx), std::move(task));
+  u32 i = 0;
+  for (;;) {  // while let Some(reply) = stream.message().await.unwrap()
+    stream.armed = true;
+    auto m = co_await stream.rx.recv();
+    if (m.is_err()) co_return R::Error(m.err);
+    if (m.ok->v[0] == TONIC_TRAILER) {
+      stream.end_of_stream();
+      break;
+    }
+    if (m.ok->v[0] != TONIC_OK || m.ok->v[1] != tonic_reply_for(TONIC_NAME + i, me)) panic("unexpected bidi reply", 79);
+    i++;
+    if (drop_after_first) co_return R::Ok(1);  // the stream drops here: cancel the sender, then close the Receiver
+  }
+  if (i != 3) panic("bidi stream ended early", 79);
+  co_return R::Ok(3);
+}
+
 /// the client node's init task (tests/test.rs:176-194, unary part)
 inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::shared_ptr<TonicStats> st) {
   st->starts[c]++;
@@ -222,6 +317,13 @@ inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::sh
     if ((p.flags & TONIC_STREAMING_MIX) && pick >= 1 && pick <= 3) {  // lots_of_replies; pick 3 drops the stream at once
       auto sr = co_await tonic_server_streaming(server, q, pick == 3, tonic_reply_for(TONIC_NAME, me));
       if (sr.is_err()) panic("lots_of_replies failed", 71);
+      st->replies[c]++;
+      co_await sleep(p.think_ns);
+      continue;
+    }
+    if ((p.flags & TONIC_STREAMING_MIX) && (pick == 5 || pick == 6)) {  // bidi_hello; pick 6 drops the stream after one reply
+      auto sr = co_await tonic_bidi(server, seq, me, pick == 6);
+      if (sr.is_err()) panic("bidi_hello failed", 71);
       st->replies[c]++;
       co_await sleep(p.think_ns);
       continue;

@@ -119,7 +119,8 @@ typedef struct msim_config {
  *  ETCD     n_nodes = 1 server + (n_nodes-1) clients (default 3); p0 = operations per client (default 32, clients x p0 <= 128),
  *           p1 = think time ns (default 50 ms), p2 = SimServer::timeout_rate as IEEE f32 bits (default 0),
  *           p3 = bug bits (1 = server read cache that delete does not invalidate,
- *           2 = clients also delete the leased key: reaches the crate's own expect("no lease")), p4 = lease ttl s (default 1)
+ *           2 = clients also delete the leased key: reaches the crate's own expect("no lease")), p4 = lease ttl s (default 1),
+ *           p7 = 1: the clients also use the rest of LeaseClient (revoke, keep_alive, time_to_live, leases)
  *  TONIC    n_nodes = 1 server + (n_nodes-1) client nodes (default 7); p0 = chaos rounds (default 10),
  *           p1 = think time ns between unary calls (default 100 ms), p2 = flags (1 = restart only, never kill;
  *           2 = clients also make server-streaming calls, sometimes dropping the response stream at once,

@@ -99,13 +99,14 @@ struct Workload {
     return w;
   }
   /// madsim-etcd-client SimServer (timeout_rate: server.rs:21-25) + KV clients + linearizability check
-  static Workload etcd(uint32_t clients = 2, uint64_t ops = 32, float timeout_rate = 0.0f, uint32_t bug = 0) {
+  static Workload etcd(uint32_t clients = 2, uint64_t ops = 32, float timeout_rate = 0.0f, uint32_t bug = 0,
+                       bool lease_admin = false) {
     Workload w;
     check(msim_workload_default(MSIM_WL_ETCD, &w.desc));
     uint32_t bits;
     static_assert(sizeof(bits) == sizeof(timeout_rate), "f32");
     std::memcpy(&bits, &timeout_rate, 4);
-    w.desc.n_nodes = clients + 1, w.desc.p[0] = ops, w.desc.p[2] = bits, w.desc.p[3] = bug;
+    w.desc.n_nodes = clients + 1, w.desc.p[0] = ops, w.desc.p[2] = bits, w.desc.p[3] = bug, w.desc.p[7] = lease_admin ? 1 : 0;
     return w;
   }
   /// time::interval + MissedTickBehavior (0 Burst, 1 Delay, 2 Skip), signal::ctrl_c, Handle::send_ctrl_c

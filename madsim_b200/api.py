@@ -105,14 +105,14 @@ class Workload:
 
     @staticmethod
     def etcd(clients: int = 2, ops: int = 32, think_ns: int = 50 * MS, timeout_rate: float = 0.0, bug: int = 0,
-             lease_ttl_s: int = 1) -> "Workload":
+             lease_ttl_s: int = 1, lease_admin: bool = False) -> "Workload":
         """madsim-etcd-client SimServer + `clients` KV clients (one connection per request) with a
         linearizability check of the history (BASELINE config 4); `timeout_rate` is
         SimServer::timeout_rate (an f32 in the reference: passed as its bit pattern)."""
         import struct
 
         bits = struct.unpack("<I", struct.pack("<f", timeout_rate))[0]
-        return Workload(N.WL_ETCD, clients + 1, [ops, think_ns, bits, bug, lease_ttl_s, 0, 0, 0])
+        return Workload(N.WL_ETCD, clients + 1, [ops, think_ns, bits, bug, lease_ttl_s, 0, 0, int(lease_admin)])
 
     @staticmethod
     def tonic(clients: int = 6, rounds: int = 10, think_ns: int = 100 * MS, restart_only: bool = False,

@@ -156,13 +156,13 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
       float rate;
       u32 bits = (u32)wl.p[2];
       std::memcpy(&rate, &bits, 4);
-      if (P.n_nodes < 2 || P.n_nodes > 4 || wl.p[0] * (P.n_nodes - 1) > 128 || wl.p[3] > 3 || wl.p[4] > 0xffff ||
+      if (P.n_nodes < 2 || P.n_nodes > 4 || wl.p[0] * (P.n_nodes - 1) > 128 || wl.p[3] > 3 || wl.p[4] > 0xffff || wl.p[7] > 1 ||
           !(rate >= 0.0f && rate <= 1.0f)) {
         if (err) *err = "etcd: need 1..3 clients, clients x ops <= 128, bug bits <= 3, 0 <= timeout_rate <= 1";
         return MSIM_EINVAL;
       }
       // Bernoulli::new(timeout_rate as f64) (service.rs:166)
-      P.p[5] = rate == 1.0f ? 1 : 0;
+      P.p[5] = rate == 1.0f ? 1 : 0;  // (p[7], the lease-admin switch, passes through)
       P.p[6] = rate == 1.0f ? 0 : (u64)((double)rate * 18446744073709551616.0);
       break;
     }

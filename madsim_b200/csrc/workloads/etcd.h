@@ -5,7 +5,7 @@
 //   EtcdService::new        src/service.rs:20-39                     (1 s lease tick task)
 //   EtcdService::timeout    src/service.rs:165-176                   (gen_bool(rate), gen_range(5 s..15 s), sleep)
 //   ServiceInner            src/service.rs:282-492                   (put / get / delete / txn / lease_grant / tick)
-//   KvClient / LeaseClient  src/kv.rs:26-75, src/lease.rs            (connect1 -> send -> recv per call)
+//   KvClient / LeaseClient  src/kv.rs:26-75, src/lease.rs:30-88      (connect1 -> send -> recv per call; keep_alive: a ping / response loop)
 //
 // Oracle twin: oracle/workloads_etcd.hpp (same programs as coroutines on the reference's API, the
 // store in std::map; here the store is a fixed table in the seed's state block).  Keys are
@@ -18,14 +18,14 @@ namespace msim {
 struct WL_Etcd {
   static constexpr int NKEY = 5, LEASE_KEY = 4, LEASE_ID = 7, MAX_HIST = 128;
   enum : int {  // wl_s scalars
-    S_REV = 0, S_MAXREV, S_NOK, S_NERR, S_NHIST, S_CNT, S_LEASE_ON, S_LEASE_ID, S_LEASE_TTL, S_LEASE_KEYS,
-    S_KV = 10,             // [NKEY*2] value | lease<<16 | present<<31 ; create_rev | mod_rev<<16
+    S_REV = 0, S_MAXREV, S_NOK, S_NERR, S_NHIST, S_CNT, S_LEASE_ON, S_LEASE_ID, S_LEASE_TTL, S_LEASE_KEYS, S_LEASE_GRANTED,
+    S_KV = 11,             // [NKEY*2] value | lease<<16 | present<<31 ; create_rev | mod_rev<<16
     S_CACHE = S_KV + 2 * NKEY,  // [NKEY] bug mode read cache: value | mod_rev<<16 (0 = empty)
     S_JH = S_CACHE + NKEY,      // [3] the clients' JoinHandles (main)
     S_HIST = S_JH + 3,          // [MAX_HIST*3]
     S_END = S_HIST + 3 * MAX_HIST
   };
-  enum : int { F_I = 0, F_NEED_GRANT, F_SEEN01, F_SEEN23, F_SEEN4, F_REQ0, F_REQ1, F_FLOOR, F_NFIELD };  // wl_w per client node
+  enum : int { F_I = 0, F_NEED_GRANT, F_SEEN01, F_SEEN23, F_SEEN4, F_REQ0, F_REQ1, F_FLOOR, F_KA_PHASE, F_NFIELD };  // wl_w per client node
   struct Caps {
     static constexpr int NT = 16, TQ = 48, NMSG = 2, NSOCK = 4, NREG = 2, NMBOX = 2, NNODE = 5, NPARK = 1;
     static constexpr int WQ = 0, WW = F_NFIELD, WS = S_END;
@@ -37,7 +37,7 @@ struct WL_Etcd {
     static constexpr int NCONN = 6, NCQ = 2, NACC = 4;
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_TICK, K_REQ, K_CLIENT };
-  enum : u32 { OP_PUT = 1, OP_GET = 2, OP_DELETE = 3, OP_CAS = 4, OP_GRANT = 5 };
+  enum : u32 { OP_REVOKE = 0, OP_PUT = 1, OP_GET = 2, OP_DELETE = 3, OP_CAS = 4, OP_GRANT = 5, OP_LEASE_READ = 6, OP_KEEP_ALIVE = 7 };
   enum : u32 { ST_OK = 0, ST_TIMED_OUT = 1, ST_LEASE_NOT_FOUND = 2, ST_REFUSED = 3 };
   enum : u32 { BUG_STALE_READ = 1, BUG_LEASE_KEY_DELETE = 2 };
   static constexpr u32 MAIN_KIND = K_MAIN;
@@ -147,7 +147,61 @@ struct WL_Etcd {
       return r;
     }
     e.wl_s(S_LEASE_ON) = 1, e.wl_s(S_LEASE_ID) = id, e.wl_s(S_LEASE_TTL) = ttl, e.wl_s(S_LEASE_KEYS) = 0;
+    e.wl_s(S_LEASE_GRANTED) = ttl;
     r.revision = ++e.wl_s(S_REV);
+    return r;
+  }
+  /// lease_revoke (service.rs:423-435)
+  template <class E>
+  static MSIM_HD Rsp sv_lease_revoke(E& e, u32 id) {
+    Rsp r;
+    if (!lease_exists(e, id)) {
+      r.status = ST_LEASE_NOT_FOUND;
+      return r;
+    }
+    u32 keys = e.wl_s(S_LEASE_KEYS);
+    for (u32 k = 0; k < (u32)NKEY; k++) {
+      if (!(keys >> k & 1)) continue;
+      if (!(e.wl_s(S_KV + 2 * k) >> 31)) {
+        r.panic_code = 63;  // .expect("no key")
+        return r;
+      }
+      e.wl_s(S_KV + 2 * k) = 0;
+      e.wl_s(S_KV + 2 * k + 1) = 0;
+    }
+    e.wl_s(S_LEASE_ON) = 0;
+    r.revision = ++e.wl_s(S_REV);
+    return r;
+  }
+  /// lease_keep_alive (service.rs:437-448): ttl = granted_ttl, and the revision moves
+  template <class E>
+  static MSIM_HD Rsp sv_lease_keep_alive(E& e, u32 id) {
+    Rsp r;
+    if (!lease_exists(e, id)) {
+      r.status = ST_LEASE_NOT_FOUND;
+      return r;
+    }
+    e.wl_s(S_LEASE_TTL) = e.wl_s(S_LEASE_GRANTED);
+    r.revision = ++e.wl_s(S_REV);
+    r.value = e.wl_s(S_LEASE_GRANTED);
+    return r;
+  }
+  /// lease_time_to_live (what = 0) / lease_leases (what = 1) (service.rs:450-470)
+  template <class E>
+  static MSIM_HD Rsp sv_lease_read(E& e, u32 what, u32 id) {
+    Rsp r;
+    r.revision = e.wl_s(S_REV);
+    if (what == 1) {
+      r.value = e.wl_s(S_LEASE_ON) ? 1 : 0;
+      return r;
+    }
+    if (!lease_exists(e, id)) {
+      r.status = ST_LEASE_NOT_FOUND;
+      r.revision = 0;
+      return r;
+    }
+    r.value = e.wl_s(S_LEASE_TTL) & 0xffff;
+    r.flag = 1;
     return r;
   }
   /// tick (service.rs:472-492).  0 or a panic code
@@ -187,6 +241,7 @@ struct WL_Etcd {
     u32 r0 = e.wl_w(F_REQ0, node), r1 = e.wl_w(F_REQ1, node);
     u32 op = r0 & 15, key = (r0 >> 4) & 15, req_value = r1 & 0xffff;
     bool read = op == OP_GET || (op == OP_CAS && !flag);
+    bool carries_value = read || op == OP_LEASE_READ || op == OP_KEEP_ALIVE;
     if (status == ST_OK) {
       e.wl_s(S_NOK)++;
       if (revision > e.wl_s(S_MAXREV)) e.wl_s(S_MAXREV) = revision;
@@ -194,13 +249,14 @@ struct WL_Etcd {
       if (op == OP_PUT || (op == OP_CAS && flag)) seen_set(e, node, key, req_value);
       if (read) seen_set(e, node, key, value);
       if (op == OP_DELETE) seen_set(e, node, key, 0);
+      if (op == OP_REVOKE) e.wl_w(F_NEED_GRANT, node) = c == 0;
     } else {
       e.wl_s(S_NERR)++;
       if (status == ST_LEASE_NOT_FOUND && c == 0) e.wl_w(F_NEED_GRANT, node) = 1;
     }
     u32 n = e.wl_s(S_NHIST);
     if (n >= (u32)MAX_HIST) return 67;
-    u32 hv = read ? value : req_value;
+    u32 hv = carries_value ? value : req_value;
     e.wl_s(S_HIST + 3 * n) = c | op << 2 | key << 5 | status << 8 | flag << 10 | hv << 16;
     e.wl_s(S_HIST + 3 * n + 1) = revision | mod_revision << 16;
     e.wl_s(S_HIST + 3 * n + 2) = e.wl_w(F_FLOOR, node);
@@ -217,7 +273,7 @@ MSIM_NOUNROLL
       u32 op = (w0 >> 2) & 7, key = (w0 >> 5) & 7, status = (w0 >> 8) & 3, flag = (w0 >> 10) & 1, value = w0 >> 16;
       u32 revision = w1 & 0xffff, mod_revision = w1 >> 16;
       if (status != ST_OK) continue;
-      bool changes = op == OP_PUT || op == OP_GRANT || op == OP_CAS || (op == OP_DELETE && flag);
+      bool changes = op == OP_PUT || op == OP_GRANT || op == OP_CAS || (op == OP_DELETE && flag) || op == OP_REVOKE || op == OP_KEEP_ALIVE;
       if (revision < floor || (changes && revision <= floor)) return 60;
       bool is_read = op == OP_GET || (op == OP_CAS && !flag);
       if (!is_read || key == (u32)LEASE_KEY) continue;
@@ -338,6 +394,11 @@ MSIM_NOUNROLL
         case K_REQ * 16 + 0:
           e.t_pc(t) = 1;
           return RQ_CH_RECV;
+        case K_REQ * 16 + 5:  // LeaseKeepAlive: rx.recv().await? — the keeper's next ping — then answer again
+          if (e.ret < 0) return RQ_READY;
+          e.t_pc(t) = 1;
+          e.rv0 = e.t_a(t), e.rv1 = e.t_b(t);
+          // fallthrough
         case K_REQ * 16 + 1: {
           if (e.ret < 0) return RQ_READY;
           e.t_a(t) = e.rv0;
@@ -359,6 +420,9 @@ MSIM_NOUNROLL
             case OP_DELETE: r = sv_delete(e, key); break;
             case OP_CAS: r = sv_txn_cas(e, key, expect, value); break;
             case OP_GRANT: r = sv_lease_grant(e, ttl, lease); break;
+            case OP_REVOKE: r = sv_lease_revoke(e, lease); break;
+            case OP_KEEP_ALIVE: r = sv_lease_keep_alive(e, lease); break;
+            case OP_LEASE_READ: r = sv_lease_read(e, key, lease); break;
             default: r.panic_code = 64;
           }
           if (r.panic_code) return panic(e, (u32)r.panic_code);
@@ -371,6 +435,11 @@ MSIM_NOUNROLL
           e.yb = ST_TIMED_OUT, e.yc = 0;
           return RQ_CH_SEND;
         case K_REQ * 16 + 3:
+          if ((e.t_a(t) & 15) == OP_KEEP_ALIVE) {  // server.rs:65-69: loop { send(response)?; rx.recv()?; }
+            if (e.ret < 0) return RQ_READY;
+            e.t_pc(t) = 5;
+            return RQ_CH_RECV;
+          }
           return RQ_READY;  // tx, rx drop with the future
 
         // ---- etcd_client ----
@@ -417,12 +486,24 @@ MSIM_NOUNROLL
             op = OP_GET;
           } else if (r < 85) {
             op = OP_DELETE;
+          } else if (P.p[7] && r < 95) {  // the rest of LeaseClient (lease.rs:46-88)
+            lease = LEASE_ID, value = 0;
+            if (r < 88) {
+              op = OP_LEASE_READ, key = 0;
+            } else if (r < 91) {
+              op = OP_LEASE_READ, key = 1;
+            } else if (r < 94 || c != 0) {
+              op = OP_KEEP_ALIVE, key = 0;
+            } else {
+              op = OP_REVOKE, key = 0;
+            }
           } else {
             op = OP_CAS, expect = seen_get(e, node, key);
           }
           e.wl_w(F_REQ0, node) = op | key << 4 | lease << 8 | ttl << 16;
           e.wl_w(F_REQ1, node) = value | expect << 16;
           e.wl_w(F_FLOOR, node) = e.wl_s(S_MAXREV);
+          e.wl_w(F_KA_PHASE, node) = 0;
           e.t_pc(t) = 5;
           e.ya = SERVER_ADDR;
           return RQ_CONNECT1;
@@ -448,9 +529,19 @@ MSIM_NOUNROLL
           if (e.ret < 0) return panic(e, 66);
           u32 node = e.t_node(t);
           u32 v0 = e.rv0, v1 = e.rv1;
-          e.conn_drop_end(t);  // the call's tx, rx drop when it returns
           u32 status = v0 & 15;
           if (status == ST_OK) e.t_a(t)++;
+          if ((e.wl_w(F_REQ0, node) & 15) == OP_KEEP_ALIVE && e.wl_w(F_KA_PHASE, node) == 0) {
+            // LeaseClient::keep_alive's first response is logged on arrival; then LeaseKeeper::keep_alive pings again
+            int bad1 = client_complete(e, node, status, (v0 >> 4) & 1, v0 >> 16, v1 & 0xffff, v1 >> 16);
+            if (bad1) return panic(e, (u32)bad1);
+            e.wl_w(F_FLOOR, node) = e.wl_s(S_MAXREV);
+            e.wl_w(F_KA_PHASE, node) = 1;
+            e.t_pc(t) = 6;
+            e.yb = e.wl_w(F_REQ0, node), e.yc = e.wl_w(F_REQ1, node);
+            return RQ_CH_SEND;
+          }
+          e.conn_drop_end(t);  // the call's tx, rx drop when it returns
           int bad = client_complete(e, node, status, (v0 >> 4) & 1, v0 >> 16, v1 & 0xffff, v1 >> 16);
           if (bad) return panic(e, (u32)bad);
           e.t_pc(t) = 8;

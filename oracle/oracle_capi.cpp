@@ -87,6 +87,7 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
         std::memcpy(&ep.timeout_rate, &bits, 4);
         ep.bug = u32(wl->p[3]);
         ep.lease_ttl = u32(wl->p[4]);
+        ep.lease_admin = u32(wl->p[7]);
         if (ep.n_clients < 1 || ep.n_clients > 3 || !(ep.timeout_rate >= 0.0f && ep.timeout_rate <= 1.0f)) return MSIM_EINVAL;
         rt.block_on(wl_etcd_main(ep, &user));
         rt.teardown();

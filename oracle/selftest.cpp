@@ -356,14 +356,43 @@ static Async<Unit> etcd_lease_client(SocketAddr server) {
   CHECK(r.status == ETCD_OK);
   r = co_await call(ETCD_GET, 1, 0);
   CHECK(r.flag == 1);
+  r = co_await call(ETCD_LEASE_READ, 1, 0);  // leases(): exactly one
+  CHECK(r.status == ETCD_OK && r.value == 1);
+  // keep alive for 90 s: the first response is produced when the keep-alive connection opens,
+  // the second when the keeper pings again
   co_await sleep(45 * SEC);
+  {
+    auto cn = co_await ep.connect1(server);
+    Connection conn = std::move(cn.unwrap());
+    EtcdRequest ka;
+    ka.op = ETCD_KEEP_ALIVE, ka.lease = 9;
+    conn.tx.send(ka.encode()).unwrap();
+    EtcdResponse k1 = EtcdResponse::decode((co_await conn.rx.recv()).unwrap());
+    CHECK(k1.status == ETCD_OK && k1.value == 60);
+    co_await sleep(45 * SEC);
+    conn.tx.send(ka.encode()).unwrap();
+    EtcdResponse k2 = EtcdResponse::decode((co_await conn.rx.recv()).unwrap());
+    CHECK(k2.status == ETCD_OK && k2.revision == k1.revision + 1);
+  }
+  r = co_await call(ETCD_LEASE_READ, 0, 0, 9);  // time_to_live: just refreshed
+  CHECK(r.status == ETCD_OK && r.value <= 60 && r.value > 50);
   r = co_await call(ETCD_GET, 1, 0);
   CHECK(r.flag == 1);
-  co_await sleep(60 * SEC);  // wait for the lease to expire
+  co_await sleep(61 * SEC);  // wait for the lease to expire
   r = co_await call(ETCD_GET, 1, 0);
   CHECK(r.flag == 0);
   r = co_await call(ETCD_PUT, 1, 7, 1);  // put with an invalid lease
   CHECK(r.status == ETCD_LEASE_NOT_FOUND);
+  r = co_await call(ETCD_REVOKE, 0, 0, 1);  // revoke an invalid lease
+  CHECK(r.status == ETCD_LEASE_NOT_FOUND);
+  r = co_await call(ETCD_LEASE_READ, 0, 0, 1);  // time_to_live of an invalid lease
+  CHECK(r.status == ETCD_LEASE_NOT_FOUND);
+  r = co_await call(ETCD_GRANT, 0, 0, 9, 60);  // a revoked lease takes its keys with it
+  r = co_await call(ETCD_PUT, 2, 5, 9);
+  r = co_await call(ETCD_REVOKE, 0, 0, 9);
+  CHECK(r.status == ETCD_OK);
+  r = co_await call(ETCD_GET, 2, 0);
+  CHECK(r.flag == 0);
   co_return {};
 }
 template <class F>
@@ -654,7 +683,7 @@ int main() {
     CHECK(detected);
   });
   run_case("etcd::kv (madsim-etcd-client/tests/test.rs:9-62)", [] { etcd_case(etcd_kv_client); });
-  run_case("etcd::lease expiry + lease not found (tests/test.rs:64-128)", [] { etcd_case(etcd_lease_client); });
+  run_case("etcd::lease grant / leases / keep_alive / time_to_live / expiry / revoke / not found (tests/test.rs:64-128)", [] { etcd_case(etcd_lease_client); });
   run_case("tonic::basic unary + invalid_argument (tonic-example/tests/test.rs:22-70)", [] {
     Runtime rt;
     SocketAddr a{ip4(10, 0, 0, 1), 50051};

@@ -24,7 +24,8 @@ constexpr u32 ETCD_NKEY = 5;       // keys 0..3 are plain, key 4 is always writt
 constexpr u32 ETCD_LEASE_KEY = 4;
 constexpr u32 ETCD_LEASE_ID = 7;
 constexpr u32 ETCD_MAX_HIST = 128;
-enum : u32 { ETCD_PUT = 1, ETCD_GET = 2, ETCD_DELETE = 3, ETCD_CAS = 4, ETCD_GRANT = 5 };
+enum : u32 { ETCD_REVOKE = 0, ETCD_PUT = 1, ETCD_GET = 2, ETCD_DELETE = 3, ETCD_CAS = 4, ETCD_GRANT = 5, ETCD_LEASE_READ = 6, ETCD_KEEP_ALIVE = 7 };
+// ETCD_LEASE_READ: key 0 = LeaseTimeToLive (value = remaining ttl), key 1 = LeaseLeases (value = number of leases)
 enum : u32 { ETCD_OK = 0, ETCD_TIMED_OUT = 1, ETCD_LEASE_NOT_FOUND = 2, ETCD_REFUSED = 3 };
 enum : u32 { ETCD_BUG_STALE_READ = 1, ETCD_BUG_LEASE_KEY_DELETE = 2 };
 
@@ -35,6 +36,7 @@ struct EtcdParams {
   float timeout_rate = 0.0f;
   u32 bug = 0;
   u32 lease_ttl = 1;
+  u32 lease_admin = 0;  // 1: the clients also revoke / keep alive / query the lease (lease.rs:46-88)
 };
 
 // ---- wire format (the crate moves Box<dyn Any>; here two u32 words) ----
@@ -170,6 +172,53 @@ struct EtcdServiceInner {
     rsp.revision = revision;
     return rsp;
   }
+  /// service.rs:423-435
+  EtcdResponse lease_revoke(u32 id) {
+    EtcdResponse rsp;
+    auto l = lease.find(id);
+    if (l == lease.end()) {
+      rsp.status = ETCD_LEASE_NOT_FOUND;
+      return rsp;
+    }
+    for (u32 key : l->second.keys)
+      if (!kv.erase(key)) panic("no key", 63);
+    lease.erase(l);
+    revision += 1;
+    rsp.revision = revision;
+    return rsp;
+  }
+  /// service.rs:437-448: resets the ttl AND bumps the revision
+  EtcdResponse lease_keep_alive(u32 id) {
+    EtcdResponse rsp;
+    auto l = lease.find(id);
+    if (l == lease.end()) {
+      rsp.status = ETCD_LEASE_NOT_FOUND;
+      return rsp;
+    }
+    l->second.ttl = l->second.granted_ttl;
+    revision += 1;
+    rsp.revision = revision;
+    rsp.value = u32(l->second.granted_ttl);
+    return rsp;
+  }
+  /// service.rs:450-470 lease_time_to_live / lease_leases
+  EtcdResponse lease_read(u32 what, u32 id) {
+    EtcdResponse rsp;
+    rsp.revision = revision;
+    if (what == 1) {
+      rsp.value = u32(lease.size());
+      return rsp;
+    }
+    auto l = lease.find(id);
+    if (l == lease.end()) {
+      rsp.status = ETCD_LEASE_NOT_FOUND;
+      rsp.revision = 0;
+      return rsp;
+    }
+    rsp.value = u32(l->second.ttl) & 0xffff;
+    rsp.flag = 1;
+    return rsp;
+  }
   /// service.rs:472-492: called every second
   void tick() {
     size_t origin_len = lease.size();
@@ -233,6 +282,9 @@ struct EtcdService {
       case ETCD_DELETE: co_return inner->del(req.key);
       case ETCD_CAS: co_return inner->txn_cas(req.key, req.expect, req.value);
       case ETCD_GRANT: co_return inner->lease_grant(req.ttl, req.lease);
+      case ETCD_REVOKE: co_return inner->lease_revoke(req.lease);
+      case ETCD_KEEP_ALIVE: co_return inner->lease_keep_alive(req.lease);
+      case ETCD_LEASE_READ: co_return inner->lease_read(req.key, req.lease);
     }
     panic("unknown request", 64);
   }
@@ -242,7 +294,15 @@ struct EtcdService {
 inline Async<Unit> etcd_request_task(Connection conn, std::shared_ptr<EtcdService> service) {
   auto r = co_await conn.rx.recv();
   if (r.is_err()) co_return {};
-  EtcdResponse rsp = co_await service->handle(EtcdRequest::decode(*r.ok));
+  EtcdRequest req = EtcdRequest::decode(*r.ok);
+  if (req.op == ETCD_KEEP_ALIVE) {  // server.rs:65-69: answer, then wait for the keeper's next ping
+    for (;;) {
+      EtcdResponse ka = co_await service->handle(req);
+      if (conn.tx.send(ka.encode()).is_err()) co_return {};
+      if ((co_await conn.rx.recv()).is_err()) co_return {};
+    }
+  }
+  EtcdResponse rsp = co_await service->handle(req);
   (void)conn.tx.send(rsp.encode());  // tx.send(response).await?; the task ends either way
   co_return {};
 }
@@ -281,6 +341,36 @@ inline Async<EtcdResponse> etcd_call(const Endpoint& ep, SocketAddr server, Etcd
   co_return EtcdResponse::decode(*r.ok);
 }
 
+/// LeaseClient::keep_alive (lease.rs:56-63) + one more LeaseKeeper::keep_alive / stream.message() round.
+/// The first response is logged when it arrives (its own history entry); the second is returned.
+inline Async<EtcdResponse> etcd_keep_alive_twice(const Endpoint& ep, SocketAddr server, EtcdRequest req, u32 c,
+                                                 std::shared_ptr<EtcdHistory> h, u32* n_ok, u32* floor, bool* need_grant) {
+  EtcdResponse refused;
+  refused.status = ETCD_REFUSED;
+  auto cn = co_await ep.connect1(server);
+  if (cn.is_err()) co_return refused;
+  Connection conn = std::move(*cn.ok);
+  EtcdResponse rsp;
+  for (int k = 0; k < 2; k++) {
+    if (conn.tx.send(req.encode()).is_err()) panic("etcd client: send failed", 65);
+    auto r = co_await conn.rx.recv();
+    if (r.is_err()) panic("etcd client: connection reset", 66);
+    rsp = EtcdResponse::decode(*r.ok);
+    if (k == 1) break;
+    if (rsp.status == ETCD_OK) {
+      (*n_ok)++, h->n_ok++;
+      if (rsp.revision > h->max_done_revision) h->max_done_revision = rsp.revision;
+    } else {
+      h->n_err++;
+      if (rsp.status == ETCD_LEASE_NOT_FOUND && c == 0) *need_grant = true;
+    }
+    if (h->entries.size() >= ETCD_MAX_HIST) panic("history full", 67);
+    h->entries.push_back({c, req.op, req.key, rsp.status, rsp.flag, rsp.value, rsp.revision, rsp.mod_revision, *floor});
+    *floor = h->max_done_revision;  // the second ping is invoked now
+  }
+  co_return rsp;
+}
+
 inline Async<u32> etcd_client(u32 c, SocketAddr server, EtcdParams p, std::shared_ptr<EtcdHistory> h) {
   Endpoint ep = std::move((co_await Endpoint::connect(server)).unwrap());  // Client::connect
   GlobalRng& rng = thread_rng();
@@ -309,11 +399,27 @@ inline Async<u32> etcd_client(u32 c, SocketAddr server, EtcdParams p, std::share
       req.op = ETCD_GET;
     } else if (r < 85) {
       req.op = ETCD_DELETE;
+    } else if (p.lease_admin && r < 95) {  // the rest of LeaseClient
+      req.lease = ETCD_LEASE_ID, req.value = 0;
+      if (r < 88) {
+        req.op = ETCD_LEASE_READ, req.key = 0;  // time_to_live
+      } else if (r < 91) {
+        req.op = ETCD_LEASE_READ, req.key = 1;  // leases
+      } else if (r < 94 || c != 0) {
+        req.op = ETCD_KEEP_ALIVE, req.key = 0;
+      } else {
+        req.op = ETCD_REVOKE, req.key = 0;
+      }
     } else {
       req.op = ETCD_CAS, req.expect = last_seen[key];
     }
     u32 floor = h->max_done_revision;
-    EtcdResponse rsp = co_await etcd_call(ep, server, req);
+    EtcdResponse rsp;
+    if (req.op == ETCD_KEEP_ALIVE) {
+      rsp = co_await etcd_keep_alive_twice(ep, server, req, c, h, &n_ok, &floor, &need_grant);
+    } else {
+      rsp = co_await etcd_call(ep, server, req);
+    }
     if (rsp.status == ETCD_OK) {
       n_ok++;
       h->n_ok++;
@@ -322,12 +428,14 @@ inline Async<u32> etcd_client(u32 c, SocketAddr server, EtcdParams p, std::share
       if (req.op == ETCD_PUT || (req.op == ETCD_CAS && rsp.flag)) last_seen[key] = req.value;
       if (req.op == ETCD_GET || (req.op == ETCD_CAS && !rsp.flag)) last_seen[key] = rsp.value;
       if (req.op == ETCD_DELETE) last_seen[key] = 0;
+      if (req.op == ETCD_REVOKE) need_grant = c == 0;
     } else {
       h->n_err++;
       if (rsp.status == ETCD_LEASE_NOT_FOUND && c == 0) need_grant = true;
     }
     if (h->entries.size() >= ETCD_MAX_HIST) panic("history full", 67);
-    h->entries.push_back({c, req.op, req.key, rsp.status, rsp.flag, req.op == ETCD_GET || (req.op == ETCD_CAS && !rsp.flag) ? rsp.value : req.value,
+    bool carries_value = req.op == ETCD_GET || (req.op == ETCD_CAS && !rsp.flag) || req.op == ETCD_LEASE_READ || req.op == ETCD_KEEP_ALIVE;
+    h->entries.push_back({c, req.op, req.key, rsp.status, rsp.flag, carries_value ? rsp.value : req.value,
                           rsp.revision, rsp.mod_revision, floor});
     co_await sleep(p.think_ns);
   }
@@ -339,7 +447,8 @@ inline Async<u32> etcd_client(u32 c, SocketAddr server, EtcdParams p, std::share
 /// store; (B) every read of a plain key returns the latest logged write at or below its revision.
 inline void etcd_check_history(const EtcdHistory& h) {
   auto changes = [](const EtcdHistEntry& e) {
-    return e.op == ETCD_PUT || e.op == ETCD_GRANT || e.op == ETCD_CAS || (e.op == ETCD_DELETE && e.flag);
+    return e.op == ETCD_PUT || e.op == ETCD_GRANT || e.op == ETCD_CAS || (e.op == ETCD_DELETE && e.flag) ||
+           e.op == ETCD_REVOKE || e.op == ETCD_KEEP_ALIVE;
   };
   for (const auto& e : h.entries) {
     if (e.status != ETCD_OK) continue;

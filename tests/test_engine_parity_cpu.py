@@ -54,6 +54,8 @@ CASES = [
     ("etcd-timeouts-3clients", m.Config(packet_loss_rate=0.1), m.Workload.etcd(clients=3, ops=42, timeout_rate=0.15), 50, 48),
     ("etcd-stale-read-bug", m.Config(packet_loss_rate=0.05), m.Workload.etcd(bug=1), 0, 64),
     ("etcd-reference-no-lease-panic", m.Config(), m.Workload.etcd(bug=2), 0, 64),
+    ("etcd-lease-admin-timeouts", m.Config(packet_loss_rate=0.1), m.Workload.etcd(lease_admin=True, timeout_rate=0.1), 0, 96),
+    ("etcd-lease-admin-3clients-bugs", m.Config(), m.Workload.etcd(lease_admin=True, clients=3, ops=30, bug=3, lease_ttl_s=2), 0, 64),
     ("etcd-always-timeout", m.Config(), m.Workload.etcd(ops=3, timeout_rate=1.0), 0, 16),
     # tonic-example Greeter under madsim-tonic + kill/restart chaos (BASELINE config 5)
     ("tonic", m.Config(), m.Workload.tonic(), 0, 32),

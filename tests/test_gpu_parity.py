@@ -88,6 +88,8 @@ CASES = [
     ("etcd-timeouts-3clients", m.Config(packet_loss_rate=0.1), m.Workload.etcd(clients=3, ops=42, timeout_rate=0.15), 50, 300),
     ("etcd-stale-read-bug", m.Config(packet_loss_rate=0.05), m.Workload.etcd(bug=1), 0, 300),
     ("etcd-reference-no-lease-panic", m.Config(), m.Workload.etcd(bug=2), 0, 300),
+    ("etcd-lease-admin-timeouts", m.Config(packet_loss_rate=0.1), m.Workload.etcd(lease_admin=True, timeout_rate=0.1), 0, 400),
+    ("etcd-lease-admin-3clients-bugs", m.Config(), m.Workload.etcd(lease_admin=True, clients=3, ops=30, bug=3, lease_ttl_s=2), 0, 300),
     ("etcd-always-timeout-buggify", m.Config(buggify=True), m.Workload.etcd(ops=3, timeout_rate=1.0), 0, 64),
     ("tonic-kill-restart-chaos", m.Config(), m.Workload.tonic(), 0, 300),
     ("tonic-restart-only-1client", m.Config(), m.Workload.tonic(clients=1, restart_only=True), 0, 200),

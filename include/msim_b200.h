@@ -124,7 +124,9 @@ typedef struct msim_config {
  *  TONIC    n_nodes = 1 server + (n_nodes-1) client nodes (default 7); p0 = chaos rounds (default 10),
  *           p1 = think time ns between unary calls (default 100 ms), p2 = flags (1 = restart only, never kill;
  *           2 = clients also make server-streaming calls, sometimes dropping the response stream at once,
- *           client-streaming calls and bidi calls whose response stream is sometimes dropped early)
+ *           client-streaming calls and bidi calls whose response stream is sometimes dropped early;
+ *           4 = halfway through the supervisor kills the SERVER: calls in flight break, later ones are refused,
+ *           the clients count failures (user[3]) instead of panicking)
  *  SIGNAL   p0 = supervisor rounds (default 8), p1 = interval period ms (default 100),
  *           p2 = MissedTickBehavior (0 Burst, 1 Delay, 2 Skip), p3 = flags (1 = the worker installs a ctrl-c handler; default 1)
  *  CHAOS    p0 = rounds, p1 = period ms, p2 = worker panics on its first p2 starts (restart_on_panic)

@@ -769,7 +769,7 @@ MSIM_NOUNROLL
   MSIM_HD int sock_find(int node, u32 ipk, u32 port) const {
 MSIM_NOUNROLL
     for (int k = 0; k < C::NSOCK; k++)
-      if (sk_state(k) && b(L::B_SK_NODE, k) == node && b(L::B_SK_IPK, k) == ipk && sk_port(k) == port) return k;
+      if (sk_state(k) == 1 && b(L::B_SK_NODE, k) == node && b(L::B_SK_IPK, k) == ipk && sk_port(k) == port) return k;
     return -1;
   }
   /// Network::bind (network.rs:206-251).  >= 0 socket slot; -1 AddrNotAvailable; -2 AddrInUse
@@ -818,15 +818,24 @@ MSIM_NOUNROLL
     sk_state(k) = 0;
     w(L::W_SK_PORTGEN, k) = (w(L::W_SK_PORTGEN, k) & 0xffff0000u) + 0x10000u;  // gen++ : stale refs miss
   }
+  /// NetSim::reset_node (network.rs:142-147): every socket of the node leaves the address map.  The socket
+  /// OBJECT lives on until the killed futures that hold it are dropped — observable only through the
+  /// connections still waiting in its accept queue (they close then, not now): such a socket stays behind
+  /// unbound (state 2) until its last reference goes (sock_unref).
   MSIM_HD void reset_node_sockets(int n) {
 MSIM_NOUNROLL
     for (int k = 0; k < C::NSOCK; k++)
-      if (sk_state(k) && b(L::B_SK_NODE, k) == n) {
-        // The reference frees the socket OBJECT (and with it the un-accepted connections) only when the
-        // killed listener's future is dropped; this build frees it here.  Unobservable unless connections
-        // are waiting to be accepted — that case is reported, not approximated.
-        if (C::NCONN && b(L::B_ACC_LEN, k) != 0) fail_cap(MSIM_CAP_SOCKETS);
-        sock_release_storage(k);
+      if (sk_state(k) == 1 && b(L::B_SK_NODE, k) == n) {
+        if (C::NCONN && b(L::B_ACC_LEN, k) != 0) {
+          u32 ml = b(L::B_SK_MBLEN, k);
+          for (u32 i = 0; i < ml; i++) msg_free(b(L::B_MB, k * C::NMBOX + i));
+          b(L::B_SK_MBLEN, k) = 0;
+          b(L::B_SK_REGLEN, k) = 0;
+          w(L::W_ACC_WAITER, k) = NONE32;
+          sk_state(k) = 2;
+        } else {
+          sock_release_storage(k);
+        }
       }
   }
   /// A future takes / drops a clone of the Endpoint (Arc<BindGuard>)
@@ -846,6 +855,10 @@ MSIM_NOUNROLL
     t_sock(t) = NONE8;
     if (!sk_state(k) || (u8)sk_gen(k) != t_sockgen(t)) return;
     if (--b(L::B_SK_REFS, k) != 0) return;
+    if (C::NCONN && sk_state(k) == 2) {  // the last holder of a reset socket: its accept queue closes now
+      sock_release_storage(k);
+      return;
+    }
     int n = b(L::B_SK_NODE, k);
     bool killed = b(L::B_SK_EPOCH, k) != n_epoch(n) || (n_flags(n) & NF_KILLED);
     if (!killed) sock_release_storage(k);
@@ -1005,7 +1018,7 @@ MSIM_NOUNROLL
   MSIM_HD void deliver(int m) {
     u32 d = w(L::W_M_DST, m);
     int k = d >> 16;
-    if (!sk_state(k) || (sk_gen(k) & 0xffff) != (d & 0xffff)) {
+    if (sk_state(k) != 1 || (sk_gen(k) & 0xffff) != (d & 0xffff)) {
       msg_free(m);
       return;
     }

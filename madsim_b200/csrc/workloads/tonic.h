@@ -18,7 +18,7 @@
 namespace msim {
 
 struct WL_Tonic {
-  enum : int { S_HANDLED = 0, S_CNT, S_ROUND, S_C, S_END };  // wl_s scalars
+  enum : int { S_HANDLED = 0, S_CNT, S_ROUND, S_C, S_FAILURES, S_END };  // wl_s scalars
   enum : int { F_REPLIES = 0, F_STARTS, F_NFIELD };           // wl_w per client node
   struct Caps {
     static constexpr int NT = 32, TQ = 64, NMSG = 2, NSOCK = 24, NREG = 1, NMBOX = 1, NNODE = 8, NPARK = 1;
@@ -33,7 +33,7 @@ struct WL_Tonic {
   enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_RSP_BIDI, K_SENDER };
   enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u };
   enum : u32 { ST_OK = 0, ST_INVALID_ARGUMENT = 1, ST_EOF = 2, ST_TRAILER = 3 };
-  enum : u32 { SERVER_STREAMING = 1u << 31, CLIENT_STREAMING = 1u << 30, FLAG_RESTART_ONLY = 1, FLAG_STREAMING_MIX = 2 };
+  enum : u32 { SERVER_STREAMING = 1u << 31, CLIENT_STREAMING = 1u << 30, FLAG_RESTART_ONLY = 1, FLAG_STREAMING_MIX = 2, FLAG_SERVER_CRASH = 4 };
   static constexpr u32 MAIN_KIND = K_MAIN;
   static constexpr u32 SERVER_ADDR = (IPK_NODE << 24) | (1u << 16) | 50051u;  // 10.0.0.1:50051
   /// NodeBuilder::init(|| tonic_client(c)) — what Handle::restart re-runs
@@ -43,6 +43,31 @@ struct WL_Tonic {
   static MSIM_HD int panic(E& e, u32 code) {
     e.ya = code;
     return RQ_PANIC;
+  }
+
+  /// A failed call: `.unwrap()` panics — except in the server-crash schedule (tests/test.rs:233-278), where the
+  /// client counts the failure, drops what the call held (`_task`, the connection, the endpoint) and goes on
+  template <class E>
+  static MSIM_HD int call_failed(E& e, int t, u32 code) {
+    if (!(e.P->p[2] & FLAG_SERVER_CRASH)) return panic(e, code);
+    if (e.t_handle(t) != NONE8) {
+      if (e.t_handle(t) & 0x80)
+        e.join_detach(e.t_handle(t) & 0x7f);
+      else
+        e.task_cancel_detach(e.t_handle(t));
+      e.t_handle(t) = NONE8;
+    }
+    e.conn_drop_end(t);
+    e.sock_unref(t);
+    e.wl_s(S_FAILURES)++;
+    if (code == 70) {
+      e.t_pc(t) = 18;  // GreeterClient::connect again
+    } else {
+      e.t_b(t)++;
+      e.t_pc(t) = 3;
+    }
+    e.xa = e.P->p[1];
+    return RQ_SLEEP_FOR;
   }
 
   template <class E>
@@ -92,7 +117,9 @@ struct WL_Tonic {
           return RQ_GEN_RANGE;
         case K_MAIN * 32 + 7: {
           int id = 2 + (int)e.wl_s(S_C);
-          if (e.ret64 == 3 && !(P.p[2] & FLAG_RESTART_ONLY))
+          if ((P.p[2] & FLAG_SERVER_CRASH) && (u64)e.wl_s(S_ROUND) == P.p[0] / 2)
+            e.kill(1);
+          else if (e.ret64 == 3 && !(P.p[2] & FLAG_RESTART_ONLY))
             e.kill(id);
           else
             e.restart(id);
@@ -107,7 +134,7 @@ struct WL_Tonic {
           e.w(L::W_USER0) = replies;
           e.w(L::W_USER1) = starts;
           e.w(L::W_USER2) = e.wl_s(S_HANDLED);
-          e.w(L::W_USER3) = e.w(L::W_MSG_COUNT);
+          e.w(L::W_USER3) = (P.p[2] & FLAG_SERVER_CRASH) ? e.wl_s(S_FAILURES) : e.w(L::W_MSG_COUNT);
           return RQ_READY;
         }
 
@@ -269,16 +296,18 @@ struct WL_Tonic {
         // ---- tonic_client: the client node's init task ----
         case K_CLIENT * 32 + 0:  // GreeterClient::connect: connect_ep, then drop it
           e.wl_w(F_STARTS, e.t_node(t))++;
+          // fallthrough
+        case K_CLIENT * 32 + 18:
           e.t_pc(t) = 1;
           e.ya = mk_addr(IPK_UNSPEC, 0, 0);
           return RQ_BIND;
         case K_CLIENT * 32 + 1:
-          if (e.ret < 0) return panic(e, 70);
+          if (e.ret < 0) return call_failed(e, t, 70);
           e.t_pc(t) = 2;
           e.ya = SERVER_ADDR;
           return RQ_CONNECT1;
         case K_CLIENT * 32 + 2:
-          if (e.ret < 0) return panic(e, 70);
+          if (e.ret < 0) return call_failed(e, t, 70);
           e.conn_drop_end(t);
           e.sock_unref(t);
           e.t_b(t) = 0;  // seq
@@ -295,18 +324,18 @@ struct WL_Tonic {
           e.ya = mk_addr(IPK_UNSPEC, 0, 0);
           return RQ_BIND;
         case K_CLIENT * 32 + 5:  // the handshake connection
-          if (e.ret < 0) return panic(e, 71);
+          if (e.ret < 0) return call_failed(e, t, 71);
           e.t_pc(t) = 6;
           e.ya = SERVER_ADDR;
           return RQ_CONNECT1;
         case K_CLIENT * 32 + 6:  // the request's connection
-          if (e.ret < 0) return panic(e, 71);
+          if (e.ret < 0) return call_failed(e, t, 71);
           e.conn_drop_end(t);
           e.t_pc(t) = 7;
           e.ya = SERVER_ADDR;
           return RQ_CONNECT1;
         case K_CLIENT * 32 + 7:
-          if (e.ret < 0) return panic(e, 71);
+          if (e.ret < 0) return call_failed(e, t, 71);
           if (e.t_c(t) >= 5) {  // bidi: spawn the task that sends the requests; it takes the Sender
             e.t_pc(t) = 15;
             e.ya = K_SENDER | SPAWN_CONN_TX | SPAWN_JOINABLE, e.yb = e.t_node(t), e.yc = e.t_b(t), e.yd = 0, e.xa = e.xb = 0;
@@ -323,11 +352,11 @@ struct WL_Tonic {
           e.yb = e.t_a(t), e.yc = e.t_b(t) | (e.t_c(t) ? (u32)SERVER_STREAMING : 0u);
           return RQ_CH_SEND;
         case K_CLIENT * 32 + 8:
-          if (e.ret < 0) return panic(e, 71);
+          if (e.ret < 0) return call_failed(e, t, 71);
           e.t_pc(t) = 9;
           return RQ_CH_RECV;
         case K_CLIENT * 32 + 9: {
-          if (e.ret < 0) return panic(e, 71);
+          if (e.ret < 0) return call_failed(e, t, 71);
           u32 node = e.t_node(t);
           u32 st = e.rv0, reply = e.rv1;
           if (e.t_c(t)) {  // the header of a server-streaming call
@@ -359,7 +388,7 @@ struct WL_Tonic {
           return RQ_SLEEP_FOR;
         }
         case K_CLIENT * 32 + 10: {  // Streaming::message(): three replies, then the EOF status
-          if (e.ret < 0) return panic(e, 71);
+          if (e.ret < 0) return call_failed(e, t, 71);
           u32 node = e.t_node(t), i = e.t_c(t) - 16;
           if (i < 3) {
             if (e.rv0 != ST_OK || e.rv1 != NAME * 31u + node + i) return panic(e, 76);
@@ -376,7 +405,7 @@ struct WL_Tonic {
           return RQ_SLEEP_FOR;
         }
         case K_CLIENT * 32 + 11:  // header sent (tx.send(..).await?), then: yield item i; sleep(1 s)
-          if (e.ret < 0) return panic(e, 71);
+          if (e.ret < 0) return call_failed(e, t, 71);
           // fallthrough
         case K_CLIENT * 32 + 12: {
           u32 i = e.t_c(t) - 32;
@@ -401,7 +430,7 @@ struct WL_Tonic {
           e.xa = NS_PER_SEC;
           return RQ_SLEEP_FOR;
         case K_CLIENT * 32 + 14: {
-          if (e.ret < 0) return panic(e, 71);
+          if (e.ret < 0) return call_failed(e, t, 71);
           u32 node = e.t_node(t);
           if (e.rv0 != ST_OK || e.rv1 != e.t_a(t) * 31u + node) return panic(e, 78);
           e.conn_drop_end(t);
@@ -419,13 +448,13 @@ struct WL_Tonic {
           e.t_pc(t) = 16;
           return RQ_CH_RECV;
         case K_CLIENT * 32 + 16:  // the header: Result<Response<()>>
-          if (e.ret < 0) return panic(e, 71);
+          if (e.ret < 0) return call_failed(e, t, 71);
           if (e.rv0 != ST_OK) return panic(e, 75);
           e.t_handle(t) = e.t_handle(t) & 0x7f;  // first poll of the response stream: `_task = task.cancel_on_drop()`
           e.t_pc(t) = 17;
           return RQ_CH_RECV;
         case K_CLIENT * 32 + 17: {  // while let Some(reply) = stream.message().await.unwrap()
-          if (e.ret < 0) return panic(e, 71);
+          if (e.ret < 0) return call_failed(e, t, 71);
           u32 node = e.t_node(t);
           bool done = false;
           if (e.rv0 == ST_TRAILER) {

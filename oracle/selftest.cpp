@@ -502,6 +502,40 @@ static Async<Unit> tonic_server_stream_client(SocketAddr server, std::shared_ptr
   co_return {};
 }
 
+// ---- tonic-example/tests/test.rs:233-278 server_crash ----
+static Async<Unit> tonic_server_crash_client(Runtime* rt, u64 server_node, SocketAddr server) {
+  SocketAddr me{ip4(10, 0, 0, 2), 0};
+  Payload q;
+  q.v[0] = TONIC_NAME;
+  auto r = co_await tonic_unary(server, q);
+  CHECK(r.is_ok());
+  // a bidi call is in flight when the server dies: the stream ends in "broken pipe", not in a trailer
+  auto ep = co_await tonic_connect_ep(server);
+  auto c = co_await ep.unwrap().connect1(server);
+  Connection conn = std::move(c.unwrap());
+  auto task = spawn(tonic_bidi_sender(std::move(conn.tx), 0));
+  auto header = co_await conn.rx.recv();
+  CHECK(header.is_ok() && header.ok->v[0] == TONIC_OK);
+  co_await sleep(1 * SEC);
+  rt->kill(server_node);
+  co_await sleep(1 * SEC);
+  bool broken = false;
+  for (;;) {
+    auto m = co_await conn.rx.recv();
+    if (m.is_err()) {
+      broken = true;
+      break;
+    }
+    CHECK(m.ok->v[0] == TONIC_OK);  // replies that were already on their way
+  }
+  CHECK(broken);
+  r = co_await tonic_unary(server, q);  // Code::Unavailable: nobody listens any more
+  CHECK(r.is_err());
+  (void)task;
+  (void)me;
+  co_return {};
+}
+
 int main() {
   run_case("task::spawn_in_block_on", [] {
     Runtime rt;
@@ -704,6 +738,17 @@ int main() {
     auto st = std::make_shared<TonicStats>();
     server.spawn(tonic_serve(a, st));
     auto h = cl.spawn(tonic_server_stream_client(a, st));
+    rt.block_on(join_unwrap(std::move(h)));
+    rt.teardown();
+  });
+  run_case("tonic::server_crash (tests/test.rs:233-278)", [] {
+    Runtime rt;
+    SocketAddr a{ip4(10, 0, 0, 1), 50051};
+    auto server = rt.create_node().ip(a.ip).build();
+    auto cl = rt.create_node().ip(ip4(10, 0, 0, 2)).build();
+    auto st = std::make_shared<TonicStats>();
+    server.spawn(tonic_serve(a, st));
+    auto h = cl.spawn(tonic_server_crash_client(&rt, server.id(), a));
     rt.block_on(join_unwrap(std::move(h)));
     rt.teardown();
   });

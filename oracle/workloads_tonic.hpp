@@ -25,18 +25,20 @@ constexpr u32 TONIC_ERROR = 0x6f727265u;  // "erro"
 enum : u32 { TONIC_OK = 0, TONIC_INVALID_ARGUMENT = 1, TONIC_EOF = 2, TONIC_TRAILER = 3 };
 constexpr u32 TONIC_SERVER_STREAMING = 1u << 31;  // the `server_streaming: bool` of the first message (client.rs:128)
 constexpr u32 TONIC_CLIENT_STREAMING = 1u << 30;  // the first message is the stream-start header Box<()> (client.rs:170-176)
-enum : u32 { TONIC_RESTART_ONLY = 1, TONIC_STREAMING_MIX = 2 };
+enum : u32 { TONIC_RESTART_ONLY = 1, TONIC_STREAMING_MIX = 2, TONIC_SERVER_CRASH = 4 };
 
 struct TonicParams {
   u32 n_clients = 6;
   u64 rounds = 10;
   u64 think_ns = 100 * MS;
+  // 4: halfway through, the supervisor kills the SERVER (tests/test.rs:233-278 server_crash): calls in flight end in
+  //    "broken pipe", later ones are refused; the clients count failures instead of unwrapping
   u32 flags = 0;  // 1: the supervisor never kills, only restarts (client_crash as written); 2: clients also make
                   // server-streaming calls (lots_of_replies), sometimes dropping the response stream at once
 };
 struct TonicStats {
   std::array<u32, 8> replies{}, starts{};
-  u32 handled = 0;
+  u32 handled = 0, failures = 0;
 };
 inline u32 tonic_reply_for(u32 name, SocketAddr remote) { return name * 31u + (remote.ip & 0xff); }
 
@@ -304,9 +306,14 @@ inline Async<Result<u32>> tonic_bidi(SocketAddr server, u32 seq, SocketAddr me, 
 inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::shared_ptr<TonicStats> st) {
   st->starts[c]++;
   SocketAddr me{ip4(10, 0, 0, 2 + c), 0};
-  {  // GreeterClient::connect: Endpoint::connect_inner only checks that the endpoint is reachable
+  const bool tolerant = p.flags & TONIC_SERVER_CRASH;
+  for (;;) {  // GreeterClient::connect: Endpoint::connect_inner only checks that the endpoint is reachable
     auto ep = co_await tonic_connect_ep(server);
-    if (ep.is_err()) panic("GreeterClient::connect failed", 70);
+    if (ep.is_ok()) break;
+    if (!tolerant) panic("GreeterClient::connect failed", 70);
+    st->failures++;
+    ep.ok.reset();
+    co_await sleep(p.think_ns);
   }
   GlobalRng& rng = thread_rng();
   for (u32 seq = 0;; seq++) {
@@ -316,27 +323,47 @@ inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::sh
     q.v[1] = seq;
     if ((p.flags & TONIC_STREAMING_MIX) && pick >= 1 && pick <= 3) {  // lots_of_replies; pick 3 drops the stream at once
       auto sr = co_await tonic_server_streaming(server, q, pick == 3, tonic_reply_for(TONIC_NAME, me));
-      if (sr.is_err()) panic("lots_of_replies failed", 71);
+      if (sr.is_err()) {
+        if (!tolerant) panic("lots_of_replies failed", 71);
+        st->failures++;
+        co_await sleep(p.think_ns);
+        continue;
+      }
       st->replies[c]++;
       co_await sleep(p.think_ns);
       continue;
     }
     if ((p.flags & TONIC_STREAMING_MIX) && (pick == 5 || pick == 6)) {  // bidi_hello; pick 6 drops the stream after one reply
       auto sr = co_await tonic_bidi(server, seq, me, pick == 6);
-      if (sr.is_err()) panic("bidi_hello failed", 71);
+      if (sr.is_err()) {
+        if (!tolerant) panic("bidi_hello failed", 71);
+        st->failures++;
+        co_await sleep(p.think_ns);
+        continue;
+      }
       st->replies[c]++;
       co_await sleep(p.think_ns);
       continue;
     }
     if ((p.flags & TONIC_STREAMING_MIX) && pick == 4) {  // lots_of_greetings
       auto sr = co_await tonic_client_streaming(server, seq, me);
-      if (sr.is_err()) panic("lots_of_greetings failed", 71);
+      if (sr.is_err()) {
+        if (!tolerant) panic("lots_of_greetings failed", 71);
+        st->failures++;
+        co_await sleep(p.think_ns);
+        continue;
+      }
       st->replies[c]++;
       co_await sleep(p.think_ns);
       continue;
     }
     auto r = co_await tonic_unary(server, q);
-    if (r.is_err()) panic("say_hello failed", 71);
+    if (r.is_err()) {
+      if (!tolerant) panic("say_hello failed", 71);
+      st->failures++;
+      co_await sleep(p.think_ns);
+      continue;
+    }
     if (q.v[0] == TONIC_ERROR) {
       if (r.ok->v[0] != TONIC_INVALID_ARGUMENT) panic("expected invalid_argument", 72);
     } else if (r.ok->v[0] != TONIC_OK || r.ok->v[1] != tonic_reply_for(TONIC_NAME, me)) {
@@ -366,7 +393,9 @@ inline Async<u32> wl_tonic_main(TonicParams p, std::array<u32, 4>* user) {
     co_await sleep(rng.gen_range_duration(0, 5 * SEC));
     u64 c = rng.gen_range_u64(0, p.n_clients);
     u64 k = rng.gen_range_u64(0, 4);
-    if (k == 3 && !(p.flags & TONIC_RESTART_ONLY))
+    if ((p.flags & TONIC_SERVER_CRASH) && i == p.rounds / 2)
+      rt.kill(node0.id());
+    else if (k == 3 && !(p.flags & TONIC_RESTART_ONLY))
       rt.kill(ids[c]);
     else
       rt.restart(ids[c]);
@@ -378,7 +407,7 @@ inline Async<u32> wl_tonic_main(TonicParams p, std::array<u32, 4>* user) {
   (*user)[0] = replies;
   (*user)[1] = starts;
   (*user)[2] = st->handled;
-  (*user)[3] = u32(current_net().msg_count());
+  (*user)[3] = (p.flags & TONIC_SERVER_CRASH) ? st->failures : u32(current_net().msg_count());
   co_return 0;
 }
 

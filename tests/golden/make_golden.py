@@ -37,6 +37,7 @@ CASES = {
     "signal_skip_no_handler": (dict(), dict(kind="signal", behavior=2, catch=False), list(range(4))),
     "tonic_cfg5_streaming": (dict(), dict(kind="tonic", streaming=True), list(range(6))),
     "etcd_cfg4_lease_admin": (dict(packet_loss_rate=0.1), dict(kind="etcd", lease_admin=True, timeout_rate=0.125), list(range(6))),
+    "tonic_server_crash": (dict(), dict(kind="tonic", streaming=True, server_crash=True), list(range(6))),
     "raft_cfg3_loss5": (dict(packet_loss_rate=0.05), dict(kind="raft", faults=7), list(range(4))),
 }
 

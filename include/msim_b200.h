@@ -126,7 +126,9 @@ typedef struct msim_config {
  *           2 = clients also make server-streaming calls, sometimes dropping the response stream at once,
  *           client-streaming calls and bidi calls whose response stream is sometimes dropped early;
  *           4 = halfway through the supervisor kills the SERVER: calls in flight break, later ones are refused,
- *           the clients count failures (user[3]) instead of panicking)
+ *           the clients count failures (user[3]) instead of panicking;
+ *           8 = unary calls run inside time::timeout (channel timeout 1 s) and some call `delay`, which must end in
+ *           DeadlineExceeded after 1 s / 5 s)
  *  SIGNAL   p0 = supervisor rounds (default 8), p1 = interval period ms (default 100),
  *           p2 = MissedTickBehavior (0 Burst, 1 Delay, 2 Skip), p3 = flags (1 = the worker installs a ctrl-c handler; default 1)
  *  CHAOS    p0 = rounds, p1 = period ms, p2 = worker panics on its first p2 starts (restart_on_panic)

@@ -116,12 +116,12 @@ class Workload:
 
     @staticmethod
     def tonic(clients: int = 6, rounds: int = 10, think_ns: int = 100 * MS, restart_only: bool = False,
-              streaming: bool = False, server_crash: bool = False) -> "Workload":
+              streaming: bool = False, server_crash: bool = False, timeouts: bool = False) -> "Workload":
         """tonic-example Greeter service under madsim-tonic (a fresh endpoint + handshake + connection per
         unary call) while a supervisor kills / restarts the client nodes (BASELINE config 5); with `streaming`
         the clients also make server-streaming (lots_of_replies, sometimes dropping the response stream) and
         client-streaming (lots_of_greetings) and bidi (bidi_hello, sometimes dropped after one reply) calls."""
-        return Workload(N.WL_TONIC, clients + 1, [rounds, think_ns, int(restart_only) | 2 * int(streaming) | 4 * int(server_crash), 0, 0, 0, 0, 0])
+        return Workload(N.WL_TONIC, clients + 1, [rounds, think_ns, int(restart_only) | 2 * int(streaming) | 4 * int(server_crash) | 8 * int(timeouts), 0, 0, 0, 0, 0])
 
     @staticmethod
     def signal(rounds: int = 8, period_ms: int = 100, behavior: int = 0, catch: bool = True) -> "Workload":

@@ -80,6 +80,10 @@ enum : int {
   RQ_CTRL_C,        // signal::ctrl_c().await (installs the node's handler on first use)
   RQ_SLEEP_OR_CLOSED,  // select_biased!{ conn.tx.closed() => -2, sleep(xa ns) => 0 }  (madsim-tonic server.rs:289-300)
   RQ_CH_RECV_OR_CLOSED,  // select_biased!{ conn.tx.closed() => -2, conn.rx.recv() => 0 / -1 }
+  RQ_TIMEOUT_BEGIN,  // time::timeout(xa ns, async { ..the awaits up to RQ_TIMEOUT_END.. }) (time/mod.rs:128-140): the Sleep is
+                     // created now; at every pending poll the inner future goes first, then the Sleep; when it fires the
+                     // pending await is dropped where it stands and the state machine continues with ret = -3 (Elapsed)
+  RQ_TIMEOUT_END,
 };
 enum : u32 { SPAWN_EP = 0x100, SPAWN_JOINABLE = 0x200, SPAWN_CONN = 0x400, SPAWN_CONN_TX = 0x800 };  // clone the Endpoint / keep a JoinHandle / move the connection end / move only its Sender
 enum : u32 { NODE_IP = 1, NODE_INIT = 2, NODE_RESTART_ON_PANIC = 4 };
@@ -101,7 +105,9 @@ struct Layout {
   static constexpr int Q_HEAP_DL = 10;                      // [TQ] timer deadlines (implicit binary heap)
   static constexpr int Q_T_DL0 = Q_HEAP_DL + C::TQ;         // [NT] Sleep deadline of the task's current await
   static constexpr int Q_T_DL1 = Q_T_DL0 + C::NT;           // [NT] timeout deadline / generic u64 local
-  static constexpr int Q_M_TAG = Q_T_DL1 + C::NT;           // [NMSG]
+  static constexpr int NTT = C::USES_TIMEOUT ? C::NT : 0;
+  static constexpr int Q_T_DL2 = Q_T_DL1 + C::NT;           // [NTT] deadline of the time::timeout scope the future is inside, or NONE64
+  static constexpr int Q_M_TAG = Q_T_DL2 + NTT;             // [NMSG]
   static constexpr int Q_M_W = Q_M_TAG + C::NMSG;           // [NMSG] payload.w (rpc response tag)
   static constexpr int Q_RG_TAG = Q_M_W + C::NMSG;          // [NSOCK*NREG] registered receive tags
   static constexpr int Q_WL = Q_RG_TAG + C::NSOCK * C::NREG;  // [WQ*NNODE] workload per-node u64
@@ -237,6 +243,7 @@ struct Engine {
   MSIM_HD u32& t_c(int t) const { return w(L::W_T_C, t); }
   MSIM_HD u64& t_dl0(int t) const { return q(L::Q_T_DL0, t); }
   MSIM_HD u64& t_dl1(int t) const { return q(L::Q_T_DL1, t); }
+  MSIM_HD u64& t_dl2(int t) const { return q(L::Q_T_DL2, t); }
   MSIM_HD u32 t_gen(int t) const { return t_spawn(t) & 0xfffffu; }
   MSIM_HD u8& n_flags(int n) const { return b(L::B_N_FLAGS, n); }
   MSIM_HD u8& n_epoch(int n) const { return b(L::B_N_EPOCH, n); }
@@ -570,6 +577,7 @@ MSIM_NOUNROLL
     t_msg(t) = NONE8;
     if (C::NCONN) t_conn(t) = NONE8;
     if (C::USES_SPLIT) t_connhalf(t) = 3, t_handle(t) = NONE8;
+    if (C::USES_TIMEOUT) t_dl2(t) = NONE64;
     t_spawn(t) = idx;
     t_aw(t) = NONE32;
     u32 live = ++w(L::W_LIVE_TASKS);
@@ -1395,7 +1403,30 @@ MSIM_NOUNROLL
         }
         t_wait(t) = wt;
         if (pend) {
+          if (C::USES_TIMEOUT && t_dl2(t) != NONE64 && (st < W_CALL_SEND || st > W_CALL_DELAY)) {
+            u64 dl2 = t_dl2(t);
+            if (now < dl2) {
+              timer_push(dl2, timer_payload(TK_WAKE, t, t_gen(t)));
+              return POLL_PENDING;
+            }
+            // Elapsed: the future inside the timeout is dropped where it stands
+            if (st == W_RECV_RX) mbox_unregister(t);
+            if (t_rx(t) != NONE8) {
+              msg_free(t_rx(t));
+              t_rx(t) = NONE8;
+            }
+            if (t_msg(t) != NONE8) {
+              msg_free(t_msg(t));
+              t_msg(t) = NONE8;
+            }
+            if (sel_closed) w(L::W_CH_CLOSED_WAITER, t_conn(t)) = NONE32;
+            if (C::USES_CTRLC && st == W_CTRLC) w(L::W_N_CTRLC_WAITER, t_node(t)) = NONE32;  // Notified::drop leaves the list
+            t_wait(t) = W_NONE;
+            t_dl2(t) = NONE64;
+            ret = -3;
+          } else
           if (st < W_CALL_SEND || st > W_CALL_DELAY) return POLL_PENDING;
+          else {
           // timeout(): select_biased polls the call first, then the timeout's Sleep (time/mod.rs:128-140)
           u64 dl1 = t_dl1(t);
           if (now < dl1) {
@@ -1414,6 +1445,7 @@ MSIM_NOUNROLL
           }
           t_wait(t) = W_NONE;
           ret = CALL_TIMEOUT;
+          }
         }
       }
       // ---- run the state machine until its next request ----
@@ -1440,6 +1472,14 @@ MSIM_NOUNROLL
         case RQ_CH_RECV_OR_CLOSED:
           if (!C::USES_CLOSED) break;
           t_wait(t) = W_CH_RECV | WF_CLOSED;
+          break;
+        case RQ_TIMEOUT_BEGIN:
+          if (!C::USES_TIMEOUT) break;
+          t_dl2(t) = sleep_deadline(now + xa);
+          break;
+        case RQ_TIMEOUT_END:
+          if (!C::USES_TIMEOUT) break;
+          t_dl2(t) = NONE64;
           break;
         case RQ_SLEEP_RAW:
           t_dl0(t) = xa;

@@ -168,8 +168,8 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
     }
     case MSIM_WL_TONIC:
       if (P.n_nodes == 0) P.n_nodes = 7;
-      if (P.n_nodes < 2 || P.n_nodes > 7 || wl.p[2] > 7) {
-        if (err) *err = "tonic: need 1..6 client nodes, flags <= 7";
+      if (P.n_nodes < 2 || P.n_nodes > 7 || wl.p[2] > 15) {
+        if (err) *err = "tonic: need 1..6 client nodes, flags <= 15";
         return MSIM_EINVAL;
       }
       break;

@@ -267,7 +267,7 @@ cudaError_t launch_wl(const KernelArgs& a, dim3 grid, dim3 block, size_t smem, c
   return cudaGetLastError();
 }
 
-int state_bytes_of(uint32_t workload) {
+int state_bytes_of(uint32_t workload, uint64_t flags = 0) {
   switch (workload) {
     case MSIM_WL_SLEEP: return Layout<WL_Sleep::Caps>::BYTES;
     case MSIM_WL_PINGPONG: return Layout<WL_PingPong::Caps>::BYTES;
@@ -275,7 +275,7 @@ int state_bytes_of(uint32_t workload) {
     case MSIM_WL_CHAOS: return Layout<WL_Chaos::Caps>::BYTES;
     case MSIM_WL_STREAM: return Layout<WL_Stream::Caps>::BYTES;
     case MSIM_WL_ETCD: return Layout<WL_Etcd::Caps>::BYTES;
-    case MSIM_WL_TONIC: return Layout<WL_Tonic::Caps>::BYTES;
+    case MSIM_WL_TONIC: return (flags & 8) ? Layout<WL_TonicBig::Caps>::BYTES : Layout<WL_Tonic::Caps>::BYTES;
     case MSIM_WL_SIGNAL: return Layout<WL_Signal::Caps>::BYTES;
   }
   return -1;
@@ -317,7 +317,7 @@ struct msim_batch {
 namespace {
 
 int choose_geometry(msim_batch* b, uint64_t n) {
-  int bytes = state_bytes_of(b->wl.workload);
+  int bytes = state_bytes_of(b->wl.workload, b->wl.p[2]);
   if (bytes <= 0) return set_err(MSIM_EINVAL, "unknown workload");
   uint32_t s_max = (uint32_t)((b->max_smem - SMEM_HDR) / bytes);
   if (s_max == 0) return set_err(MSIM_EINVAL, "state block of one seed exceeds shared memory");
@@ -388,7 +388,9 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
     case MSIM_WL_CHAOS: e = launch_wl<WL_Chaos>(a, grid, block, b->smem, b->stream); break;
     case MSIM_WL_STREAM: e = launch_wl<WL_Stream>(a, grid, block, b->smem, b->stream); break;
     case MSIM_WL_ETCD: e = launch_wl<WL_Etcd>(a, grid, block, b->smem, b->stream); break;
-    case MSIM_WL_TONIC: e = launch_wl<WL_Tonic>(a, grid, block, b->smem, b->stream); break;
+    case MSIM_WL_TONIC:
+      e = (a.P.p[2] & 8) ? launch_wl<WL_TonicBig>(a, grid, block, b->smem, b->stream) : launch_wl<WL_Tonic>(a, grid, block, b->smem, b->stream);
+      break;
     case MSIM_WL_SIGNAL: e = launch_wl<WL_Signal>(a, grid, block, b->smem, b->stream); break;
     default: return set_err(MSIM_EINVAL, "unknown workload");
   }

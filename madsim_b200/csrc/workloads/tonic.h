@@ -17,23 +17,27 @@
 
 namespace msim {
 
-struct WL_Tonic {
+/// BIG: the capacities of the request-timeout schedule (flag 8): every pending poll inside time::timeout adds a
+/// timer that lingers 1-5 s, and `delay` response tasks live 10 s.
+template <bool BIG>
+struct WL_TonicT {
   enum : int { S_HANDLED = 0, S_CNT, S_ROUND, S_C, S_FAILURES, S_END };  // wl_s scalars
   enum : int { F_REPLIES = 0, F_STARTS, F_NFIELD };           // wl_w per client node
   struct Caps {
-    static constexpr int NT = 32, TQ = 64, NMSG = 2, NSOCK = 24, NREG = 1, NMBOX = 1, NNODE = 8, NPARK = 1;
+    static constexpr int NT = BIG ? 80 : 32, TQ = BIG ? 768 : 64, NMSG = 2, NSOCK = 24, NREG = 1, NMBOX = 1, NNODE = 8, NPARK = 1;
     static constexpr int WQ = 0, WW = F_NFIELD, WS = S_END;
     static constexpr bool USES_JOIN = false;
     static constexpr bool USES_KILL = true;
     static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
     static constexpr bool USES_CLOSED = true;   // does any task await Sender::closed()?
     static constexpr bool USES_SPLIT = true;    // does any task give the Sender half of its connection to another task?
-    static constexpr int NCONN = 32, NCQ = 4, NACC = 32;  // a client-streaming call queues header + 3 items at a slow server
+    static constexpr bool USES_TIMEOUT = true;   // does any task wrap awaits in time::timeout (beyond call_timeout)?
+    static constexpr int NCONN = BIG ? 64 : 32, NCQ = 4, NACC = 32;  // a client-streaming call queues header + 3 items at a slow server
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_RSP_BIDI, K_SENDER };
-  enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u };
+  enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u, DELAY_NAME = 0x616c6564u };
   enum : u32 { ST_OK = 0, ST_INVALID_ARGUMENT = 1, ST_EOF = 2, ST_TRAILER = 3 };
-  enum : u32 { SERVER_STREAMING = 1u << 31, CLIENT_STREAMING = 1u << 30, FLAG_RESTART_ONLY = 1, FLAG_STREAMING_MIX = 2, FLAG_SERVER_CRASH = 4 };
+  enum : u32 { SERVER_STREAMING = 1u << 31, CLIENT_STREAMING = 1u << 30, FLAG_RESTART_ONLY = 1, FLAG_STREAMING_MIX = 2, FLAG_SERVER_CRASH = 4, FLAG_TIMEOUTS = 8 };
   static constexpr u32 MAIN_KIND = K_MAIN;
   static constexpr u32 SERVER_ADDR = (IPK_NODE << 24) | (1u << 16) | 50051u;  // 10.0.0.1:50051
   /// NodeBuilder::init(|| tonic_client(c)) — what Handle::restart re-runs
@@ -49,7 +53,8 @@ struct WL_Tonic {
   /// client counts the failure, drops what the call held (`_task`, the connection, the endpoint) and goes on
   template <class E>
   static MSIM_HD int call_failed(E& e, int t, u32 code) {
-    if (!(e.P->p[2] & FLAG_SERVER_CRASH)) return panic(e, code);
+    const bool deadline = e.ret == -3 && code == 71 && e.t_a(t) == DELAY_NAME;  // what `delay` must end in
+    if (!deadline && !(e.P->p[2] & FLAG_SERVER_CRASH)) return panic(e, code);
     if (e.t_handle(t) != NONE8) {
       if (e.t_handle(t) & 0x80)
         e.join_detach(e.t_handle(t) & 0x7f);
@@ -59,7 +64,11 @@ struct WL_Tonic {
     }
     e.conn_drop_end(t);
     e.sock_unref(t);
-    e.wl_s(S_FAILURES)++;
+    e.t_dl2(t) = E::NONE64;  // the Timeout future is gone either way
+    if (deadline)
+      e.wl_w(F_REPLIES, e.t_node(t))++;
+    else
+      e.wl_s(S_FAILURES)++;
     if (code == 70) {
       e.t_pc(t) = 18;  // GreeterClient::connect again
     } else {
@@ -130,7 +139,7 @@ struct WL_Tonic {
         case K_MAIN * 32 + 8: {
           u32 replies = 0, starts = 0;
           for (u32 c = 0; c < n_clients; c++) replies += e.wl_w(F_REPLIES, 2 + c), starts += e.wl_w(F_STARTS, 2 + c);
-          if (e.wl_s(S_HANDLED) < replies) return panic(e, 74);
+          if (!(P.p[2] & FLAG_TIMEOUTS) && e.wl_s(S_HANDLED) < replies) return panic(e, 74);
           e.w(L::W_USER0) = replies;
           e.w(L::W_USER1) = starts;
           e.w(L::W_USER2) = e.wl_s(S_HANDLED);
@@ -171,6 +180,13 @@ struct WL_Tonic {
         // ---- tonic_response_task ----
         case K_RSP * 32 + 0:
           e.wl_s(S_HANDLED)++;
+          if (e.t_a(t) == DELAY_NAME) {  // AnotherGreeter::delay: sleep(10 s) inside rsp_future.await
+            e.t_pc(t) = 2;
+            e.xa = 10 * NS_PER_SEC;
+            return RQ_SLEEP_FOR;
+          }
+          // fallthrough
+        case K_RSP * 32 + 2:
           e.t_pc(t) = 1;
           if (e.t_a(t) == ERROR_NAME) {
             e.yb = ST_INVALID_ARGUMENT, e.yc = 0;
@@ -320,6 +336,12 @@ struct WL_Tonic {
         case K_CLIENT * 32 + 4:  // Grpc::unary / server_streaming -> connect_ep: Endpoint::connect
           e.t_a(t) = e.ret64 == 0 ? (u32)ERROR_NAME : (u32)NAME;
           e.t_c(t) = ((P.p[2] & FLAG_STREAMING_MIX) && e.ret64 >= 1 && e.ret64 <= 6) ? (u32)e.ret64 : 0u;  // 1..3: lots_of_replies, 4: lots_of_greetings, 5..6: bidi_hello
+          if ((P.p[2] & FLAG_TIMEOUTS) && e.t_c(t) == 0) {  // with_timeout (client.rs:246-258): unary calls only
+            u64 tmo = NS_PER_SEC;  // Endpoint::timeout(1 s)
+            if (e.ret64 == 7 || e.ret64 == 8) e.t_a(t) = DELAY_NAME;
+            if (e.ret64 == 8) tmo = 5 * NS_PER_SEC;  // Request::set_timeout overrides the channel's
+            e.t_dl2(t) = e.sleep_deadline(e.now + tmo);  // the Sleep is created now (time/mod.rs:128-140)
+          }
           e.t_pc(t) = 5;
           e.ya = mk_addr(IPK_UNSPEC, 0, 0);
           return RQ_BIND;
@@ -376,6 +398,8 @@ struct WL_Tonic {
           }
           e.conn_drop_end(t);  // rx, tx, then the last BindGuard reference
           e.sock_unref(t);
+          e.t_dl2(t) = E::NONE64;  // the call completed inside its timeout
+          if (e.t_a(t) == DELAY_NAME) return panic(e, 80);  // delay must end in DeadlineExceeded
           if (e.t_a(t) == ERROR_NAME) {
             if (st != ST_INVALID_ARGUMENT) return panic(e, 72);
           } else if (st != ST_OK || reply != NAME * 31u + node) {
@@ -481,5 +505,7 @@ struct WL_Tonic {
       }
   }
 };
+using WL_Tonic = WL_TonicT<false>;
+using WL_TonicBig = WL_TonicT<true>;
 
 }  // namespace msim

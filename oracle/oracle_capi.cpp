@@ -99,7 +99,7 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
         tp.rounds = wl->p[0];
         tp.think_ns = wl->p[1];
         tp.flags = u32(wl->p[2]);
-        if (tp.n_clients < 1 || tp.n_clients > 6 || tp.flags > 7) return MSIM_EINVAL;
+        if (tp.n_clients < 1 || tp.n_clients > 6 || tp.flags > 15) return MSIM_EINVAL;
         rt.block_on(wl_tonic_main(tp, &user));
         rt.teardown();
         break;

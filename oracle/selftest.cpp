@@ -536,6 +536,34 @@ static Async<Unit> tonic_server_crash_client(Runtime* rt, u64 server_node, Socke
   co_return {};
 }
 
+// ---- tonic-example/tests/test.rs:369-410 request_timeout ----
+static Async<Unit> tonic_timeout_client(SocketAddr server) {
+  co_await sleep(1 * SEC);
+  Payload q;
+  q.v[0] = TONIC_DELAY;  // AnotherGreeter::delay answers after 10 s
+  u64 t0 = now();
+  {
+    auto t = timeout(1 * SEC, tonic_unary(server, q));  // Endpoint::timeout(1 s)
+    auto r = co_await t;
+    CHECK(r.is_err());  // Code::DeadlineExceeded
+  }
+  CHECK(now() - t0 >= 1 * SEC && now() - t0 < 1 * SEC + 10 * MS);
+  t0 = now();
+  {
+    auto t = timeout(5 * SEC, tonic_unary(server, q));  // Request::set_timeout(5 s) overrides the channel's
+    auto r = co_await t;
+    CHECK(r.is_err());
+  }
+  CHECK(now() - t0 >= 5 * SEC && now() - t0 < 5 * SEC + 10 * MS);
+  q.v[0] = TONIC_NAME;
+  {
+    auto t = timeout(1 * SEC, tonic_unary(server, q));
+    auto r = co_await t;
+    CHECK(r.is_ok() && r.ok->is_ok());  // a prompt call is untouched by the timeout
+  }
+  co_return {};
+}
+
 int main() {
   run_case("task::spawn_in_block_on", [] {
     Runtime rt;
@@ -749,6 +777,17 @@ int main() {
     auto st = std::make_shared<TonicStats>();
     server.spawn(tonic_serve(a, st));
     auto h = cl.spawn(tonic_server_crash_client(&rt, server.id(), a));
+    rt.block_on(join_unwrap(std::move(h)));
+    rt.teardown();
+  });
+  run_case("tonic::request_timeout (tests/test.rs:369-410)", [] {
+    Runtime rt;
+    SocketAddr a{ip4(10, 0, 0, 1), 50051};
+    auto server = rt.create_node().ip(a.ip).build();
+    auto cl = rt.create_node().ip(ip4(10, 0, 0, 2)).build();
+    auto st = std::make_shared<TonicStats>();
+    server.spawn(tonic_serve(a, st));
+    auto h = cl.spawn(tonic_timeout_client(a));
     rt.block_on(join_unwrap(std::move(h)));
     rt.teardown();
   });

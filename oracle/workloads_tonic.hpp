@@ -25,7 +25,8 @@ constexpr u32 TONIC_ERROR = 0x6f727265u;  // "erro"
 enum : u32 { TONIC_OK = 0, TONIC_INVALID_ARGUMENT = 1, TONIC_EOF = 2, TONIC_TRAILER = 3 };
 constexpr u32 TONIC_SERVER_STREAMING = 1u << 31;  // the `server_streaming: bool` of the first message (client.rs:128)
 constexpr u32 TONIC_CLIENT_STREAMING = 1u << 30;  // the first message is the stream-start header Box<()> (client.rs:170-176)
-enum : u32 { TONIC_RESTART_ONLY = 1, TONIC_STREAMING_MIX = 2, TONIC_SERVER_CRASH = 4 };
+enum : u32 { TONIC_RESTART_ONLY = 1, TONIC_STREAMING_MIX = 2, TONIC_SERVER_CRASH = 4, TONIC_TIMEOUTS = 8 };
+constexpr u32 TONIC_DELAY = 0x616c6564u;  // "dela": AnotherGreeter::delay sleeps 10 s before it answers (lib.rs:36-43)
 
 struct TonicParams {
   u32 n_clients = 6;
@@ -33,6 +34,9 @@ struct TonicParams {
   u64 think_ns = 100 * MS;
   // 4: halfway through, the supervisor kills the SERVER (tests/test.rs:233-278 server_crash): calls in flight end in
   //    "broken pipe", later ones are refused; the clients count failures instead of unwrapping
+  // 8: the channel has a 1 s timeout (Endpoint::timeout, tests/test.rs:369-410 request_timeout): unary calls run
+  //    inside time::timeout; picks 7 / 8 call `delay` with the channel's 1 s / a 5 s request timeout and must
+  //    come back DeadlineExceeded (streaming calls are not wrapped here)
   u32 flags = 0;  // 1: the supervisor never kills, only restarts (client_crash as written); 2: clients also make
                   // server-streaming calls (lots_of_replies), sometimes dropping the response stream at once
 };
@@ -46,6 +50,7 @@ inline u32 tonic_reply_for(u32 name, SocketAddr remote) { return name * 31u + (r
 inline Async<Unit> tonic_response_task(Connection conn, Payload request, std::shared_ptr<TonicStats> st) {
   st->handled++;
   u32 name = request.v[0];
+  if (name == TONIC_DELAY) co_await sleep(10 * SEC);  // inside rsp_future.await, before the closed() race
   Payload rsp;
   if (name == TONIC_ERROR) {  // Err(Status::invalid_argument("error!")): sent without the closed() race
     rsp.v[0] = TONIC_INVALID_ARGUMENT;
@@ -357,7 +362,28 @@ inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::sh
       co_await sleep(p.think_ns);
       continue;
     }
-    auto r = co_await tonic_unary(server, q);
+    u64 tmo = 0;
+    if (p.flags & TONIC_TIMEOUTS) {
+      tmo = 1 * SEC;
+      if (pick == 7 || pick == 8) q.v[0] = TONIC_DELAY;
+      if (pick == 8) tmo = 5 * SEC;  // Request::set_timeout overrides the channel's
+    }
+    Result<Payload> r = Result<Payload>::Error(Err::Elapsed);
+    if (tmo) {  // with_timeout (client.rs:246-258): the Timeout future is consumed by the await
+      auto t = timeout(tmo, tonic_unary(server, q));
+      auto tr = co_await t;
+      if (tr.is_ok()) r = std::move(*tr.ok);
+    } else {
+      r = co_await tonic_unary(server, q);
+    }
+    if (q.v[0] == TONIC_DELAY) {
+      if (r.is_ok()) panic("delay must end in DeadlineExceeded", 80);
+      if (r.err == Err::Elapsed) {
+        st->replies[c]++;
+        co_await sleep(p.think_ns);
+        continue;
+      }
+    }
     if (r.is_err()) {
       if (!tolerant) panic("say_hello failed", 71);
       st->failures++;
@@ -403,7 +429,7 @@ inline Async<u32> wl_tonic_main(TonicParams p, std::array<u32, 4>* user) {
   co_await sleep(1 * SEC);
   u32 replies = 0, starts = 0;
   for (u32 c = 0; c < p.n_clients; c++) replies += st->replies[c], starts += st->starts[c];
-  if (st->handled < replies) panic("more replies than requests handled", 74);
+  if (!(p.flags & TONIC_TIMEOUTS) && st->handled < replies) panic("more replies than requests handled", 74);
   (*user)[0] = replies;
   (*user)[1] = starts;
   (*user)[2] = st->handled;

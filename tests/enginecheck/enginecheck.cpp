@@ -62,7 +62,9 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
     case MSIM_WL_CHAOS: return run_wl<WL_Chaos>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_STREAM: return run_wl<WL_Stream>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_ETCD: return run_wl<WL_Etcd>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
-    case MSIM_WL_TONIC: return run_wl<WL_Tonic>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
+    case MSIM_WL_TONIC:
+      return (P.p[2] & 8) ? run_wl<WL_TonicBig>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr)
+                          : run_wl<WL_Tonic>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_SIGNAL: return run_wl<WL_Signal>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
   }
   return MSIM_EINVAL;

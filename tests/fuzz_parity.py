@@ -42,7 +42,7 @@ def rand_wl(rnd):
                              lease_admin=rnd.random() < 0.5)
     if k == "tonic":
         return Workload.tonic(clients=rnd.randint(1, 6), rounds=rnd.randint(0, 12), think_ns=rnd.choice([0, 10 * MS, 100 * MS]),
-                              restart_only=rnd.random() < 0.3, streaming=rnd.random() < 0.5, server_crash=rnd.random() < 0.4)
+                              restart_only=rnd.random() < 0.3, streaming=rnd.random() < 0.5, server_crash=rnd.random() < 0.4, timeouts=rnd.random() < 0.3)
     return Workload.signal(rounds=rnd.randint(0, 10), period_ms=rnd.choice([1, 10, 100]), behavior=rnd.randint(0, 2), catch=rnd.random() < 0.6)
 
 

@@ -38,6 +38,7 @@ CASES = {
     "tonic_cfg5_streaming": (dict(), dict(kind="tonic", streaming=True), list(range(6))),
     "etcd_cfg4_lease_admin": (dict(packet_loss_rate=0.1), dict(kind="etcd", lease_admin=True, timeout_rate=0.125), list(range(6))),
     "tonic_server_crash": (dict(), dict(kind="tonic", streaming=True, server_crash=True), list(range(6))),
+    "tonic_request_timeouts": (dict(), dict(kind="tonic", streaming=True, timeouts=True), list(range(4))),
     "raft_cfg3_loss5": (dict(packet_loss_rate=0.05), dict(kind="raft", faults=7), list(range(4))),
 }
 

@@ -65,6 +65,8 @@ CASES = [
     ("tonic-server-streaming-restart-only", m.Config(), m.Workload.tonic(streaming=True, restart_only=True, clients=2, rounds=16), 0, 64),
     ("tonic-server-crash-streaming", m.Config(), m.Workload.tonic(streaming=True, server_crash=True), 0, 96),
     ("tonic-server-crash-buggify", m.Config(buggify=True), m.Workload.tonic(server_crash=True, rounds=8, think_ns=0), 0, 64),
+    ("tonic-request-timeouts", m.Config(), m.Workload.tonic(timeouts=True), 0, 64),
+    ("tonic-request-timeouts-everything", m.Config(buggify=True), m.Workload.tonic(streaming=True, timeouts=True, server_crash=True, rounds=8), 0, 64),
     ("tonic-buggify-slow-server", m.Config(buggify=True), m.Workload.tonic(clients=3, rounds=5), 0, 160),
     # time::interval + MissedTickBehavior, signal::ctrl_c, Handle::send_ctrl_c
     ("signal-burst-catch", m.Config(), m.Workload.signal(behavior=0, rounds=12), 0, 100),

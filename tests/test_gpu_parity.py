@@ -98,6 +98,8 @@ CASES = [
     ("tonic-server-streaming-slow-links", m.Config(send_latency_ns=(1 * m.MS, 900 * m.MS)), m.Workload.tonic(streaming=True, think_ns=0), 0, 300),
     ("tonic-server-crash-streaming", m.Config(), m.Workload.tonic(streaming=True, server_crash=True), 0, 400),
     ("tonic-server-crash-buggify", m.Config(buggify=True), m.Workload.tonic(server_crash=True, rounds=8, think_ns=0), 0, 200),
+    ("tonic-request-timeouts", m.Config(), m.Workload.tonic(timeouts=True), 0, 200),
+    ("tonic-request-timeouts-everything", m.Config(buggify=True), m.Workload.tonic(streaming=True, timeouts=True, server_crash=True, rounds=8), 0, 200),
     ("tonic-buggify-slow-server", m.Config(buggify=True), m.Workload.tonic(clients=3, rounds=5), 0, 200),
     ("tonic-16-rounds-slow-links", m.Config(send_latency_ns=(1 * m.MS, 400 * m.MS)), m.Workload.tonic(rounds=16, think_ns=0), 0, 200),
     ("signal-interval-burst-ctrlc-caught", m.Config(), m.Workload.signal(behavior=0, rounds=12), 0, 500),

@@ -181,6 +181,10 @@ int msim_device_count(void);
 /* Runtime::with_seed_and_config for a whole batch (runtime/mod.rs:53-69): one
  * batch = many Runtimes that share a config.  device = CUDA ordinal.          */
 int msim_config_default(msim_config* cfg);
+/* `impl FromStr for Config` (config.rs:28-35): parse the TOML of a MADSIM_TEST_CONFIG file (builder.rs:82-88) —
+ * `[net] packet_loss_rate = .., send_latency = { start = { secs, nanos }, end = { secs, nanos } }`, `[tcp]` —
+ * over the defaults; time_limit_ns and buggify are not part of the file and come back 0.                      */
+int msim_config_from_toml(const char* text, msim_config* cfg);
 int msim_batch_create(const msim_config* cfg, int device, msim_batch** out);
 void msim_batch_destroy(msim_batch* b);
 
@@ -188,7 +192,10 @@ void msim_batch_destroy(msim_batch* b);
 int msim_workload_default(uint32_t workload, msim_workload_desc* out);
 int msim_workload_load(msim_batch* b, const msim_workload_desc* w);
 
-/* Launch tuning: seeds per CTA, active lanes per warp (0 = auto).              */
+/* Launch tuning: seeds per CTA, active lanes per warp (0 = auto).  lanes_per_warp | MSIM_GEOMETRY_LOCKSTEP sends
+ * run-to-completion launches with >= 2 lanes through the lock-step kernel (a warp's lanes walk the phases of the
+ * event step together: profiles/r2a_*; the default lets the lanes of a warp run free).                          */
+#define MSIM_GEOMETRY_LOCKSTEP 0x100u
 int msim_batch_set_geometry(msim_batch* b, uint32_t seeds_per_cta, uint32_t lanes_per_warp);
 /* Optional: run on the caller's stream (a cudaStream_t, e.g. torch's current). */
 int msim_batch_set_stream(msim_batch* b, void* cuda_stream);
@@ -214,6 +221,12 @@ int msim_batch_trace_hash(msim_batch* b, uint64_t* hash /*n_seeds*/);
  * {ev_pop, ev_fire, draws, n_pass, n_fail, n_unfinished, first_fail_seed, n_seeds} followed by
  * u32 fail_bitmap[ceil(n/32)].  Enqueued on the batch's stream.                              */
 int msim_batch_summarize_device(msim_batch* b, void* d_out, size_t bytes);
+/* The same for one shard of an N-GPU sweep over seeds seed_base..seed_base+n_total, shaped so that ONE sum
+ * all-reduce of the buffer over the ranks gives the global result: u64 counters[8] (slot 6 unused), u64
+ * first_fail_of_rank[world] (own slot: first failing seed or UINT64_MAX; others 0), u32 bitmap[ceil(n_total/32)]
+ * holding this shard's bits at their GLOBAL position.  A rank with an empty shard calls it without having run.   */
+int msim_batch_summarize_sharded(msim_batch* b, void* d_out, size_t bytes, uint32_t rank, uint32_t world,
+                                 uint64_t seed_base, uint64_t n_total);
 /* bytes of per-seed device state of a workload (capacity table in DESIGN.md)                */
 int msim_workload_state_bytes(uint32_t workload);
 /* device pointer of the result array (msim_seed_result[n_seeds]) for zero-copy consumers (torch / NCCL) */
@@ -223,6 +236,13 @@ int msim_batch_results_device(msim_batch* b, void** dptr, size_t* bytes);
  * MADSIM_TEST_SEED, runtime/mod.rs:205-210).  *n = records produced (may exceed cap). */
 int msim_batch_trace(msim_batch* b, uint64_t seed, msim_trace_rec* out, size_t cap, size_t* n,
                      msim_seed_result* result);
+
+/* The log of Runtime::check_determinism (runtime/mod.rs:178-202, rand.rs:64-89) for ONE seed (device replay): one
+ * byte per GlobalRng::with call — every gen_range / gen_bool / random() of the runtime and of the program —
+ * = (next u8 of a clone of the rng) ^ (xor of the bytes of the elapsed nanos).  Two runs of a deterministic program
+ * give equal logs; the first differing index is the first diverging draw.  *n = bytes produced (may exceed cap). */
+int msim_batch_determinism_log(msim_batch* b, uint64_t seed, uint8_t* out, size_t cap, size_t* n,
+                               msim_seed_result* result);
 
 #ifdef __cplusplus
 }

@@ -7,19 +7,25 @@
 //       ::with_seed_and_config(seed, cfg)    :53-69
 //       ::block_on(workload)                 :127-130   (one seed; panics ⇒ exception with the seed note)
 //       ::set_time_limit(d)                  :132-137
-//       ::check_determinism(seed, cfg, wl)   :178-202   (run twice, compare the traces)
+//       ::check_determinism(seed, cfg, wl)   :178-202   (run twice, compare the per-draw rng log of rand.rs:64-89)
 //   madsim::runtime::Builder               madsim/src/sim/runtime/builder.rs:7-162
-//       ::from_env()                         :64-118    MADSIM_TEST_{SEED,NUM,JOBS,TIME_LIMIT,CHECK_DETERMINISM}
-//       ::run(workload)                      :121-162   seeds seed..seed+count on the GPU; the first
+//       ::from_env()                         :64-118    MADSIM_TEST_{SEED,NUM,JOBS,CONFIG,TIME_LIMIT,CHECK_DETERMINISM}
+//                                                        with the reference's defaults (time-based seed, count >= 2
+//                                                        under the check)
+//       ::run(workload)                      :121-162   seeds seed..seed+count on the GPU(s); the first
 //                                                        failing seed is re-raised with the reference's note
 //
 // A `Workload` is the registered program that stands where the reference takes an async closure
 // (arbitrary futures cannot run on a GPU; see include/msim_b200.h MSIM_WL_*).
 #pragma once
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
-#include <stdexcept>
 #include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
@@ -54,6 +60,16 @@ struct Config {
     uint64_t send_latency_lo_ns = 1000000, send_latency_hi_ns = 10000000;  // 1 ms..10 ms
   } net;
   bool buggify = false;
+  /// `impl FromStr for Config` (config.rs:28-35): TOML text of a MADSIM_TEST_CONFIG file
+  static Config from_toml(const std::string& text) {
+    msim_config c{};
+    check(msim_config_from_toml(text.c_str(), &c));
+    Config out;
+    out.net.packet_loss_rate = c.packet_loss_rate;
+    out.net.send_latency_lo_ns = c.send_latency_lo_ns;
+    out.net.send_latency_hi_ns = c.send_latency_hi_ns;
+    return out;
+  }
   msim_config to_c(uint64_t time_limit_ns = 0) const {
     msim_config c{};
     c.packet_loss_rate = net.packet_loss_rate;
@@ -174,12 +190,26 @@ class Runtime {
     if (r.status != MSIM_ST_PASS) throw SimulationFailure(seed_, r.status, r.fail_code);
     return r;
   }
-  /// Runtime::check_determinism: run the seed twice and compare the event traces
-  static msim_seed_result check_determinism(uint64_t seed, Config cfg, const Workload& wl) {
-    Runtime rt(seed, std::move(cfg));
-    msim_seed_result a = rt.block_on(wl), b2 = rt.block_on(wl);
-    if (a.trace_hash != b2.trace_hash || a.draws != b2.draws) throw std::runtime_error("non-determinism detected");
-    return a;
+  /// Runtime::check_determinism (runtime/mod.rs:178-202): the first run records one byte per GlobalRng::with call,
+  /// (next u8 of a clone of the rng) ^ fold(elapsed); the second run must reproduce every byte
+  static msim_seed_result check_determinism(uint64_t seed, Config cfg, const Workload& wl, int device = 0) {
+    Batch b(cfg, 0, device);
+    check(msim_workload_load(b.get(), &wl.desc));
+    auto log_of = [&](msim_seed_result* r) {
+      size_t n = 0;
+      check(msim_batch_determinism_log(b.get(), seed, nullptr, 0, &n, r));
+      std::vector<uint8_t> log(n);
+      check(msim_batch_determinism_log(b.get(), seed, log.data(), n, &n, r));
+      return log;
+    };
+    msim_seed_result r1{}, r2{};
+    std::vector<uint8_t> first = log_of(&r1);
+    if (r1.status != MSIM_ST_PASS) throw SimulationFailure(seed, r1.status, r1.fail_code);
+    std::vector<uint8_t> second = log_of(&r2);
+    for (size_t i = 0; i < first.size() || i < second.size(); i++)
+      if (i >= first.size() || i >= second.size() || first[i] != second[i])
+        throw std::runtime_error("non-determinism detected at draw " + std::to_string(i));
+    return r2;
   }
 
  private:
@@ -200,25 +230,64 @@ struct Builder {
 
   static Builder from_env() {
     Builder b;
-    if (const char* s = std::getenv("MADSIM_TEST_SEED")) b.seed = std::strtoull(s, nullptr, 10);
-    if (const char* s = std::getenv("MADSIM_TEST_NUM")) b.count = std::strtoull(s, nullptr, 10);
+    if (const char* s = std::getenv("MADSIM_TEST_SEED"))
+      b.seed = std::strtoull(s, nullptr, 10);
+    else  // builder.rs:69-74: the current time in nanoseconds
+      b.seed = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
     if (const char* s = std::getenv("MADSIM_TEST_JOBS")) b.jobs = std::strtoull(s, nullptr, 10);
+    if (const char* s = std::getenv("MADSIM_TEST_CONFIG")) {
+      std::ifstream f(s);
+      if (!f) throw std::runtime_error("failed to read config file");
+      std::stringstream ss;
+      ss << f.rdbuf();
+      b.config = Config::from_toml(ss.str());
+    }
+    if (const char* s = std::getenv("MADSIM_TEST_NUM")) b.count = std::strtoull(s, nullptr, 10);
     if (const char* s = std::getenv("MADSIM_TEST_TIME_LIMIT")) b.time_limit_ns = uint64_t(std::strtod(s, nullptr) * 1e9);
     b.check = std::getenv("MADSIM_TEST_CHECK_DETERMINISM") != nullptr;
+    if (b.check && b.count < 2) b.count = 2;
     return b;
   }
-  /// seeds seed..seed+count; throws SimulationFailure for the FIRST failing seed (builder.rs:155-159)
+  /// seeds seed..seed+count; throws SimulationFailure for the FIRST failing seed (builder.rs:155-159).  Under `check`
+  /// only `seed` runs, through Runtime::check_determinism (builder.rs:126-128).  `jobs` > 1 shards the range over that
+  /// many GPUs: every launch is enqueued before the first result is read.
   RunOutput run(const Workload& wl, int device = 0) const {
-    RunOutput o = run_seeds(config, time_limit_ns, wl, seed, count, device);
     if (check) {
-      RunOutput o2 = run_seeds(config, time_limit_ns, wl, seed, count, device);
-      for (uint64_t i = 0; i < count; i++)
-        if (o.results[i].trace_hash != o2.results[i].trace_hash)
-          throw std::runtime_error("non-determinism detected (seed " + std::to_string(seed + i) + ")");
+      RunOutput o;
+      o.results.push_back(Runtime::check_determinism(seed, config, wl, device));
+      return o;
     }
-    if (o.stats.n_fail) {
-      const msim_seed_result& r = o.results[o.stats.first_fail_seed - seed];
-      throw SimulationFailure(o.stats.first_fail_seed, r.status, r.fail_code);
+    int n_dev = msim_device_count();
+    if (n_dev < 0) throw MsimError(n_dev, msim_last_error());
+    uint64_t shards = jobs < 1 ? 1 : jobs;
+    if (shards > (uint64_t)n_dev) shards = n_dev;
+    if (shards > count) shards = count ? count : 1;
+    std::vector<std::unique_ptr<Batch>> bs;
+    std::vector<std::pair<uint64_t, uint64_t>> ranges;
+    uint64_t first = seed;
+    for (uint64_t j = 0; j < shards; j++) {
+      uint64_t n = count / shards + (j < count % shards ? 1 : 0);
+      bs.emplace_back(new Batch(config, time_limit_ns, shards > 1 ? device + (int)j : device));
+      madsim::check(msim_workload_load(bs.back()->get(), &wl.desc));
+      madsim::check(msim_batch_run_async(bs.back()->get(), first, n, 0));
+      ranges.emplace_back(first, n);
+      first += n;
+    }
+    RunOutput o;
+    for (uint64_t j = 0; j < shards; j++) {
+      std::vector<msim_seed_result> part(ranges[j].second);
+      msim_stats st{};
+      madsim::check(msim_batch_results(bs[j]->get(), part.data(), nullptr, &st));
+      if (st.n_fail) {
+        const msim_seed_result& r = part[st.first_fail_seed - ranges[j].first];
+        throw SimulationFailure(st.first_fail_seed, r.status, r.fail_code);
+      }
+      o.results.insert(o.results.end(), part.begin(), part.end());
+      o.stats.n_seeds += st.n_seeds, o.stats.ev_pop += st.ev_pop, o.stats.ev_fire += st.ev_fire, o.stats.draws += st.draws;
+      o.stats.n_pass += st.n_pass, o.stats.n_unfinished += st.n_unfinished;
+      o.stats.first_fail_seed = ~0ull;
+      if (st.kernel_ms > o.stats.kernel_ms) o.stats.kernel_ms = st.kernel_ms;
+      o.stats.launches += st.launches;
     }
     return o;
   }

@@ -13,13 +13,16 @@ from .api import (  # noqa: F401
     Batch,
     Builder,
     Config,
+    NonDeterminism,
     SimulationFailure,
+    check_determinism,
     Workload,
     device_count,
     state_bytes,
 )
 from ._native import (  # noqa: F401
     EV_NAMES,
+    GEOMETRY_LOCKSTEP,
     RAFT_FAULT_CLOCK_JUMP,
     RAFT_FAULT_CLOG_LINK,
     RAFT_FAULT_CLOG_NODE,

@@ -18,6 +18,7 @@ WL_SLEEP, WL_PINGPONG, WL_RAFT, WL_CHAOS, WL_STREAM, WL_ETCD, WL_TONIC, WL_SIGNA
 EV_NAMES = {1: "POLL", 2: "DROP", 3: "PARK", 4: "SKIP", 5: "WAKE", 6: "DELIVER", 7: "RESTART"}
 STATUS_NAMES = {0: "RUNNING", 1: "PASS", 2: "FAIL_ASSERT", 3: "FAIL_DEADLOCK", 4: "FAIL_TIME_LIMIT", 5: "FAIL_CAPACITY"}
 RAFT_FAULT_CLOG_NODE, RAFT_FAULT_CLOG_LINK, RAFT_FAULT_CLOCK_JUMP = 1, 2, 4
+GEOMETRY_LOCKSTEP = 0x100
 
 
 class MsimConfig(C.Structure):
@@ -82,6 +83,7 @@ PROTOTYPES = {
     "msim_last_error": (C.c_char_p, []),
     "msim_device_count": (C.c_int, []),
     "msim_config_default": (C.c_int, [C.POINTER(MsimConfig)]),
+    "msim_config_from_toml": (C.c_int, [C.c_char_p, C.POINTER(MsimConfig)]),
     "msim_batch_create": (C.c_int, [C.POINTER(MsimConfig), C.c_int, C.POINTER(C.c_void_p)]),
     "msim_batch_destroy": (None, [C.c_void_p]),
     "msim_workload_default": (C.c_int, [C.c_uint32, C.POINTER(MsimWorkloadDesc)]),
@@ -95,9 +97,15 @@ PROTOTYPES = {
     "msim_batch_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(MsimStats)]),
     "msim_batch_trace_hash": (C.c_int, [C.c_void_p, C.c_void_p]),
     "msim_batch_summarize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "msim_batch_summarize_sharded": (
+        C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64]),
     "msim_workload_state_bytes": (C.c_int, [C.c_uint32]),
     "msim_batch_results_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "msim_batch_trace": (
+        C.c_int,
+        [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(MsimSeedResult)],
+    ),
+    "msim_batch_determinism_log": (
         C.c_int,
         [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(MsimSeedResult)],
     ),

@@ -49,6 +49,14 @@ class Config:
     time_limit_ns: int = 0
     buggify: bool = False
 
+    @staticmethod
+    def from_toml(text: str) -> "Config":
+        """`impl FromStr for Config` (config.rs:28-35): the TOML of a MADSIM_TEST_CONFIG file, parsed by the library
+        (msim_config_from_toml) — `[net] packet_loss_rate, send_latency = { start = {secs, nanos}, end = {..} }`."""
+        c = N.MsimConfig()
+        N.check(N.load().msim_config_from_toml(text.encode(), C.byref(c)))
+        return Config(c.packet_loss_rate, (c.send_latency_lo_ns, c.send_latency_hi_ns), 0, False)
+
     def to_c(self) -> N.MsimConfig:
         return N.MsimConfig(
             float(self.packet_loss_rate),
@@ -237,6 +245,25 @@ class Batch:
         rec = np.frombuffer(bytes(r), dtype=SEED_RESULT_DTYPE)[0]
         return buf[: min(n.value, cap)].copy(), rec, n.value
 
+    def determinism_log(self, seed: int, cap: int = 1 << 22):
+        """The log Runtime::check_determinism records (rand.rs:64-89): one byte per GlobalRng::with call of one seed
+        (device replay).  → (uint8 ndarray, result record)"""
+        buf = np.empty(cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        r = N.MsimSeedResult()
+        N.check(self._lib.msim_batch_determinism_log(self._h, seed, buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(r)))
+        if n.value > cap:
+            return self.determinism_log(seed, n.value)
+        return buf[: n.value].copy(), np.frombuffer(bytes(r), dtype=SEED_RESULT_DTYPE)[0]
+
+    def summarize_sharded_into(self, device_ptr: int, nbytes: int, rank: int, world: int, seed_base: int, n_total: int):
+        """This shard's summary in the one-all-reduce layout (msim_batch_summarize_sharded)."""
+        N.check(self._lib.msim_batch_summarize_sharded(self._h, C.c_void_p(device_ptr), nbytes, rank, world, seed_base, n_total))
+
+    @staticmethod
+    def sharded_summary_nbytes(n_total: int, world: int) -> int:
+        return 8 * (8 + world) + 4 * ((n_total + 31) // 32)
+
     def summarize_into(self, device_ptr: int, nbytes: int):
         """Device-side summary (counters + fail bitmap) into caller-owned device memory."""
         N.check(self._lib.msim_batch_summarize_device(self._h, C.c_void_p(device_ptr), nbytes))
@@ -262,51 +289,97 @@ def device_count() -> int:
     return n
 
 
+class NonDeterminism(AssertionError):
+    """The panic of GlobalRng's check mode (rand.rs:79-84)."""
+
+
+def check_determinism(seed: int, config: Config, workload: Workload, device: int = 0):
+    """Runtime::check_determinism (runtime/mod.rs:178-202): run `seed` twice; the first run records one byte per
+    GlobalRng::with call — (next u8 of a clone of the rng) ^ fold(elapsed) —, the second run must reproduce every
+    byte.  Raises NonDeterminism naming the first diverging draw; a failing seed raises SimulationFailure."""
+    with Batch(config, device) as b:
+        b.load(workload)
+        log, r1 = b.determinism_log(seed)
+        if r1["status"] != N.ST_PASS:
+            raise SimulationFailure(seed, int(r1["status"]), int(r1["fail_code"]))
+        chk, r2 = b.determinism_log(seed)
+    n = min(len(log), len(chk))
+    bad = np.nonzero(log[:n] != chk[:n])[0]
+    if len(bad) or len(log) != len(chk):
+        i = int(bad[0]) if len(bad) else n
+        raise NonDeterminism(f"non-determinism detected at draw {i} of seed {seed}")
+    return r2
+
+
 @dataclass
 class Builder:
     """runtime/builder.rs:7-162: the many-seed test driver (`#[madsim::test]`)."""
 
     seed: int = 0
     count: int = 1
-    jobs: int = 1  # MADSIM_TEST_JOBS: here the number of GPUs a sweep may use (informational)
+    jobs: int = 1  # MADSIM_TEST_JOBS: the reference's worker threads; here the number of GPUs the sweep is sharded over
     config: Config = field(default_factory=Config)
     time_limit_s: float | None = None
     check: bool = False
 
     @staticmethod
     def from_env() -> "Builder":
-        """Same environment variables as builder.rs:64-118."""
+        """The environment variables, defaults and rules of builder.rs:64-118: an unset MADSIM_TEST_SEED is the
+        current time in nanoseconds, MADSIM_TEST_CONFIG names a TOML file, and under
+        MADSIM_TEST_CHECK_DETERMINISM the count is at least 2."""
+        import time
+
         b = Builder()
         env = os.environ
-        if "MADSIM_TEST_SEED" in env:
-            b.seed = int(env["MADSIM_TEST_SEED"])
-        if "MADSIM_TEST_NUM" in env:
-            b.count = int(env["MADSIM_TEST_NUM"])
+        b.seed = int(env["MADSIM_TEST_SEED"]) if "MADSIM_TEST_SEED" in env else time.time_ns() & ((1 << 64) - 1)
         if "MADSIM_TEST_JOBS" in env:
             b.jobs = int(env["MADSIM_TEST_JOBS"])
+        if "MADSIM_TEST_CONFIG" in env:
+            with open(env["MADSIM_TEST_CONFIG"]) as f:
+                b.config = Config.from_toml(f.read())
+        if "MADSIM_TEST_NUM" in env:
+            b.count = int(env["MADSIM_TEST_NUM"])
         if "MADSIM_TEST_TIME_LIMIT" in env:
             b.time_limit_s = float(env["MADSIM_TEST_TIME_LIMIT"])
         b.check = "MADSIM_TEST_CHECK_DETERMINISM" in env
+        if b.check:
+            b.count = max(b.count, 2)
         return b
 
     def run(self, workload: Workload, device: int = 0):
-        """Run seeds seed..seed+count; raise SimulationFailure for the first failing seed
-        (builder.rs:129-159).  With `check`, every seed is run twice and the traces compared
-        (Runtime::check_determinism, runtime/mod.rs:178-202)."""
+        """Run seeds seed..seed+count; raise SimulationFailure for the first failing seed (builder.rs:129-159).
+        With `check`, Runtime::check_determinism(seed) instead — the first seed only, exactly as builder.rs:126-128.
+        `jobs` > 1 shards the range contiguously over that many GPUs (all launches are enqueued before the first
+        result is read; the reference's jobs are OS threads, runtime/builder.rs:134-150)."""
         cfg = self.config
+        if self.check:
+            return check_determinism(self.seed, cfg, workload, device), None
         if self.time_limit_s is not None:
             cfg = Config(cfg.packet_loss_rate, cfg.send_latency_ns, int(self.time_limit_s * 1e9), cfg.buggify)
-        with Batch(cfg, device) as b:
-            b.load(workload)
-            b.run(self.seed, self.count)
-            res, bitmap, stats = b.results()
-            if self.check:
-                b.run(self.seed, self.count)
-                res2, _, _ = b.results()
-                if not np.array_equal(res["trace_hash"], res2["trace_hash"]):
-                    bad = int(np.nonzero(res["trace_hash"] != res2["trace_hash"])[0][0])
-                    raise AssertionError(f"non-determinism detected (seed {self.seed + bad})")
-        if stats["n_fail"]:
-            i = int(stats["first_fail_seed"] - self.seed)
-            raise SimulationFailure(self.seed + i, int(res["status"][i]), int(res["fail_code"][i]))
-        return res, stats
+        from .dist import shard
+
+        jobs = max(1, min(int(self.jobs), device_count(), self.count))
+        batches = []
+        try:
+            for j in range(jobs):
+                first, n = shard(self.seed, self.count, j, jobs)
+                b = Batch(cfg, device + j if jobs > 1 else device).load(workload)
+                batches.append((first, b))
+                b.run(first, n, sync=False)
+            parts, stats = [], None
+            for first, b in batches:
+                res, bitmap, st = b.results()
+                if st["n_fail"]:
+                    i = int(st["first_fail_seed"] - first)
+                    raise SimulationFailure(first + i, int(res["status"][i]), int(res["fail_code"][i]))
+                parts.append(res)
+                if stats is None:
+                    stats = dict(st)
+                else:
+                    for k in ("n_seeds", "ev_pop", "ev_fire", "draws", "n_pass", "n_fail", "n_unfinished", "launches"):
+                        stats[k] += st[k]
+                    stats["kernel_ms"] = max(stats["kernel_ms"], st["kernel_ms"])
+        finally:
+            for _, b in batches:
+                b.close()
+        return np.concatenate(parts), stats

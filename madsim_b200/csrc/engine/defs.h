@@ -82,7 +82,7 @@ constexpr u64 NS_PER_MS = 1000000ull;
 constexpr u64 NS_PER_SEC = 1000000000ull;
 
 // ---- poll results ----
-enum : int { POLL_PENDING = 0, POLL_READY = 1, POLL_PANIC = 2, POLL_ADVANCE = 3 };
+enum : int { POLL_PENDING = 0, POLL_READY = 1, POLL_PANIC = 2, POLL_ADVANCE = 3, POLL_AGAIN = 4 };  // AGAIN: the poll goes on (poll_iter)
 
 // ---- task flags (async-task's state bits + bookkeeping) ----
 enum : u8 {
@@ -137,6 +137,9 @@ struct Params {
   u32 buggify;
   u32 reserved;
   u64 buggify_p10_int;  // (0.1 * 2^64) as u64, computed on the host in f64 like rand does
+  // determinism log of a single-seed replay (rand.rs:64-89): {u32 count, u32 capacity, u8 bytes[]} or 0.  Set per
+  // replay launch by msim_batch_determinism_log, never by make_params; read only by the TRACE kernels.
+  unsigned char* dlog;
 };
 
 /// Per-seed result exactly as the C-ABI returns it.

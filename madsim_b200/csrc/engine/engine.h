@@ -333,6 +333,37 @@ struct Engine {
     r3 = rotl64(r3, 45);
     return result;
   }
+  /// The determinism log / check of GlobalRng::with (rand.rs:64-89): after EVERY call that goes through the global
+  /// RNG — one gen_range, one gen_bool, one random() — the reference records
+  ///     (next u8 of a CLONE of the rng) ^ (xor of the bytes of elapsed nanos as u128)
+  /// and Runtime::check_determinism compares the second run's bytes with the first run's (runtime/mod.rs:178-202).
+  /// `Standard` for u8 is `next_u32() as u8`, and next_u32 is `next_u64() >> 32`.  Compiled only into the replay
+  /// kernel (TRACE); the batch kernels carry none of the code.  The log lives behind Params::dlog (single-seed
+  /// replay): u32 count, u32 capacity, then the bytes.
+  MSIM_HD void log_point() {
+    if (TRACE && P->dlog) {
+      u32* hdr = reinterpret_cast<u32*>(P->dlog);
+      u64 peek = rotl64(r0 + r3, 23) + r0;  // what the clone's next_u64 would return
+      u64 f = now ^ (now >> 32);
+      f ^= f >> 16;
+      f ^= f >> 8;
+      u32 i = hdr[0];
+      if (i < hdr[1]) reinterpret_cast<u8*>(hdr + 2)[i] = (u8)(peek >> 32) ^ (u8)f;
+      hdr[0] = i + 1;
+    }
+  }
+  /// random::<u64>() / one raw draw that is a whole `with` call of its own
+  MSIM_HD u64 random_u64() {
+    u64 v = next_u64();
+    log_point();
+    return v;
+  }
+  /// Rng::gen_bool(p) with p pre-digested to p_int = (p * 2^64) as u64 (rand 0.8 Bernoulli; p == 1.0 never gets here)
+  MSIM_HD bool gen_bool_int(u64 p_int) {
+    bool r = next_u64() < p_int;
+    log_point();
+    return r;
+  }
   /// Rng::gen_range(lo..hi) for u64/usize: UniformInt::sample_single (widening multiply + zone)
   MSIM_HD u64 gen_range_u64(u64 lo, u64 hi) {
     u64 range = hi - lo;
@@ -340,7 +371,10 @@ struct Engine {
     for (;;) {
       u64 v = next_u64();
       u64 l = v * range;
-      if (l <= zone) return lo + mulhi64(v, range);
+      if (l <= zone) {
+        log_point();
+        return lo + mulhi64(v, range);
+      }
     }
   }
   /// the same sampler for ranges that fit 32 bits (ready-queue index, 50..100 ns, 0..5 us): the
@@ -354,7 +388,10 @@ struct Engine {
       u64 p_hi = (v >> 32) * range;
       u64 l = p_lo + (p_hi << 32);            // low 64 bits of v * range
       u64 h = (p_hi + (p_lo >> 32)) >> 32;    // high 64 bits (fits 32)
-      if (l <= zone) return lo + (u32)h;
+      if (l <= zone) {
+        log_point();
+        return lo + (u32)h;
+      }
     }
   }
   /// Uniform::<u64>::new_inclusive(lo, hi).sample — modulo zone (UniformDuration Medium)
@@ -364,7 +401,10 @@ struct Engine {
     for (;;) {
       u64 v = next_u64();
       u64 l = v * range;
-      if (l <= zone) return lo + mulhi64(v, range);
+      if (l <= zone) {
+        log_point();
+        return lo + mulhi64(v, range);
+      }
     }
   }
   /// gen_range(config.send_latency): sampler pre-digested on the host (Params.lat_*)
@@ -374,14 +414,20 @@ struct Engine {
       for (;;) {
         u32 v = (u32)(next_u64() >> 32);
         u64 m = (u64)v * range;
-        if ((u32)m <= zone) return P->lat_base + (u32)P->lat_lo + (u32)(m >> 32);
+        if ((u32)m <= zone) {
+          log_point();
+          return P->lat_base + (u32)P->lat_lo + (u32)(m >> 32);
+        }
       }
     } else {
       u64 range = P->lat_range, zone = P->lat_zone;
       for (;;) {
         u64 v = next_u64();
         u64 l = v * range;
-        if (l <= zone) return P->lat_lo + mulhi64(v, range);
+        if (l <= zone) {
+          log_point();
+          return P->lat_lo + mulhi64(v, range);
+        }
       }
     }
   }
@@ -448,22 +494,25 @@ struct Engine {
   }
   /// Timer::expire(limit): fire every timer with deadline <= limit, in heap order.
   /// `now` is NOT touched: advance_to_next_event fires callbacks under the old clock.
+  MSIM_HD bool timer_due(u64 limit) const { return heap_len > 0 && h_dl(0) <= limit && running(); }
+  /// one `pop; callback(now)` of naive_timer::Timer::expire
+  MSIM_HD void fire_one() {
+    u64 dl;
+    u32 pl;
+    timer_pop(dl, pl);
+    ev_fire++;
+    u32 kind = pl >> 28, a = (pl >> 20) & 0xff, g = pl & 0xfffffu;
+    u32 id = kind == TK_WAKE ? g : (kind == TK_DELIVER ? w(L::W_M_SERIAL, a) : a);
+    trace(now, dl, MSIM_EV_WAKE + kind, id);  // MSIM_EV_WAKE / DELIVER / RESTART = 5 + TK_*
+    if (kind == TK_WAKE)
+      wake(a, g);
+    else if (MSIM_LIKELY(kind == TK_DELIVER))
+      deliver(a);
+    else
+      restart(a);
+  }
   MSIM_HD void expire(u64 limit) {
-    while (heap_len > 0 && h_dl(0) <= limit && running()) {
-      u64 dl;
-      u32 pl;
-      timer_pop(dl, pl);
-      ev_fire++;
-      u32 kind = pl >> 28, a = (pl >> 20) & 0xff, g = pl & 0xfffffu;
-      u32 id = kind == TK_WAKE ? g : (kind == TK_DELIVER ? w(L::W_M_SERIAL, a) : a);
-      trace(now, dl, MSIM_EV_WAKE + kind, id);  // MSIM_EV_WAKE / DELIVER / RESTART = 5 + TK_*
-      if (kind == TK_WAKE)
-        wake(a, g);
-      else if (MSIM_LIKELY(kind == TK_DELIVER))
-        deliver(a);
-      else
-        restart(a);
-    }
+    while (timer_due(limit)) fire_one();
   }
   /// sleep()/sleep_until(): deadline = max(deadline, now + 1 ms)  (time/mod.rs:111-124)
   MSIM_HD u64 sleep_deadline(u64 deadline) const {
@@ -889,7 +938,7 @@ MSIM_NOUNROLL
   MSIM_HD u64 rand_delay_deadline() {
     u64 delay = (u64)gen_range_small(0, 5) * 1000ull;
     if (P->buggify) {
-      if (next_u64() < P->buggify_p10_int) delay = (u64)gen_range_small(1, 5) * NS_PER_SEC;
+      if (gen_bool_int(P->buggify_p10_int)) delay = (u64)gen_range_small(1, 5) * NS_PER_SEC;
     }
     return sleep_deadline(now + delay);
   }
@@ -907,7 +956,7 @@ MSIM_NOUNROLL
     }
     // "ip not set" / destination not found: before any draw.  `clogged || gen_bool(loss)`: no
     // draw when clogged
-    if (dst_node < 0 || link_clogged(src_node, dst_node) || P->loss_always || next_u64() < P->loss_p_int) return -1;
+    if (dst_node < 0 || link_clogged(src_node, dst_node) || P->loss_always || gen_bool_int(P->loss_p_int)) return -1;
     ++w(L::W_MSG_COUNT);
     latency = sample_latency();
     // socket lookup AFTER the draws: exact address, then (UNSPECIFIED, port)
@@ -1160,6 +1209,9 @@ MSIM_NOUNROLL
     for (int k = 0; k < L::NSA; k++) w(L::W_ACC_WAITER, k) = NONE32;
     int m = spawn(WL::MAIN_KIND, 0, TF_JOINABLE);
     w(L::W_MAIN_SLOT) = (u32)m;
+    // check_determinism enables the rng log AFTER the Runtime is constructed (runtime/mod.rs:185-187): the base-time
+    // draw above is not part of it
+    if (TRACE && P->dlog) reinterpret_cast<u32*>(P->dlog)[0] = 0;
   }
   static MSIM_NI void init_cold(unsigned char* sb_, const Params* P_, u64 now_, u64 seed) {
     Engine e_;
@@ -1212,8 +1264,11 @@ MSIM_NOUNROLL
   /// state machine, executing the primitives it requests, until it is Pending / Ready / panics.
   /// Each primitive reproduces the poll-by-poll behaviour of SURVEY.md §3.4 (timers pushed per
   /// pending poll, draws in program order).
-  MSIM_HD int poll_task(int t) {
-    for (;;) {
+  /// poll_iter is ONE round of that loop — resume the awaited primitive, or run the state machine up to its next
+  /// request and register it — and returns POLL_AGAIN when the poll goes on.  The single-lane kernels loop over it
+  /// (poll_task); the multi-lane kernel runs the rounds of all lanes of a warp in lock step.
+  MSIM_HD int poll_iter(int t) {
+    {
       if (MSIM_UNLIKELY(!running())) return POLL_PENDING;
       u8 wt = t_wait(t);
       if (wt != W_NONE) {
@@ -1274,7 +1329,7 @@ MSIM_NOUNROLL
                 pend = true;
               } else {
                 t_wait(t) = (st == W_RECV_RX ? W_RECV_DELAY : W_CALL_DELAY) | WF_RD;
-                continue;
+                return POLL_AGAIN;
               }
               break;
             case W_RECV_DELAY:
@@ -1504,7 +1559,7 @@ MSIM_NOUNROLL
         case RQ_CALL:  // call_timeout: the timeout's Sleep is created first; call: rsp_tag = random::<u64>()
           t_dl1(t) = sleep_deadline(now + xb);
           t_c(t) = ya;
-          xb = next_u64();
+          xb = random_u64();
           yd = W_CALL_SEND | WF_RD;
           goto prepare;
         case RQ_SEND:
@@ -1589,12 +1644,21 @@ MSIM_NOUNROLL
           return POLL_ADVANCE;  // re-enters this poll (W_RESUME) before anything else runs
       }
     }
+    return POLL_AGAIN;
+  }
+  MSIM_HD int poll_task(int t) {
+    for (;;) {
+      int r = poll_iter(t);
+      if (r != POLL_AGAIN) return r;
+    }
   }
 
-  /// Runnable::run (async-task) + the panic policy of run_all_ready (task/mod.rs:285-317)
-  MSIM_HD bool run_task(int t, bool cont) {
-    u8 f = t_flags(t);
+  /// Runnable::run (async-task) + the panic policy of run_all_ready (task/mod.rs:285-317), in three parts so that the
+  /// multi-lane kernel can align the polls of a warp's lanes: run_begin, the poll, run_end.
+  /// run_begin: false = the task had been closed while it was queued: its future was dropped instead of polled
+  MSIM_HD bool run_begin(int t, bool cont) {
     if (!cont) {
+      u8 f = t_flags(t);
       if (C::USES_KILL && MSIM_UNLIKELY(f & TF_CLOSED)) {
         drop_future(t);
         t_flags(t) = t_flags(t) & ~TF_SCHEDULED;
@@ -1604,8 +1668,11 @@ MSIM_NOUNROLL
       }
       t_flags(t) = (f & ~TF_SCHEDULED) | TF_RUNNING;
     }
-    int r = poll_task(t);
-    if (MSIM_UNLIKELY(r == POLL_ADVANCE)) return true;  // still RUNNING: the poll continues after the timers fired
+    return true;
+  }
+  /// run_end: true = the poll was interrupted by time::advance (still RUNNING: it continues after the timers fired)
+  MSIM_HD bool run_end(int t, int r) {
+    if (MSIM_UNLIKELY(r == POLL_ADVANCE)) return true;
     if (r == POLL_READY) {
       if (C::USES_KILL && MSIM_UNLIKELY(t_flags(t) & TF_INIT)) node_exit(t_node(t), t_epoch(t));  // `future.await; h.exit()`
       drop_future(t);
@@ -1621,7 +1688,7 @@ MSIM_NOUNROLL
       maybe_free(t);
       panicked(n);
     } else {
-      f = t_flags(t) & ~TF_RUNNING;
+      u8 f = t_flags(t) & ~TF_RUNNING;
       t_flags(t) = f;
       if (C::USES_KILL && MSIM_UNLIKELY(f & TF_CLOSED)) {
         t_flags(t) = f & ~TF_SCHEDULED;
@@ -1633,6 +1700,10 @@ MSIM_NOUNROLL
       }
     }
     return false;
+  }
+  MSIM_HD bool run_task(int t, bool cont) {
+    if (!run_begin(t, cont)) return false;
+    return run_end(t, poll_task(t));
   }
   /// run_all_ready's panic policy (task/mod.rs:289-317): restart_on_panic nodes are killed and
   /// restarted after gen_range(1s..10s); anything else fails the test
@@ -1653,6 +1724,85 @@ MSIM_NOUNROLL
     return POLL_PANIC;
   }
 
+  // ---------------- the event step, in the pieces both kernels are made of ----------------
+  enum : int { ACT_NONE = 0, ACT_RUN = 1, ACT_DROP = 2 };
+  /// try_recv_random (utils/mpsc.rs:73-83) + the dispatch decision of run_all_ready (task/mod.rs:262-283).
+  /// ACT_NONE: the pop was a SKIP or a PARK — that step is over (no clock advance, no timers).
+  MSIM_HD int pop_ready(int& t) {
+    u32 len = rq_len;
+    u32 idx = gen_range_small(0, len);
+    t = b(L::B_RQ, idx);
+    b(L::B_RQ, idx) = b(L::B_RQ, len - 1);  // swap_remove
+    rq_len = len - 1;
+    ev_pop++;
+    u64 aux = ((u64)len << 32) | idx;
+    u8 f = 0;
+    u32 kind = MSIM_EV_POLL;
+    if (C::USES_KILL) {  // programs that never kill / pause / abort / exit a node only ever POLL
+      f = t_flags(t);
+      if (!(f & TF_ALIVE))
+        kind = MSIM_EV_SKIP;  // metadata().upgrade() failed: future already dropped
+      else if ((f & TF_CANCELLED) || task_node_killed(t))
+        kind = MSIM_EV_DROP;
+      else if (n_flags(t_node(t)) & NF_PAUSED)
+        kind = MSIM_EV_PARK;
+    }
+    trace(now, aux, kind, t_spawn(t));
+    if (MSIM_UNLIKELY(kind == MSIM_EV_SKIP)) {
+      t_flags(t) = f & ~TF_SCHEDULED;
+      maybe_free(t);
+      return ACT_NONE;
+    }
+    if (MSIM_UNLIKELY(kind == MSIM_EV_PARK)) {
+      u32 pl = w(L::W_PK_LEN);
+      if (pl >= (u32)C::NPARK) {
+        fail_cap(MSIM_CAP_PARKED);
+        return ACT_NONE;
+      }
+      b(L::B_PK, pl) = (u8)t;
+      w(L::W_PK_LEN) = pl + 1;
+      return ACT_NONE;
+    }
+    return kind == MSIM_EV_DROP ? ACT_DROP : ACT_RUN;
+  }
+  /// The ready Vec is drained: block_on returns if the main task is finished (task/mod.rs:241-243), panics on a
+  /// deadlock (:250), else advance_to_next_event (time/mod.rs:45-60): callbacks fire under the OLD clock.
+  /// false: the seed has stopped; true: `limit` is what Timer::expire gets.
+  MSIM_HD bool jump_limit(u64& limit) {
+    int m = (int)w(L::W_MAIN_SLOT);
+    u8 mf = t_flags(m);
+    if (MSIM_UNLIKELY(mf & (TF_COMPLETED | TF_CLOSED))) {
+      if (mf & TF_COMPLETED)
+        status = MSIM_ST_PASS;
+      else
+        fail(MSIM_ST_FAIL_ASSERT, 0xdead);  // main task cancelled
+      return false;
+    }
+    if (MSIM_UNLIKELY(heap_len == 0)) {
+      fail(MSIM_ST_FAIL_DEADLOCK, 0);
+      return false;
+    }
+    limit = h_dl(0) + 50;
+    return true;
+  }
+  /// after Timer::expire(limit): the clock moves to `limit`; Runtime::set_time_limit (task/mod.rs:253-258)
+  MSIM_HD void clock_to(u64 limit) {
+    if (now != limit) {
+      now = limit;
+      if (MSIM_UNLIKELY(now >= P->time_limit_cmp))  // u64::MAX when there is no limit
+        fail(MSIM_ST_FAIL_TIME_LIMIT, 0);
+    }
+  }
+  /// after the poll / drop of a popped runnable: remember an interrupted poll, or advance time 50-100 ns
+  /// (task/mod.rs:319-321); the timers due by then fire next
+  MSIM_HD u64 after_run(int t, bool adv) {
+    if (MSIM_UNLIKELY(adv))
+      w(L::W_RESUME) = (u32)t;
+    else
+      now += gen_range_small(50, 100);
+    return now;
+  }
+
   /// ONE EVENT STEP of Executor::block_on (task/mod.rs:239-259): if the ready Vec is not empty,
   /// pop a random runnable, dispatch it and advance the clock 50-100 ns; otherwise finish, or
   /// jump to the next timer.  Returns false when the seed has stopped.
@@ -1662,86 +1812,26 @@ MSIM_NOUNROLL
     bool cont = rs != NONE32;  // a poll interrupted by time::advance continues before anything else
     if (cont || rq_len > 0) {
       int t;
-      bool do_drop = false;
+      int act = ACT_RUN;
       if (cont) {
         t = (int)rs;
         w(L::W_RESUME) = NONE32;
       } else {
-        // try_recv_random (utils/mpsc.rs:73-83)
-        u32 len = rq_len;
-        u32 idx = gen_range_small(0, len);
-        t = b(L::B_RQ, idx);
-        b(L::B_RQ, idx) = b(L::B_RQ, len - 1);  // swap_remove
-        rq_len = len - 1;
-        ev_pop++;
-        u64 aux = ((u64)len << 32) | idx;
-        u8 f = 0;
-        u32 kind = MSIM_EV_POLL;
-        if (C::USES_KILL) {  // programs that never kill / pause / abort / exit a node only ever POLL
-          f = t_flags(t);
-          if (!(f & TF_ALIVE))
-            kind = MSIM_EV_SKIP;  // metadata().upgrade() failed: future already dropped
-          else if ((f & TF_CANCELLED) || task_node_killed(t))
-            kind = MSIM_EV_DROP;
-          else if (n_flags(t_node(t)) & NF_PAUSED)
-            kind = MSIM_EV_PARK;
-        }
-        trace(now, aux, kind, t_spawn(t));
-        if (MSIM_UNLIKELY(kind == MSIM_EV_SKIP)) {
-          t_flags(t) = f & ~TF_SCHEDULED;
-          maybe_free(t);
-          return true;
-        }
-        if (MSIM_UNLIKELY(kind == MSIM_EV_PARK)) {
-          u32 pl = w(L::W_PK_LEN);
-          if (pl >= (u32)C::NPARK) {
-            fail_cap(MSIM_CAP_PARKED);
-            return false;
-          }
-          b(L::B_PK, pl) = (u8)t;
-          w(L::W_PK_LEN) = pl + 1;
-          return true;
-        }
-        do_drop = kind == MSIM_EV_DROP;
+        act = pop_ready(t);
+        if (MSIM_UNLIKELY(act == ACT_NONE)) return running();
       }
       bool adv = false;
-      if (MSIM_UNLIKELY(do_drop))
+      if (MSIM_UNLIKELY(act == ACT_DROP))
         drop_runnable(t);
       else
         adv = run_task(t, cont);
       if (MSIM_UNLIKELY(!running())) return false;
-      if (MSIM_UNLIKELY(adv)) {
-        w(L::W_RESUME) = (u32)t;
-      } else {
-        now += gen_range_small(50, 100);  // advance time: 50-100ns (task/mod.rs:319-321)
-      }
-      limit = now;
+      limit = after_run(t, adv);
     } else {
-      // ready Vec drained: task.is_finished()?
-      int m = (int)w(L::W_MAIN_SLOT);
-      u8 mf = t_flags(m);
-      if (MSIM_UNLIKELY(mf & (TF_COMPLETED | TF_CLOSED))) {
-        if (mf & TF_COMPLETED)
-          status = MSIM_ST_PASS;
-        else
-          fail(MSIM_ST_FAIL_ASSERT, 0xdead);  // main task cancelled
-        return false;
-      }
-      // advance_to_next_event (time/mod.rs:45-60): callbacks fire under the OLD clock
-      if (MSIM_UNLIKELY(heap_len == 0)) {
-        fail(MSIM_ST_FAIL_DEADLOCK, 0);
-        return false;
-      }
-      limit = h_dl(0) + 50;
+      if (!jump_limit(limit)) return false;
     }
     expire(limit);  // the one place timers fire from the event loop
-    if (now != limit) {
-      now = limit;
-      if (MSIM_UNLIKELY(now >= P->time_limit_cmp)) {  // u64::MAX when there is no limit
-        fail(MSIM_ST_FAIL_TIME_LIMIT, 0);
-        return false;
-      }
-    }
+    clock_to(limit);
     return running();
   }
 };

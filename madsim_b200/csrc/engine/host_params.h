@@ -5,7 +5,9 @@
 // (reference call sites network.rs:262,267).
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 
 #include "defs.h"
@@ -69,6 +71,162 @@ inline void config_defaults(msim_config* c) {
   c->packet_loss_rate = 0.0;
   c->send_latency_lo_ns = 1 * NS_PER_MS;
   c->send_latency_hi_ns = 10 * NS_PER_MS;
+}
+
+/// `impl FromStr for Config` (config.rs:28-35): the TOML a MADSIM_TEST_CONFIG file holds (builder.rs:82-88) —
+///   [net]  packet_loss_rate = 0.1
+///          send_latency = { start = { secs = 0, nanos = 1000000 }, end = { secs = 0, nanos = 10000000 } }
+///   [tcp]
+/// in the inline form of the reference's own test (config.rs:52-61) or the dotted-table form its Display impl
+/// prints ([net.send_latency.start] ...).  A small TOML subset: tables, dotted keys, inline tables, integers,
+/// floats, booleans and strings; unknown keys are ignored (serde's default), missing ones take the serde defaults
+/// (packet_loss_rate 0.0, send_latency 1 ms..10 ms).  Runtime knobs (time limit, buggify) are not part of the file.
+namespace toml_detail {
+struct Parser {
+  const char* s;
+  std::string* err;
+  std::map<std::string, double> num;  // dotted path -> numeric value
+  std::map<std::string, bool> seen;   // dotted path -> present (any type)
+  bool fail(const std::string& m) {
+    if (err && err->empty()) *err = "config: " + m;
+    return false;
+  }
+  void mark(const std::string& path) {  // the path and every table above it exist
+    for (size_t i = 0; i <= path.size(); i++)
+      if (i == path.size() || path[i] == '.') seen[path.substr(0, i)] = true;
+  }
+  void ws(bool newlines) {
+    for (;;) {
+      while (*s == ' ' || *s == '\t' || *s == '\r' || (newlines && *s == '\n')) s++;
+      if (*s == '#') {
+        while (*s && *s != '\n') s++;
+        if (newlines) continue;
+      }
+      break;
+    }
+  }
+  bool key(std::string* out) {  // bare or quoted, dotted
+    out->clear();
+    for (;;) {
+      ws(false);
+      std::string part;
+      if (*s == '"' || *s == '\'') {
+        char q = *s++;
+        while (*s && *s != q) part += *s++;
+        if (*s != q) return fail("unterminated key");
+        s++;
+      } else {
+        while ((*s >= 'a' && *s <= 'z') || (*s >= 'A' && *s <= 'Z') || (*s >= '0' && *s <= '9') || *s == '_' || *s == '-') part += *s++;
+      }
+      if (part.empty()) return fail("expected a key");
+      if (!out->empty()) *out += '.';
+      *out += part;
+      ws(false);
+      if (*s != '.') return true;
+      s++;
+    }
+  }
+  bool value(const std::string& path) {
+    ws(false);
+    mark(path);
+    if (*s == '{') {  // inline table
+      s++;
+      ws(true);
+      if (*s == '}') return s++, true;
+      for (;;) {
+        std::string k;
+        if (!key(&k)) return false;
+        if (*s != '=') return fail("expected '=' in inline table");
+        s++;
+        if (!value(path + "." + k)) return false;
+        ws(true);
+        if (*s == ',') {
+          s++;
+          ws(true);
+          continue;
+        }
+        if (*s == '}') return s++, true;
+        return fail("expected ',' or '}' in inline table");
+      }
+    }
+    if (*s == '"' || *s == '\'') {
+      char q = *s++;
+      while (*s && *s != q) s += (*s == '\\' && q == '"' && s[1]) ? 2 : 1;
+      if (*s != q) return fail("unterminated string");
+      s++;
+      return true;
+    }
+    if (!std::strncmp(s, "true", 4) || !std::strncmp(s, "false", 5)) {
+      num[path] = *s == 't';
+      s += *s == 't' ? 4 : 5;
+      return true;
+    }
+    if (*s == '[') return fail("arrays are not part of madsim::Config");
+    std::string lit;
+    while (*s && !std::strchr(" \t\r\n,}#", *s)) {
+      if (*s != '_') lit += *s;
+      s++;
+    }
+    if (lit == "inf" || lit == "+inf") return num[path] = INFINITY, true;
+    if (lit == "nan" || lit == "+nan" || lit == "-nan") return num[path] = NAN, true;
+    char* end = nullptr;
+    double v = std::strtod(lit.c_str(), &end);
+    if (lit.empty() || *end) return fail("bad value for " + path);
+    num[path] = v;
+    return true;
+  }
+  bool document() {
+    std::string table;
+    for (;;) {
+      ws(true);
+      if (!*s) return true;
+      if (*s == '[') {
+        if (s[1] == '[') return fail("arrays of tables are not part of madsim::Config");
+        s++;
+        if (!key(&table)) return false;
+        if (*s != ']') return fail("expected ']'");
+        s++;
+        mark(table);
+      } else {
+        std::string k;
+        if (!key(&k)) return false;
+        if (*s != '=') return fail("expected '='");
+        s++;
+        if (!value(table.empty() ? k : table + "." + k)) return false;
+      }
+      ws(false);
+      if (*s && *s != '\n') return fail("expected end of line");
+    }
+  }
+};
+}  // namespace toml_detail
+
+inline int config_from_toml(const char* text, msim_config* out, std::string* err) {
+  toml_detail::Parser p{text, err, {}, {}};
+  if (err) err->clear();
+  if (!p.document()) return MSIM_EINVAL;
+  config_defaults(out);
+  if (p.num.count("net.packet_loss_rate")) out->packet_loss_rate = p.num["net.packet_loss_rate"];
+  if (p.seen.count("net.send_latency")) {
+    u64 v[2];
+    const char* ends[2] = {"start", "end"};
+    for (int i = 0; i < 2; i++) {
+      std::string base = std::string("net.send_latency.") + ends[i];
+      if (!p.num.count(base + ".secs") || !p.num.count(base + ".nanos")) {
+        if (err) *err = "config: send_latency needs " + base + " = { secs, nanos }";  // serde: missing field
+        return MSIM_EINVAL;
+      }
+      double secs = p.num[base + ".secs"], nanos = p.num[base + ".nanos"];
+      if (!(secs >= 0 && secs < 1.8e10) || !(nanos >= 0 && nanos < 4294967296.0) || secs != std::floor(secs) || nanos != std::floor(nanos)) {
+        if (err) *err = "config: " + base + " out of range";
+        return MSIM_EINVAL;
+      }
+      v[i] = (u64)secs * NS_PER_SEC + (u64)nanos;  // Duration::new carries nanos >= 1e9 into secs
+    }
+    out->send_latency_lo_ns = v[0];
+    out->send_latency_hi_ns = v[1];
+  }
+  return 0;
 }
 
 /// Returns 0 or MSIM_EINVAL (+ message).

@@ -53,6 +53,7 @@ struct KernelArgs {
   uint32_t* unfinished;     // device counter: seeds still RUNNING after this launch
   uint32_t* next_seed;      // device counter of the seed queue (dynamic mode)
   uint32_t dynamic;         // 1: run-to-completion launch, every warp slot pulls the next seed when its own finishes
+  uint32_t lockstep;        // 1: dynamic launch with L >= 2 through the lock-step (phase-aligned) kernel
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -195,11 +196,118 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
   }
 }
 
+/// The multi-lane batch kernel (run to completion, dynamic seed queue, L >= 2 populated lanes per warp).
+/// A warp advances its L seeds in LOCK STEP through the phases of the event step, so that the lanes execute the
+/// common spine — jump to the next timer, timer pop (heap sift), ready-queue pop draw, clock-advance draw — as one
+/// instruction stream and only diverge inside the polls, whose rounds (poll_iter) are aligned too:
+///   refill | J: drained queue -> finished / deadlock / jump limit | X: fire due timers, one per round, while any
+///   lane has one | P: pop a runnable | R: poll rounds while any lane is still polling | A: clock += 50..100 ns |
+///   X again | retire finished seeds.
+/// A lane whose queue is drained does J+X and then P+R+A+X in the same iteration (jump steps and pop steps
+/// alternate in most programs), i.e. up to two event steps per iteration; every lane still executes exactly the
+/// sequence of steps Engine::step() would, so results do not depend on L.  Warp votes (__any_sync) pick the
+/// phases that still have work; __syncwarp semantics come with them.
+template <class WL>
+__global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel_ml(const __grid_constant__ KernelArgs a) {
+  using E = Engine<WL, false>;
+  using LY = typename E::L;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* block = smem + SMEM_HDR;
+  const uint32_t S = a.S, L = a.L;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp * L >= S) return;
+  const uint32_t nl = S - warp * L < L ? S - warp * L : L;  // populated lanes of this warp
+  if (lane >= nl) return;
+  const unsigned mask = nl >= 32 ? 0xffffffffu : ((1u << nl) - 1u);
+  const uint32_t col = warp * L + lane;
+
+  E e;
+  e.sb = block + (size_t)col * LY::BYTES;
+  e.P = &a.P;
+  e.tr = nullptr;
+  e.tr_cap = 0;
+  e.tr_n = 0;
+  e.status = MSIM_ST_PASS;
+  bool live = false, exhausted = false;
+  uint32_t idx = 0;
+  for (;;) {
+    // ---- refill: a lane without a seed takes the next one from the queue ----
+    if (!live && !exhausted) {
+      idx = atomicAdd(a.next_seed, 1u);
+      if (idx < a.n_seeds) {
+        e.init(a.seed_base + idx);
+        live = true;
+      } else {
+        exhausted = true;
+      }
+    }
+    if (!__any_sync(mask, live)) break;  // every lane is out of seeds
+    // ---- J: the ready Vec is drained ----
+    u64 limit = 0;
+    bool ex = false;
+    bool cont = live && e.w(LY::W_RESUME) != NONE32;
+    if (live && !cont && e.rq_len == 0) ex = e.jump_limit(limit);
+    // ---- X: timers due by `limit` ----
+    for (;;) {
+      bool due = ex && e.timer_due(limit);
+      if (!__any_sync(mask, due)) break;
+      if (due) e.fire_one();
+    }
+    if (ex) e.clock_to(limit);
+    // ---- P: pop a runnable (or continue the poll that time::advance interrupted) ----
+    int t = 0, act = E::ACT_NONE;
+    if (live && e.running() && (cont || e.rq_len > 0)) {
+      if (cont) {
+        t = (int)e.w(LY::W_RESUME);
+        e.w(LY::W_RESUME) = NONE32;
+        act = E::ACT_RUN;
+      } else {
+        act = e.pop_ready(t);
+      }
+    }
+    // ---- R: dispatch; the polls of all lanes advance round by round ----
+    bool polling = false;
+    if (act == E::ACT_DROP) e.drop_runnable(t);
+    if (act == E::ACT_RUN) polling = e.run_begin(t, cont);
+    int r = POLL_AGAIN;
+    for (;;) {
+      bool more = polling && r == POLL_AGAIN;
+      if (!__any_sync(mask, more)) break;
+      if (more) r = e.poll_iter(t);
+    }
+    bool adv = false;
+    if (polling) adv = e.run_end(t, r);
+    // ---- A: clock advance 50-100 ns, then the timers due by then ----
+    ex = act != E::ACT_NONE && e.running();
+    if (ex) limit = e.after_run(t, adv);
+    for (;;) {
+      bool due = ex && e.timer_due(limit);
+      if (!__any_sync(mask, due)) break;
+      if (due) e.fire_one();
+    }
+    if (ex) e.clock_to(limit);
+    // ---- retire ----
+    if (live && !e.running()) {
+      e.store();
+      SeedResult res;
+      e.result(res);
+      a.results[idx] = res;
+      live = false;
+    }
+  }
+}
+
 /// Batch summary on the device: counters + pass/fail bitmap (what the N-GPU run all-reduces).
 /// out: u64 counters[8] = {ev_pop, ev_fire, draws, n_pass, n_fail, n_unfinished, first_fail_seed, n_seeds}
-///      followed by u32 bitmap[ceil(n/32)] (bit set = seed failed)
+///      [sharded layout only: u64 first_fail_of_rank[world]]
+///      u32 bitmap[...] (bit set = seed failed), this batch's bits starting at bit `bit_off`
+/// Local layout (msim_batch_summarize_device): bit_off = 0, slot = nullptr.  Sharded layout
+/// (msim_batch_summarize_sharded): the buffer of every rank has the SAME shape and is zero outside the rank's own
+/// slot / bit range, so that ONE sum all-reduce of the whole buffer yields the global counters, every rank's first
+/// failing seed (a MIN the host takes over `world` slots) and the global bitmap (disjoint bits: sum == or).
 __global__ void msim_summary_kernel(const SeedResult* __restrict__ res, uint64_t n, uint64_t seed_base,
-                                    unsigned long long* __restrict__ counters, uint32_t* __restrict__ bitmap) {
+                                    unsigned long long* __restrict__ counters, unsigned long long* __restrict__ slot,
+                                    uint32_t* __restrict__ bitmap, uint64_t bit_off) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long pop = 0, fire = 0, draws = 0, pass = 0, failn = 0, unf = 0, first = ~0ull;
   bool failed = false;
@@ -219,7 +327,12 @@ __global__ void msim_summary_kernel(const SeedResult* __restrict__ res, uint64_t
     }
   }
   uint32_t bits = __ballot_sync(0xffffffffu, failed);
-  if ((threadIdx.x & 31) == 0 && i < n) bitmap[i >> 5] = bits;
+  if ((threadIdx.x & 31) == 0 && i < n && bits) {
+    uint64_t g = bit_off + i;  // global index of this warp's first seed
+    uint32_t sh = (uint32_t)(g & 31);
+    atomicOr(&bitmap[g >> 5], bits << sh);
+    if (sh && (bits >> (32 - sh))) atomicOr(&bitmap[(g >> 5) + 1], bits >> (32 - sh));
+  }
   for (int o = 16; o > 0; o >>= 1) {
     pop += __shfl_xor_sync(0xffffffffu, pop, o);
     fire += __shfl_xor_sync(0xffffffffu, fire, o);
@@ -237,7 +350,7 @@ __global__ void msim_summary_kernel(const SeedResult* __restrict__ res, uint64_t
     atomicAdd(&counters[3], pass);
     atomicAdd(&counters[4], failn);
     atomicAdd(&counters[5], unf);
-    atomicMin(&counters[6], first);
+    if (first != ~0ull) atomicMin(slot ? slot : &counters[6], first);
   }
 }
 
@@ -260,7 +373,7 @@ template <class WL>
 cudaError_t launch_wl(const KernelArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
   // two instantiations per program: the batch kernel (dynamic run-to-completion launches), and the general
   // one (bursts through the checkpoint, resume, single-seed replay with trace records)
-  auto k = a.dynamic ? msim_step_kernel<WL, false> : msim_step_kernel<WL, true>;
+  auto k = a.dynamic ? (a.lockstep ? msim_step_kernel_ml<WL> : msim_step_kernel<WL, false>) : msim_step_kernel<WL, true>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<grid, block, smem, st>>>(a);
@@ -294,11 +407,13 @@ struct msim_batch {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   uint32_t user_S = 0, user_L = 0;
+  bool user_lockstep = false;  // MSIM_GEOMETRY_LOCKSTEP: multi-lane launches go through msim_step_kernel_ml
   // current run
   uint64_t seed_base = 0, n_seeds = 0;
   uint32_t S = 0, L = 0, n_blocks = 0, threads = 0, grid_launched = 0;
   size_t smem = 0;
   bool ran = false, pending = false;
+  bool has_checkpoint = false;  // d_blob holds the image of the CURRENT run (a burst run of this geometry)
   SeedResult* d_results = nullptr;
   size_t d_results_cap = 0;
   unsigned char* d_blob = nullptr;
@@ -311,7 +426,8 @@ struct msim_batch {
   size_t d_summary_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double kernel_ms = 0;
-  uint32_t launches = 0;
+  uint32_t launches = 0;          // step-kernel launches of the last run
+  uint32_t summary_launches = 0;  // msim_summary_kernel launches since then (not part of stats.launches)
 };
 
 namespace {
@@ -363,7 +479,7 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
   a.seed_base = b->seed_base;
   a.n_seeds = b->n_seeds;
   a.max_events = max_events;
-  a.blob = b->d_blob;
+  a.blob = b->has_checkpoint ? b->d_blob : nullptr;  // a stale image of an earlier run is never handed to a kernel
   a.results = b->d_results;
   a.trace = d_trace;
   a.trace_n = d_trace_n;
@@ -375,6 +491,7 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
   a.next_seed = b->d_unfinished + 1;
   // run-to-completion launches balance the load dynamically; bursts keep seed i in block i / S (the checkpoint layout)
   a.dynamic = (max_events == 0 && !resume && !d_trace && b->n_seeds < 0xffffffffull) ? 1 : 0;
+  a.lockstep = (a.dynamic && b->user_lockstep && b->L >= 2) ? 1 : 0;
   CUDA_TRY(cudaMemsetAsync(b->d_unfinished, 0, 2 * sizeof(uint32_t), b->stream));
   uint32_t n_grid = b->n_blocks;
   if (a.dynamic && n_grid > (uint32_t)b->sm_count) n_grid = (uint32_t)b->sm_count;  // 1 CTA per SM (shared memory)
@@ -443,10 +560,9 @@ int run_impl(msim_batch* b, uint64_t seed_base, uint64_t n, uint64_t max_events,
   if (rc) return rc;
   rc = ensure_buffers(b, n, max_events != 0);
   if (rc) return rc;
-  if (max_events == 0) {
-    // run to completion: no checkpoint needed
-  }
+  b->has_checkpoint = max_events != 0;  // run to completion keeps no checkpoint; a burst run owns d_blob from here on
   b->launches = 0;
+  b->summary_launches = 0;
   CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
   rc = launch(b, max_events, false, nullptr, nullptr, 0);
   if (rc) return rc;
@@ -480,6 +596,13 @@ int msim_config_default(msim_config* cfg) {
   return MSIM_OK;
 }
 
+int msim_config_from_toml(const char* text, msim_config* cfg) {
+  if (!text || !cfg) return set_err(MSIM_EINVAL, "null argument");
+  std::string err;
+  int rc = config_from_toml(text, cfg, &err);
+  return rc ? set_err(rc, err) : MSIM_OK;
+}
+
 int msim_workload_default(uint32_t workload, msim_workload_desc* out) {
   if (!out) return set_err(MSIM_EINVAL, "null descriptor");
   if (workload_defaults(workload, out)) return set_err(MSIM_EINVAL, "unknown workload");
@@ -493,7 +616,13 @@ int msim_batch_create(const msim_config* cfg, int device, msim_batch** out) {
   if (n < 0) return n;
   if (device < 0 || device >= n) return set_err(MSIM_EINVAL, "bad device ordinal");
   CUDA_TRY(cudaSetDevice(device));
-  auto* b = new msim_batch();
+  struct Guard {  // an early return releases whatever has been created so far
+    msim_batch* p;
+    ~Guard() {
+      if (p) msim_batch_destroy(p);
+    }
+  } guard{new msim_batch()};
+  msim_batch* b = guard.p;
   b->device = device;
   if (cfg)
     b->cfg = *cfg;
@@ -509,6 +638,7 @@ int msim_batch_create(const msim_config* cfg, int device, msim_batch** out) {
   CUDA_TRY(cudaEventCreate(&b->ev1));
   CUDA_TRY(cudaMalloc(&b->d_unfinished, 2 * sizeof(uint32_t)));
   CUDA_TRY(cudaMallocHost(&b->h_unfinished, sizeof(uint32_t)));
+  guard.p = nullptr;
   *out = b;
   return MSIM_OK;
 }
@@ -535,20 +665,24 @@ int msim_workload_load(msim_batch* b, const msim_workload_desc* w) {
   std::string err;
   int rc = make_params(b->cfg, *w, &P, &err);
   if (rc) return set_err(rc, err);
-  if (state_bytes_of(w->workload) <= 0) return set_err(MSIM_EINVAL, "workload not available on the device");
+  if (state_bytes_of(w->workload, w->p[2]) <= 0) return set_err(MSIM_EINVAL, "workload not available on the device");
   b->wl = *w;
   b->wl.n_nodes = P.n_nodes;
   b->P = P;
   b->has_wl = true;
   b->ran = false;
+  b->has_checkpoint = false;
   return MSIM_OK;
 }
 
 int msim_batch_set_geometry(msim_batch* b, uint32_t seeds_per_cta, uint32_t lanes_per_warp) {
   if (!b) return set_err(MSIM_EINVAL, "null batch");
+  const bool lockstep = lanes_per_warp & MSIM_GEOMETRY_LOCKSTEP;
+  lanes_per_warp &= ~(uint32_t)MSIM_GEOMETRY_LOCKSTEP;
   if (lanes_per_warp > 32) return set_err(MSIM_EINVAL, "lanes_per_warp must be 0..32");
   b->user_S = seeds_per_cta;
   b->user_L = lanes_per_warp;
+  b->user_lockstep = lockstep;
   return MSIM_OK;
 }
 
@@ -584,7 +718,8 @@ int msim_batch_run_async(msim_batch* b, uint64_t seed_base, uint64_t n_seeds, ui
 
 int msim_batch_resume(msim_batch* b, uint64_t max_events_per_seed) {
   if (!b || !b->ran) return set_err(MSIM_ESTATE, "nothing to resume");
-  if (!b->d_blob) return set_err(MSIM_ESTATE, "the previous run kept no checkpoint (max_events_per_seed was 0)");
+  if (!b->has_checkpoint || !b->d_blob)
+    return set_err(MSIM_ESTATE, "the previous run kept no checkpoint (max_events_per_seed was 0)");
   CUDA_TRY(cudaSetDevice(b->device));
   int rc = msim_batch_sync(b);
   if (rc) return rc;
@@ -606,8 +741,7 @@ int msim_batch_results_device(msim_batch* b, void** dptr, size_t* bytes) {
   return MSIM_OK;
 }
 
-/// Device-side summary into caller-provided DEVICE memory (e.g. a torch tensor that is then
-/// all-reduced over NCCL): u64 counters[8] + u32 bitmap[ceil(n/32)].
+/// Device-side summary into caller-provided DEVICE memory: u64 counters[8] + u32 bitmap[ceil(n/32)].
 int msim_batch_summarize_device(msim_batch* b, void* d_out, size_t bytes) {
   if (!b || !b->ran) return set_err(MSIM_ESTATE, "no run yet");
   size_t words = (b->n_seeds + 31) / 32;
@@ -615,13 +749,48 @@ int msim_batch_summarize_device(msim_batch* b, void* d_out, size_t bytes) {
   if (!d_out || bytes < need) return set_err(MSIM_ERANGE, "summary buffer too small");
   CUDA_TRY(cudaSetDevice(b->device));
   unsigned long long init[8] = {0, 0, 0, 0, 0, 0, ~0ull, (unsigned long long)b->n_seeds};
+  CUDA_TRY(cudaMemsetAsync(d_out, 0, need, b->stream));
   CUDA_TRY(cudaMemcpyAsync(d_out, init, sizeof(init), cudaMemcpyHostToDevice, b->stream));
   auto* counters = (unsigned long long*)d_out;
   auto* bitmap = (uint32_t*)((unsigned char*)d_out + sizeof(init));
   unsigned threads = 256, blocks = (unsigned)((b->n_seeds + threads - 1) / threads);
-  msim_summary_kernel<<<blocks, threads, 0, b->stream>>>(b->d_results, b->n_seeds, b->seed_base, counters, bitmap);
+  msim_summary_kernel<<<blocks, threads, 0, b->stream>>>(b->d_results, b->n_seeds, b->seed_base, counters, nullptr, bitmap, 0);
   CUDA_TRY(cudaGetLastError());
-  b->launches++;
+  b->summary_launches++;
+  return MSIM_OK;
+}
+
+/// The summary of one shard of an N-GPU sweep, shaped for ONE sum all-reduce (the reference's
+/// sweep loop is runtime/builder.rs:129-150): u64 counters[8] (slot 6 unused, 0), u64 first_fail_of_rank[world]
+/// (own slot: first failing seed or all-ones; other slots 0), u32 bitmap[ceil(n_total/32)] with this shard's bits at
+/// (first seed of the shard - seed_base) and zeros elsewhere.  A rank whose shard is empty calls this after no run
+/// at all: it contributes zeros (and all-ones in its slot).
+int msim_batch_summarize_sharded(msim_batch* b, void* d_out, size_t bytes, uint32_t rank, uint32_t world,
+                                 uint64_t seed_base, uint64_t n_total) {
+  if (!b) return set_err(MSIM_EINVAL, "null batch");
+  if (world == 0 || rank >= world) return set_err(MSIM_EINVAL, "bad rank / world");
+  const bool empty = !b->ran;  // an empty shard never ran
+  uint64_t n = empty ? 0 : b->n_seeds;
+  if (!empty && (b->seed_base < seed_base || b->seed_base - seed_base + n > n_total))
+    return set_err(MSIM_ERANGE, "the batch's seeds are not inside [seed_base, seed_base + n_total)");
+  size_t words = (n_total + 31) / 32;
+  size_t need = (8 + (size_t)world) * sizeof(unsigned long long) + words * sizeof(uint32_t);
+  if (!d_out || bytes < need) return set_err(MSIM_ERANGE, "summary buffer too small");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaMemsetAsync(d_out, 0, need, b->stream));
+  auto* counters = (unsigned long long*)d_out;
+  auto* slot = counters + 8 + rank;
+  auto* bitmap = (uint32_t*)(counters + 8 + world);
+  CUDA_TRY(cudaMemsetAsync(slot, 0xff, sizeof(unsigned long long), b->stream));
+  if (n) {
+    unsigned long long nn = n;
+    CUDA_TRY(cudaMemcpyAsync(counters + 7, &nn, sizeof(nn), cudaMemcpyHostToDevice, b->stream));
+    unsigned threads = 256, blocks = (unsigned)((n + threads - 1) / threads);
+    msim_summary_kernel<<<blocks, threads, 0, b->stream>>>(b->d_results, n, b->seed_base, counters, slot, bitmap,
+                                                           b->seed_base - seed_base);
+    CUDA_TRY(cudaGetLastError());
+    b->summary_launches++;
+  }
   return MSIM_OK;
 }
 
@@ -656,7 +825,7 @@ int msim_batch_results(msim_batch* b, msim_seed_result* out, uint32_t* fail_bitm
     stats->n_unfinished = h[5];
     stats->first_fail_seed = h[6];
     stats->kernel_ms = b->kernel_ms;
-    stats->launches = b->launches;
+    stats->launches = b->launches;  // step-kernel launches (the summary kernel is not counted)
     stats->seeds_per_cta = b->S;
     stats->lanes_per_warp = b->L;
     stats->ctas = b->grid_launched ? b->grid_launched : b->n_blocks;
@@ -678,13 +847,22 @@ int msim_batch_trace_hash(msim_batch* b, uint64_t* hash) {
   return MSIM_OK;
 }
 
-int msim_batch_trace(msim_batch* b, uint64_t seed, msim_trace_rec* out, size_t cap, size_t* n, msim_seed_result* result) {
+namespace {
+struct DevBuf {  // cudaMalloc'd scratch, released on every return path
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+/// Replays ONE seed in a scratch batch that shares config + workload, with the canonical trace and / or the
+/// determinism log switched on (both only exist in the GENERAL kernels).
+int replay_one(msim_batch* b, uint64_t seed, msim_trace_rec* tr_out, size_t tr_cap, size_t* tr_n, uint8_t* log_out,
+               size_t log_cap, size_t* log_n, bool want_log, msim_seed_result* result) {
   if (!b || !b->has_wl) return set_err(MSIM_ESTATE, "msim_workload_load must be called first");
-  if (cap > 0xffffffffull) return set_err(MSIM_ERANGE, "trace capacity too large");
+  if (tr_cap > 0xffffffffull || log_cap > 0xfffffff0ull) return set_err(MSIM_ERANGE, "capacity too large");
   CUDA_TRY(cudaSetDevice(b->device));
   int rc = msim_batch_sync(b);
   if (rc) return rc;
-  // replay this one seed in a scratch batch that shares config + workload
   msim_batch* r = nullptr;
   rc = msim_batch_create(&b->cfg, b->device, &r);
   if (rc) return rc;
@@ -702,31 +880,46 @@ int msim_batch_trace(msim_batch* b, uint64_t seed, msim_trace_rec* out, size_t c
   if (rc) return rc;
   rc = ensure_buffers(r, 1, false);
   if (rc) return rc;
-  msim_trace_rec* d_tr = nullptr;
-  uint32_t* d_n = nullptr;
-  size_t dcap = cap ? cap : 1;
-  CUDA_TRY(cudaMalloc(&d_tr, dcap * sizeof(msim_trace_rec)));
-  CUDA_TRY(cudaMalloc(&d_n, sizeof(uint32_t)));
-  CUDA_TRY(cudaMemsetAsync(d_n, 0, sizeof(uint32_t), r->stream));
-  rc = launch(r, 0, false, d_tr, d_n, (uint32_t)cap);
-  if (rc == MSIM_OK) {
-    uint32_t hn = 0;
-    cudaError_t e = cudaStreamSynchronize(r->stream);
-    if (e == cudaSuccess) e = cudaMemcpy(&hn, d_n, sizeof(hn), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && out && cap)
-      e = cudaMemcpy(out, d_tr, (hn < cap ? hn : cap) * sizeof(msim_trace_rec), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && result) e = cudaMemcpy(result, r->d_results, sizeof(SeedResult), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess)
-      rc = set_err(MSIM_ECUDA, std::string("trace replay: ") + cudaGetErrorString(e));
-    else if (n)
-      *n = hn;
+  DevBuf d_tr, d_n, d_log;
+  CUDA_TRY(cudaMalloc(&d_tr.p, (tr_cap ? tr_cap : 1) * sizeof(msim_trace_rec)));
+  CUDA_TRY(cudaMalloc(&d_n.p, sizeof(uint32_t)));
+  CUDA_TRY(cudaMemsetAsync(d_n.p, 0, sizeof(uint32_t), r->stream));
+  if (want_log) {  // {u32 count, u32 capacity, bytes}
+    CUDA_TRY(cudaMalloc(&d_log.p, 8 + (log_cap ? log_cap : 1)));
+    uint32_t hdr[2] = {0, (uint32_t)log_cap};
+    CUDA_TRY(cudaMemcpyAsync(d_log.p, hdr, sizeof(hdr), cudaMemcpyHostToDevice, r->stream));
+    r->P.dlog = (unsigned char*)d_log.p;
   }
-  cudaFree(d_tr);
-  cudaFree(d_n);
-  return rc;
+  rc = launch(r, 0, false, (msim_trace_rec*)d_tr.p, (uint32_t*)d_n.p, (uint32_t)tr_cap);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(r->stream));
+  uint32_t hn = 0, hdr[2] = {0, 0};
+  CUDA_TRY(cudaMemcpy(&hn, d_n.p, sizeof(hn), cudaMemcpyDeviceToHost));
+  if (tr_out && tr_cap)
+    CUDA_TRY(cudaMemcpy(tr_out, d_tr.p, (hn < tr_cap ? hn : tr_cap) * sizeof(msim_trace_rec), cudaMemcpyDeviceToHost));
+  if (want_log) {
+    CUDA_TRY(cudaMemcpy(hdr, d_log.p, sizeof(hdr), cudaMemcpyDeviceToHost));
+    if (log_out && log_cap)
+      CUDA_TRY(cudaMemcpy(log_out, (unsigned char*)d_log.p + 8, hdr[0] < log_cap ? hdr[0] : log_cap, cudaMemcpyDeviceToHost));
+  }
+  if (result) CUDA_TRY(cudaMemcpy(result, r->d_results, sizeof(SeedResult), cudaMemcpyDeviceToHost));
+  if (tr_n) *tr_n = hn;
+  if (log_n) *log_n = hdr[0];
+  return MSIM_OK;
+}
+}  // namespace
+
+int msim_batch_trace(msim_batch* b, uint64_t seed, msim_trace_rec* out, size_t cap, size_t* n, msim_seed_result* result) {
+  return replay_one(b, seed, out, cap, n, nullptr, 0, nullptr, false, result);
 }
 
-/// Bytes of per-seed state for a workload (DESIGN.md capacity table; bench roofline accounting)
+/// The log Runtime::check_determinism records and checks (runtime/mod.rs:178-202, rand.rs:64-89): one byte per
+/// GlobalRng::with call, (next u8 of a clone of the rng) ^ xor-fold(elapsed nanos).  Device replay of one seed.
+int msim_batch_determinism_log(msim_batch* b, uint64_t seed, uint8_t* out, size_t cap, size_t* n, msim_seed_result* result) {
+  return replay_one(b, seed, nullptr, 0, nullptr, out, cap, n, true, result);
+}
+
+/// Bytes of per-seed state for a workload's default variant (DESIGN.md capacity table; bench roofline accounting)
 int msim_workload_state_bytes(uint32_t workload) {
   int b = state_bytes_of(workload);
   return b > 0 ? b : set_err(MSIM_EINVAL, "unknown workload");

@@ -405,7 +405,7 @@ MSIM_NOUNROLL
           e.t_a(t) = e.rv0;
           e.t_b(t) = e.rv1;
           // EtcdService::timeout: gen_bool(timeout_rate) — p == 1.0 draws nothing
-          bool timed_out = P.p[5] ? true : e.next_u64() < P.p[6];
+          bool timed_out = P.p[5] ? true : e.gen_bool_int(P.p[6]);
           if (timed_out) {
             e.t_pc(t) = 2;
             e.xa = e.sample_inclusive_u64(5 * NS_PER_SEC, 15 * NS_PER_SEC - 1);  // gen_range(5 s..15 s)

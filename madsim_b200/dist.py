@@ -30,41 +30,35 @@ def summary_layout(n_local: int):
     return 8, (n_local + 31) // 32
 
 
-def reduce_summary(counters: torch.Tensor, bitmap_local: torch.Tensor, first_seed_local: int, seed_base: int,
-                   n_total: int, group=None):
-    """All-reduce one rank's summary into the global one.
-
-    counters: int64[8] on the collective's device = {ev_pop, ev_fire, draws, n_pass, n_fail,
-              n_unfinished, first_fail_seed (u64 bit pattern, all-ones = none), n_seeds}
-    bitmap_local: int32[ceil(n_local/32)] — bit i = local seed i failed
-    Returns (dict of global counters, global bitmap int32[ceil(n_total/32)] on the same device).
-    """
-    dev = counters.device
-    sums = counters[[0, 1, 2, 3, 4, 5, 7]].clone()
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    # MIN over u64 seeds done in int64 space: map all-ones (none) to INT64_MAX
-    ff = counters[6:7].clone()
-    ff = torch.where(ff < 0, torch.full_like(ff, torch.iinfo(torch.int64).max), ff)
-    dist.all_reduce(ff, op=dist.ReduceOp.MIN, group=group)
-    # scatter the local bits into the global bitmap at this rank's offset, then SUM (disjoint → OR)
+def sharded_layout(n_total: int, world: int):
+    """int64 element counts of the one-all-reduce summary buffer (msim_batch_summarize_sharded): 8 counters,
+    `world` first-fail slots, then the global fail bitmap (u32 words, padded to whole int64s)."""
     words = (n_total + 31) // 32
-    g = torch.zeros(words, dtype=torch.int64, device=dev)
-    off = first_seed_local - seed_base
-    n_local = int(counters[7].item())
-    if n_local:
-        lb = bitmap_local.to(torch.int64) & 0xFFFFFFFF
-        idx = torch.arange(n_local, device=dev)
-        bits = (lb[idx // 32] >> (idx % 32)) & 1
-        gi = idx + off
-        g.index_add_(0, gi // 32, bits << (gi % 32))
-    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
-    first = int(ff.item())
+    return 8, world, (words + 1) // 2
+
+
+def finish_summary(buf: np.ndarray, n_total: int, world: int):
+    """Host side of the reduction: `buf` = the all-reduced (summed) int64 buffer as a numpy array.
+    → (dict of global counters, global bitmap uint32[ceil(n_total/32)])."""
+    u = buf.view(np.uint64)
+    slots = u[8:8 + world]
+    first = int(slots.min()) if world else U64_MAX  # unsigned MIN over the ranks' slots (all-ones = no failure)
     out = {
-        "ev_pop": int(sums[0]), "ev_fire": int(sums[1]), "draws": int(sums[2]), "n_pass": int(sums[3]),
-        "n_fail": int(sums[4]), "n_unfinished": int(sums[5]), "n_seeds": int(sums[6]),
-        "first_fail_seed": None if first == torch.iinfo(torch.int64).max else first,
+        "ev_pop": int(u[0]), "ev_fire": int(u[1]), "draws": int(u[2]), "n_pass": int(u[3]), "n_fail": int(u[4]),
+        "n_unfinished": int(u[5]), "n_seeds": int(u[7]), "first_fail_seed": None if first == U64_MAX else first,
     }
-    return out, g.to(torch.int32) if words else g.to(torch.int32)
+    bitmap = buf[8 + world:].view(np.uint32)[: (n_total + 31) // 32].copy()
+    return out, bitmap
+
+
+def reduce_summary(buf: torch.Tensor, n_total: int, world: int, group=None):
+    """ONE collective: sum all-reduce of the whole sharded summary buffer (int64 view).  Every rank's buffer is
+    zero outside its own first-fail slot and bit range, so the sum is the global counters, every rank's first
+    failing seed in its slot (the MIN is taken on the host, unsigned — seeds near 2^64 are fine) and the OR of the
+    disjoint bitmaps.  No host synchronisation here; the caller copies the result back once."""
+    if world > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf
 
 
 def summary_from_results(res: np.ndarray, seed_first: int):
@@ -82,6 +76,25 @@ def summary_from_results(res: np.ndarray, seed_first: int):
     return c, bm
 
 
+def sharded_summary_from_results(res: np.ndarray, seed_first: int, rank: int, world: int, seed_base: int, n_total: int):
+    """Host restatement of msim_batch_summarize_sharded for a results array (used by the CPU tests): the int64
+    buffer one rank contributes to the all-reduce."""
+    nc, ns, nb = sharded_layout(n_total, world)
+    buf = np.zeros(nc + ns + nb, dtype=np.int64)
+    u = buf.view(np.uint64)
+    c, bm = summary_from_results(res, seed_first)
+    u[:6] = c[:6]
+    u[7] = c[7]
+    u[8 + rank] = c[6]  # own slot: first failing seed or all-ones
+    bits = buf[nc + ns:].view(np.uint32)
+    off = seed_first - seed_base
+    for i in range(len(res)):
+        if (bm[i // 32] >> np.uint32(i % 32)) & np.uint32(1):
+            g = off + i
+            bits[g // 32] |= np.uint32(1 << (g % 32))
+    return buf
+
+
 class ShardedRun:
     """Run `n_total` seeds of a workload across the ranks of the default process group."""
 
@@ -94,34 +107,36 @@ class ShardedRun:
         self.batch = Batch(config, device_index).load(workload)
         self.stream = torch.cuda.Stream(device=self.device)
         self.batch.set_stream(self.stream.cuda_stream)
-        self._summary = None
+        self._buf = None
+        self._host = None
 
     def run(self, seed_base: int, n_total: int, sync: bool = True):
         self.seed_base, self.n_total = seed_base, n_total
         self.first, self.count = shard(seed_base, n_total, self.rank, self.world)
-        self.batch.run(self.first, self.count, sync=sync)
+        self.ran = self.count > 0
+        if self.ran:  # a rank whose shard is empty (world > n_total) launches nothing but still joins the reduction
+            self.batch.run(self.first, self.count, sync=sync)
         return self
 
     def reduce(self):
-        """Device summary → NCCL all-reduce → global counters + bitmap."""
+        """Device summary (one kernel) → ONE sum all-reduce (NCCL) → one D2H copy → global counters + bitmap."""
         from .api import Batch
 
-        nbytes = Batch.summary_nbytes(self.count)
-        buf = torch.empty(nbytes // 8 + 1, dtype=torch.int64, device=self.device)
+        n64 = sum(sharded_layout(self.n_total, self.world))
+        if self._buf is None or self._buf.numel() != n64:
+            self._buf = torch.empty(n64, dtype=torch.int64, device=self.device)
+            self._host = torch.empty(n64, dtype=torch.int64, pin_memory=True)
         with torch.cuda.stream(self.stream):
-            self.batch.summarize_into(buf.data_ptr(), nbytes)
-            counters = buf[:8]
-            bitmap = buf[8:].view(torch.int32)[: (self.count + 31) // 32]
-            if self.world > 1:
-                out = reduce_summary(counters, bitmap, self.first, self.seed_base, self.n_total)
-            else:
-                self.stream.synchronize()
-                c = counters.cpu().numpy().view(np.uint64)
-                out = ({"ev_pop": int(c[0]), "ev_fire": int(c[1]), "draws": int(c[2]), "n_pass": int(c[3]),
-                        "n_fail": int(c[4]), "n_unfinished": int(c[5]), "n_seeds": int(c[7]),
-                        "first_fail_seed": None if int(c[6]) == U64_MAX else int(c[6])}, bitmap.clone())
+            if self.ran:
+                self.batch.summarize_sharded_into(self._buf.data_ptr(), n64 * 8, self.rank, self.world, self.seed_base,
+                                                  self.n_total)
+            else:  # nothing ran here: zeros, and "no failure" in the own slot
+                self._buf.zero_()
+                self._buf[8 + self.rank] = -1
+            reduce_summary(self._buf, self.n_total, self.world)
+            self._host.copy_(self._buf, non_blocking=True)
         self.stream.synchronize()
-        return out
+        return finish_summary(self._host.numpy(), self.n_total, self.world)
 
     def close(self):
         self.batch.close()

@@ -38,13 +38,19 @@ struct Extra {
 thread_local size_t g_peak_registered = 0, g_peak_msgs = 0;
 
 int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_seed_result* out,
-            std::vector<msim_trace_rec>* full, std::string* msg, Extra* extra) {
+            std::vector<msim_trace_rec>* full, std::string* msg, Extra* extra, std::vector<u8>* dlog = nullptr,
+            const std::vector<u8>* dcheck = nullptr) {
   g_peak_registered = g_peak_msgs = 0;
   tls_peak_registered = &g_peak_registered;
   tls_peak_msgs = &g_peak_msgs;
   Runtime rt(seed, to_config(c));
   if (c && c->time_limit_ns) rt.set_time_limit(c->time_limit_ns);
   if (c && c->buggify) rt.rand.enable_buggify();
+  // Runtime::check_determinism (runtime/mod.rs:185-187, 194-196): the log / the check is switched on after construction
+  if (dcheck)
+    rt.rand.enable_check(*dcheck);
+  else if (dlog)
+    rt.rand.enable_log();
   rt.tracer.full = full;
   msim_seed_result r{};
   std::array<u32, 4> user{0, 0, 0, 0};
@@ -149,6 +155,10 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
     extra->peak_msgs = u32(g_peak_msgs);
   }
   rt.tracer.full = nullptr;
+  if (dlog) {
+    auto l = rt.rand.take_log();
+    if (l) *dlog = std::move(*l);
+  }
   *out = r;
   return MSIM_OK;
 }
@@ -245,6 +255,31 @@ int oracle_check_determinism(const msim_config* cfg, const msim_workload_desc* w
   if (!log) return 0;
   auto log2 = run(log);
   return log2.has_value() ? 1 : 0;
+}
+
+/// The determinism log of one seed of ANY registered workload (rand.rs:64-89): what the first run of
+/// Runtime::check_determinism records.  *n = bytes produced (may exceed cap).
+int oracle_determinism_log(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed, uint8_t* out, size_t cap,
+                           size_t* n, msim_seed_result* result) {
+  std::vector<u8> log;
+  msim_seed_result r{};
+  int rc = run_one(cfg, wl, seed, &r, nullptr, nullptr, nullptr, &log);
+  if (rc) return rc;
+  if (n) *n = log.size();
+  if (out) std::memcpy(out, log.data(), std::min(cap, log.size()));
+  if (result) *result = r;
+  return MSIM_OK;
+}
+
+/// The second run of Runtime::check_determinism against a given log: 1 = every draw matched, 0 = "non-determinism
+/// detected" (the panic of rand.rs:79-84), for any registered workload.
+int oracle_check_against_log(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed, const uint8_t* log, size_t n) {
+  std::vector<u8> chk(log, log + n);
+  msim_seed_result r{};
+  std::string msg;
+  int rc = run_one(cfg, wl, seed, &r, nullptr, &msg, nullptr, nullptr, &chk);
+  if (rc) return rc;
+  return msg.find("non-determinism") == std::string::npos ? 1 : 0;
 }
 
 // ---- KAT hooks: the third-party arithmetic in isolation ----

@@ -77,8 +77,22 @@ int main() {
     b.count = 256;
     auto out = b.run(Workload::chaos());
     EXPECT(out.stats.n_pass == 256);
+    // under `check` only `seed` runs, twice, through Runtime::check_determinism (builder.rs:126-128)
     auto out2 = Builder{0, 64, 1, Config{}, 0, true}.run(Workload::chaos(4, 3000, 50));
-    EXPECT(out2.stats.n_pass == 64);
+    EXPECT(out2.results.size() == 1 && out2.results[0].status == MSIM_ST_PASS);
+    // MADSIM_TEST_JOBS: the sweep sharded over (up to) that many GPUs gives the same results
+    Builder jb;
+    jb.seed = 9, jb.count = 100, jb.jobs = 4;
+    auto out3 = jb.run(Workload::chaos());
+    Builder one;
+    one.seed = 9, one.count = 100;
+    auto out4 = one.run(Workload::chaos());
+    bool same = out3.results.size() == 100 && out4.results.size() == 100;
+    for (size_t i = 0; same && i < 100; i++) same = out3.results[i].trace_hash == out4.results[i].trace_hash;
+    EXPECT(same);
+    // MADSIM_TEST_CONFIG: TOML → Config
+    Config tc = Config::from_toml("[net]\npacket_loss_rate = 0.5\n");
+    EXPECT(tc.net.packet_loss_rate == 0.5 && tc.net.send_latency_lo_ns == 1000000);
     std::printf("ok   chaos: %llu seeds pass, worker restarted %u times in seed 0\n",
                 (unsigned long long)out.stats.n_pass, out.results[0].user[1]);
   }

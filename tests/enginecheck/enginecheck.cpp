@@ -48,6 +48,124 @@ static int run_wl(const Params& P, uint64_t seed_base, uint64_t n, uint32_t S, u
   return 0;
 }
 
+// Host emulation of msim_step_kernel_ml (the multi-lane batch kernel): `lanes` engines advance in lock step through
+// the same phases, a vote being a loop over the lanes.  Checks that the phase decomposition executes, per seed,
+// exactly the steps Engine::step() would.
+template <class WL>
+static int run_wl_ml(const Params& P, uint64_t seed_base, uint64_t n, uint32_t lanes, msim_seed_result* out) {
+  using E = Engine<WL, false>;
+  using LY = typename E::L;
+  struct Lane {
+    E e;
+    bool live = false, exhausted = false, cont = false, ex = false, polling = false, adv = false;
+    uint64_t idx = 0, limit = 0;
+    int t = 0, act = 0, r = 0;
+  };
+  std::vector<unsigned char> block((size_t)lanes * LY::BYTES + 64, 0xA5);
+  std::vector<Lane> ln(lanes);
+  for (uint32_t i = 0; i < lanes; i++) {
+    std::memset(&ln[i].e, 0, sizeof(E));
+    ln[i].e.sb = block.data() + (size_t)i * LY::BYTES;
+    ln[i].e.P = &P;
+    ln[i].e.status = MSIM_ST_PASS;
+  }
+  uint64_t next = 0;
+  auto any = [&](auto pred) {
+    for (auto& l : ln)
+      if (pred(l)) return true;
+    return false;
+  };
+  auto expire_phase = [&]() {
+    for (;;) {
+      bool some = false;
+      for (auto& l : ln) {
+        bool due = l.ex && l.e.timer_due(l.limit);
+        if (due) l.e.fire_one(), some = true;
+      }
+      if (!some) break;
+    }
+    for (auto& l : ln)
+      if (l.ex) l.e.clock_to(l.limit);
+  };
+  for (;;) {
+    for (auto& l : ln)
+      if (!l.live && !l.exhausted) {
+        l.idx = next++;
+        if (l.idx < n) {
+          l.e.init(seed_base + l.idx);
+          l.live = true;
+        } else {
+          l.exhausted = true;
+        }
+      }
+    if (!any([](Lane& l) { return l.live; })) break;
+    for (auto& l : ln) {
+      l.limit = 0;
+      l.ex = false;
+      l.cont = l.live && l.e.w(LY::W_RESUME) != NONE32;
+      if (l.live && !l.cont && l.e.rq_len == 0) l.ex = l.e.jump_limit(l.limit);
+    }
+    expire_phase();
+    for (auto& l : ln) {
+      l.t = 0;
+      l.act = E::ACT_NONE;
+      if (l.live && l.e.running() && (l.cont || l.e.rq_len > 0)) {
+        if (l.cont) {
+          l.t = (int)l.e.w(LY::W_RESUME);
+          l.e.w(LY::W_RESUME) = NONE32;
+          l.act = E::ACT_RUN;
+        } else {
+          l.act = l.e.pop_ready(l.t);
+        }
+      }
+    }
+    for (auto& l : ln) {
+      l.polling = false;
+      if (l.act == E::ACT_DROP) l.e.drop_runnable(l.t);
+      if (l.act == E::ACT_RUN) l.polling = l.e.run_begin(l.t, l.cont);
+      l.r = POLL_AGAIN;
+    }
+    while (any([](Lane& l) { return l.polling && l.r == POLL_AGAIN; }))
+      for (auto& l : ln)
+        if (l.polling && l.r == POLL_AGAIN) l.r = l.e.poll_iter(l.t);
+    for (auto& l : ln) {
+      l.adv = false;
+      if (l.polling) l.adv = l.e.run_end(l.t, l.r);
+      l.ex = l.act != E::ACT_NONE && l.e.running();
+      if (l.ex) l.limit = l.e.after_run(l.t, l.adv);
+    }
+    expire_phase();
+    for (auto& l : ln)
+      if (l.live && !l.e.running()) {
+        l.e.store();
+        l.e.result(out[l.idx]);
+        l.live = false;
+      }
+  }
+  return 0;
+}
+
+extern "C" int enginecheck_run_ml(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed_base, uint64_t n,
+                                  uint32_t lanes, msim_seed_result* out) {
+  Params P;
+  std::string err;
+  int rc = make_params(*cfg, *wl, &P, &err);
+  if (rc) return rc;
+  if (lanes == 0) lanes = 1;
+  switch (wl->workload) {
+    case MSIM_WL_SLEEP: return run_wl_ml<WL_Sleep>(P, seed_base, n, lanes, out);
+    case MSIM_WL_PINGPONG: return run_wl_ml<WL_PingPong>(P, seed_base, n, lanes, out);
+    case MSIM_WL_RAFT: return run_wl_ml<WL_Raft>(P, seed_base, n, lanes, out);
+    case MSIM_WL_CHAOS: return run_wl_ml<WL_Chaos>(P, seed_base, n, lanes, out);
+    case MSIM_WL_STREAM: return run_wl_ml<WL_Stream>(P, seed_base, n, lanes, out);
+    case MSIM_WL_ETCD: return run_wl_ml<WL_Etcd>(P, seed_base, n, lanes, out);
+    case MSIM_WL_TONIC:
+      return (P.p[2] & 8) ? run_wl_ml<WL_TonicBig>(P, seed_base, n, lanes, out) : run_wl_ml<WL_Tonic>(P, seed_base, n, lanes, out);
+    case MSIM_WL_SIGNAL: return run_wl_ml<WL_Signal>(P, seed_base, n, lanes, out);
+  }
+  return MSIM_EINVAL;
+}
+
 extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed_base, uint64_t n,
                                uint32_t S, uint64_t max_events, msim_seed_result* out, uint64_t trace_seed,
                                msim_trace_rec* tr, size_t cap, size_t* n_tr) {
@@ -68,6 +186,38 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
     case MSIM_WL_SIGNAL: return run_wl<WL_Signal>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
   }
   return MSIM_EINVAL;
+}
+
+/// The determinism log (rand.rs:64-89) as the replay kernel produces it, from the host build of the same engine.
+extern "C" int enginecheck_determinism_log(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed, uint8_t* out,
+                                           size_t cap, size_t* n, msim_seed_result* result) {
+  Params P;
+  std::string err;
+  int rc = make_params(*cfg, *wl, &P, &err);
+  if (rc) return rc;
+  std::vector<unsigned char> buf(8 + cap + 8);
+  uint32_t hdr[2] = {0, (uint32_t)cap};
+  std::memcpy(buf.data(), hdr, 8);
+  P.dlog = buf.data();
+  size_t ntr = 0;
+  switch (wl->workload) {
+    case MSIM_WL_SLEEP: rc = run_wl<WL_Sleep>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
+    case MSIM_WL_PINGPONG: rc = run_wl<WL_PingPong>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
+    case MSIM_WL_RAFT: rc = run_wl<WL_Raft>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
+    case MSIM_WL_CHAOS: rc = run_wl<WL_Chaos>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
+    case MSIM_WL_STREAM: rc = run_wl<WL_Stream>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
+    case MSIM_WL_ETCD: rc = run_wl<WL_Etcd>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
+    case MSIM_WL_TONIC:
+      rc = (P.p[2] & 8) ? run_wl<WL_TonicBig>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr)
+                        : run_wl<WL_Tonic>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr);
+      break;
+    case MSIM_WL_SIGNAL: rc = run_wl<WL_Signal>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
+    default: return MSIM_EINVAL;
+  }
+  std::memcpy(hdr, buf.data(), 8);
+  if (n) *n = hdr[0];
+  if (out) std::memcpy(out, buf.data() + 8, hdr[0] < cap ? hdr[0] : cap);
+  return rc;
 }
 
 extern "C" int enginecheck_state_bytes(uint32_t workload) {

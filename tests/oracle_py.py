@@ -22,6 +22,35 @@ from madsim_b200.api import SEED_RESULT_DTYPE, TRACE_DTYPE, Config, Workload
 
 _ora = None
 _chk = None
+ORACLE_BUILD = "x86-64-v2 (shipped: built in the build container for any x86-64 host)"
+
+
+def use_native_build():
+    """Rebuild the oracle with -march=native for THIS host (SURVEY.md §8d asks for it; the shipped library is
+    -march=x86-64-v2 because it is built in another container) into oracle/_native/ and make it the library the
+    next oracle() call loads.  Returns the description of the build in use; falls back to the shipped one."""
+    global _ora, ORACLE_LIB, ORACLE_BUILD
+    import shutil
+
+    out = os.path.join(ORACLE_DIR, "_native", "liboracle.so")
+    cxx = os.environ.get("CXX") or shutil.which("g++")
+    try:
+        if cxx is None:
+            raise RuntimeError("no g++")
+        srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".hpp"))]
+        srcs += [os.path.join(ORACLE_DIR, "rt", f) for f in os.listdir(os.path.join(ORACLE_DIR, "rt"))]
+        if not os.path.exists(out) or any(os.path.getmtime(x) > os.path.getmtime(out) for x in srcs):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.run([cxx, "-std=c++20", "-O3", "-march=native", "-fPIC", "-pthread", "-shared", "-o", out,
+                            os.path.join(ORACLE_DIR, "oracle_capi.cpp")], check=True, capture_output=True, timeout=300)
+        lib = C.CDLL(out)
+        lib.oracle_run_seed.restype = C.c_int
+        lib.oracle_run_many.restype = C.c_int
+        lib.oracle_check_determinism.restype = C.c_int
+        _ora, ORACLE_LIB, ORACLE_BUILD = lib, out, "-O3 -march=native (rebuilt on this host)"
+    except Exception as e:  # keep the shipped build
+        ORACLE_BUILD = f"x86-64-v2 (shipped; native rebuild failed: {type(e).__name__})"
+    return ORACLE_BUILD
 
 
 def oracle():
@@ -44,6 +73,7 @@ def enginecheck():
                             os.path.join(ROOT, "tests", "enginecheck", "enginecheck.cpp")], check=True)
         _chk = C.CDLL(ENGINECHECK_LIB)
         _chk.enginecheck_run.restype = C.c_int
+        _chk.enginecheck_run_ml.restype = C.c_int
     return _chk
 
 
@@ -96,6 +126,43 @@ def engine_host(config: Config, wl: Workload, seed_base: int, n: int, seeds_per_
     if rc != 0:
         raise RuntimeError(f"enginecheck_run failed: {rc}")
     return out, (buf[: min(nt.value, cap)].copy() if buf is not None else None)
+
+
+def engine_host_ml(config: Config, wl: Workload, seed_base: int, n: int, lanes: int = 4) -> np.ndarray:
+    """Host emulation of the multi-lane batch kernel's phase loop (tests/enginecheck run_wl_ml): `lanes`
+    engines in lock step — CPU-side check that the phases execute exactly Engine::step()'s sequence."""
+    cfg, d = config.to_c(), wl.to_c()
+    out = np.empty(n, dtype=SEED_RESULT_DTYPE)
+    rc = enginecheck().enginecheck_run_ml(C.byref(cfg), C.byref(d), C.c_uint64(seed_base), C.c_uint64(n),
+                                          C.c_uint32(lanes), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"enginecheck_run_ml failed: {rc}")
+    return out
+
+
+def determinism_log(config: Config, wl: Workload, seed: int, impl: str = "oracle", cap: int = 1 << 22):
+    """The per-`GlobalRng::with` byte log of Runtime::check_determinism (rand.rs:64-89) for one seed, from the oracle
+    ("oracle") or from the host build of the device engine ("engine").  → (bytes ndarray, result record)"""
+    cfg, d = config.to_c(), wl.to_c()
+    buf = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t(0)
+    r = N.MsimSeedResult()
+    fn = oracle().oracle_determinism_log if impl == "oracle" else enginecheck().enginecheck_determinism_log
+    fn.restype = C.c_int
+    rc = fn(C.byref(cfg), C.byref(d), C.c_uint64(seed), buf.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(n), C.byref(r))
+    if rc != 0:
+        raise RuntimeError(f"determinism_log({impl}) failed: {rc}")
+    assert n.value <= cap, "log capacity too small"
+    return buf[: n.value].copy(), np.frombuffer(bytes(r), dtype=SEED_RESULT_DTYPE)[0]
+
+
+def check_against_log(config: Config, wl: Workload, seed: int, log: np.ndarray) -> bool:
+    """Second run of Runtime::check_determinism on the oracle against `log`: False = "non-determinism detected"."""
+    cfg, d = config.to_c(), wl.to_c()
+    fn = oracle().oracle_check_against_log
+    fn.restype = C.c_int
+    log = np.ascontiguousarray(log, dtype=np.uint8)
+    return fn(C.byref(cfg), C.byref(d), C.c_uint64(seed), log.ctypes.data_as(C.c_void_p), C.c_size_t(len(log))) == 1
 
 
 def first_trace_diff(a: np.ndarray, b: np.ndarray):

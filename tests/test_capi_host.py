@@ -77,6 +77,51 @@ def test_builder_from_env_reads_the_reference_variables(monkeypatch):
     assert m.Builder.from_env().check is False
 
 
+def test_builder_from_env_defaults_follow_the_reference(monkeypatch, tmp_path):
+    # builder.rs:64-118: unset seed = the current time in ns; MADSIM_TEST_CONFIG names a TOML file; count >= 2 under the check
+    import time
+
+    for v in ("MADSIM_TEST_SEED", "MADSIM_TEST_NUM", "MADSIM_TEST_JOBS", "MADSIM_TEST_TIME_LIMIT", "MADSIM_TEST_CONFIG",
+              "MADSIM_TEST_CHECK_DETERMINISM"):
+        monkeypatch.delenv(v, raising=False)
+    t0 = time.time_ns()
+    b = m.Builder.from_env()
+    assert t0 <= b.seed <= time.time_ns() and (b.count, b.jobs, b.check, b.time_limit_s) == (1, 1, False, None)
+    assert b.config == m.Config()
+    monkeypatch.setenv("MADSIM_TEST_CHECK_DETERMINISM", "")
+    assert m.Builder.from_env().count == 2
+    monkeypatch.setenv("MADSIM_TEST_NUM", "7")
+    assert m.Builder.from_env().count == 7
+    cfg = tmp_path / "sim.toml"
+    cfg.write_text("[net]\npacket_loss_rate = 0.25\nsend_latency = { start = { secs = 0, nanos = 2000000 }, "
+                   "end = { secs = 1, nanos = 5 } }\n\n[tcp]\n")
+    monkeypatch.setenv("MADSIM_TEST_CONFIG", str(cfg))
+    b = m.Builder.from_env()
+    assert b.config.packet_loss_rate == 0.25 and tuple(b.config.send_latency_ns) == (2_000_000, 1_000_000_005)
+
+
+def test_config_from_toml_matches_the_reference_parse_test():
+    # the reference's own parse test (config.rs:52-75): inline tables, an empty [tcp]
+    c = m.Config.from_toml("""
+        [net]
+        packet_loss_rate = 0.1
+        send_latency = { start = { secs = 0, nanos = 1000000 }, end = { secs = 0, nanos = 10000000 } }
+
+        [tcp]
+        """)
+    assert c == m.Config(packet_loss_rate=0.1, send_latency_ns=(1 * m.MS, 10 * m.MS))
+    # what `impl Display for Config` prints (toml::to_string_pretty): dotted tables
+    c = m.Config.from_toml("[net]\npacket_loss_rate = 0.0\n\n[net.send_latency.start]\nsecs = 0\nnanos = 1000000\n\n"
+                           "[net.send_latency.end]\nsecs = 0\nnanos = 10000000\n\n[tcp]\n")
+    assert c == m.Config()
+    assert m.Config.from_toml("") == m.Config()  # #[serde(default)] everywhere
+    assert m.Config.from_toml("[net]\npacket_loss_rate = 1 # all lost\nfuture_knob = \"x\"\n").packet_loss_rate == 1.0
+    for bad in ("[net\n", "[net]\nsend_latency = { start = { secs = 0 } }\n", "[net]\npacket_loss_rate = \n", "x = [1, 2]\n"):
+        with pytest.raises(m.MsimError) as e:
+            m.Config.from_toml(bad)
+        assert e.value.code == N.EINVAL and "config" in str(e.value)
+
+
 def test_simulation_failure_message_matches_reference_note():
     e = m.SimulationFailure(1234, m.ST_FAIL_ASSERT, 1)
     assert "MADSIM_TEST_SEED=1234" in str(e)  # runtime/mod.rs:205-210

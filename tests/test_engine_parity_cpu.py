@@ -85,6 +85,39 @@ def test_engine_matches_oracle(oracle, name, cfg, wl, base, n):
     _assert_same(oracle, cfg, wl, base, n, seeds_per_block=5)
 
 
+@pytest.mark.parametrize("name,cfg,wl,base,n", CASES, ids=[c[0] for c in CASES])
+def test_multilane_phase_loop_matches_oracle(oracle, name, cfg, wl, base, n):
+    # the multi-lane batch kernel's lock-step phase loop (host emulation, 3 and 8 lanes; the seed queue hands lanes new
+    # seeds as old ones finish): per seed it must execute exactly Engine::step()'s sequence
+    ref = oracle.run_many(cfg, wl, base, n)
+    for lanes in (3, 8):
+        got = oracle.engine_host_ml(cfg, wl, base, n, lanes=lanes)
+        for f in FIELDS:
+            assert np.array_equal(ref[f], got[f]), f"{name}: {f} differs with {lanes} lanes"
+
+
+DLOG_CASES = [c for c in CASES if c[0] in ("sleep", "pingpong-buggify-medium", "pingpong-loss", "raft-faults", "raft-faults-bug-loss",
+                                            "stream-partitions-loss20", "etcd-timeouts-3clients", "etcd-lease-admin-timeouts",
+                                            "tonic-request-timeouts-everything", "signal-skip-ctrlc-kills", "chaos-long-panics")]
+
+
+@pytest.mark.parametrize("name,cfg,wl,base,n", DLOG_CASES, ids=[c[0] for c in DLOG_CASES])
+def test_determinism_log_matches_oracle(oracle, name, cfg, wl, base, n):
+    # Runtime::check_determinism's log (rand.rs:64-89): one byte per GlobalRng::with call.  The replay kernel's hook
+    # (Engine::log_point) must put a byte exactly where the reference does — every gen_range / gen_bool / random()
+    # of the runtime AND of the program — and the oracle's check mode must accept the engine's log
+    for seed in (base, base + 3):
+        a, ra = oracle.determinism_log(cfg, wl, seed, "oracle")
+        b, rb = oracle.determinism_log(cfg, wl, seed, "engine")
+        assert len(a) == len(b) and np.array_equal(a, b), f"{name} seed {seed}: logs differ"
+        assert ra["trace_hash"] == rb["trace_hash"] and len(a) <= ra["draws"]
+        assert oracle.check_against_log(cfg, wl, seed, b)
+        if len(b) > 10 and ra["status"] == m.ST_PASS:
+            flipped = b.copy()
+            flipped[len(b) // 2] ^= 0x10
+            assert not oracle.check_against_log(cfg, wl, seed, flipped), "a corrupted log must be detected"
+
+
 def test_burst_checkpoint_equals_run_to_completion(oracle):
     # registers ↔ state-block spill every k events must not change anything
     cfg, wl = m.Config(), m.Workload.raft(duration_ms=2000, faults=7)

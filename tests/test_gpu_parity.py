@@ -30,6 +30,20 @@ def run_gpu(cfg, wl, base, n, S=0, L=0, max_events=0):
     return res, bm, st
 
 
+def host_threads():
+    """host threads this process may use (affinity and cgroup quota)"""
+    import os
+
+    n = len(os.sched_getaffinity(0))
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    return n
+
+
 def assert_same(ref, got, what=""):
     for f in FIELDS:
         if not np.array_equal(ref[f], got[f]):
@@ -146,9 +160,8 @@ def test_config3_full_65536_seeds_properties():
     cfg, wl = m.Config(), m.Workload.raft(faults=7)
     full, bm, st = run_gpu(cfg, wl, 0, 65536)
     assert st["n_unfinished"] == 0
-    cap = full["status"] == m.ST_FAIL_CAPACITY
-    assert cap.mean() < 0.01, "capacity overflows must stay rare (and are never silent)"
-    assert ((full["status"] == m.ST_PASS) | cap).all()
+    assert (full["status"] == m.ST_FAIL_CAPACITY).sum() == 0, "no bounded table may overflow at the BASELINE size"
+    assert (full["status"] == m.ST_PASS).all()
     again, _, _ = run_gpu(cfg, wl, 0, 65536, S=14, L=2)
     assert np.array_equal(full, again)
     parts = [run_gpu(cfg, wl, r * 8192, 8192)[0] for r in range(8)]
@@ -167,9 +180,14 @@ def test_config4_etcd_16384_seeds_packet_drop_sweep(oracle):
         cfg = m.Config(packet_loss_rate=rate)
         got, bm, st = run_gpu(cfg, wl, 0, 16384)
         assert st["n_unfinished"] == 0 and st["n_pass"] == 16384 and not bm.any(), rate
-        lo = 2048 * i
-        ref = oracle.run_many(cfg, wl, lo, 512)
-        assert_same(ref, got[lo:lo + 512], f"config 4 loss {rate}")
+        # the WHOLE batch against the oracle where the host can afford it (16384 etcd seeds are ~1.4e7 events: a
+        # second on >= 16 threads), else a 512-seed window that moves with the rate
+        if host_threads() >= 16:
+            lo, k = 0, 16384
+        else:
+            lo, k = 2048 * i, 512
+        ref = oracle.run_many(cfg, wl, lo, k)
+        assert_same(ref, got[lo:lo + k], f"config 4 loss {rate}")
         ok_ops = int(got["user"][:, 0].sum())
         assert (got["user"][:, 0] + got["user"][:, 3] >= 64).all()  # every op ended as ok or error (+ lease grants)
         assert prev_ok is None or ok_ops < prev_ok
@@ -194,8 +212,10 @@ def test_config5_tonic_32768_seeds_kill_restart_chaos(oracle):
     cfg, wl = m.Config(), m.Workload.tonic()
     got, bm, st = run_gpu(cfg, wl, 0, 32768)
     assert st["n_unfinished"] == 0 and st["n_pass"] == 32768 and not bm.any()
-    ref = oracle.run_many(cfg, wl, 20000, 384)
-    assert_same(ref, got[20000:20384], "config 5")
+    # a window against the oracle: 8192 seeds (1.8e8 events) where the host has >= 16 threads, else 384
+    k = 8192 if host_threads() >= 16 else 384
+    ref = oracle.run_many(cfg, wl, 20000, k)
+    assert_same(ref, got[20000:20000 + k], "config 5")
     starts, replies, handled = got["user"][:, 1], got["user"][:, 0], got["user"][:, 2]
     assert (starts >= 6).all() and (starts <= 16).all() and (handled >= replies).all() and (replies > 0).all()
     again, _, _ = run_gpu(cfg, wl, 0, 32768, S=9, L=2)
@@ -274,9 +294,107 @@ def test_summary_bitmap_and_first_failing_seed(oracle):
         m.Builder(seed=e.value.seed, count=1).run(wl)
 
 
-def test_builder_check_determinism_and_pass():
-    res, st = m.Builder(seed=5, count=64, check=True).run(m.Workload.pingpong(rounds=10))
-    assert st["n_pass"] == 64
+def test_builder_check_determinism_and_pass(oracle):
+    # builder.rs:126-128: under the check only `seed` runs, twice, through Runtime::check_determinism
+    rec, st = m.Builder(seed=5, count=64, check=True).run(m.Workload.pingpong(rounds=10))
+    assert st is None and rec["status"] == m.ST_PASS
+    assert rec["trace_hash"] == oracle.run_many(m.Config(), m.Workload.pingpong(rounds=10), 5, 1)["trace_hash"][0]
+    res, st = m.Builder(seed=5, count=64).run(m.Workload.pingpong(rounds=10))
+    assert st["n_pass"] == 64 and len(res) == 64
+    # a failing seed under the check is the reference's panic_with_info
+    with pytest.raises(m.SimulationFailure):
+        m.check_determinism(0, m.Config(packet_loss_rate=1.0), m.Workload.pingpong(rounds=3))
+
+
+DLOG_CASES = [c for c in CASES if c[0] in ("sleep", "pingpong-buggify-medium-latency", "pingpong-loss-deadlocks", "raft-faults",
+                                            "stream-partitions-loss20", "etcd-timeouts-3clients", "etcd-lease-admin-timeouts",
+                                            "tonic-request-timeouts-everything", "signal-interval-skip-ctrlc-kills",
+                                            "chaos-restart-on-panic")]
+
+
+@pytest.mark.parametrize("name,cfg,wl,base,n", DLOG_CASES, ids=[c[0] for c in DLOG_CASES])
+def test_device_determinism_log_matches_oracle(oracle, name, cfg, wl, base, n):
+    """Runtime::check_determinism's per-draw log (rand.rs:64-89) from the replay kernel: byte for byte the oracle's —
+    one byte per GlobalRng::with call, (next u8 of a clone of the rng) ^ fold(elapsed) — and the oracle's check
+    mode accepts it (and rejects a corrupted copy, naming a draw)."""
+    with m.Batch(cfg, 0) as b:
+        b.load(wl)
+        for seed in (base, base + 5):
+            log, rec = b.determinism_log(seed)
+            ref, r = oracle.determinism_log(cfg, wl, seed, "oracle")
+            assert len(log) == len(ref) and np.array_equal(log, ref), f"{name} seed {seed}"
+            assert rec["trace_hash"] == r["trace_hash"] and rec["draws"] == r["draws"]
+            assert oracle.check_against_log(cfg, wl, seed, log)
+            small, _ = b.determinism_log(seed, cap=7)  # a short buffer is filled, the count still says how many
+            assert np.array_equal(small, ref[: len(small)]) or len(ref) <= 7
+
+
+def test_device_summary_sharded_layout_equals_host_restatement(oracle):
+    """msim_batch_summarize_sharded: counters, the own first-fail slot and the bits at their GLOBAL position — for a
+    shard that starts at a non-multiple of 32, seeds above 2^63, and an empty shard."""
+    import torch
+
+    cfg, wl = m.Config(), m.Workload.raft(duration_ms=1500, bug=1, faults=7)
+    for seed_base, n_total, rank, world in ((40, 150, 1, 2), (2**64 - 200, 70, 0, 2), (0, 333, 2, 3)):
+        first, count = D.shard(seed_base, n_total, rank, world)
+        n64 = sum(D.sharded_layout(n_total, world))
+        buf = torch.full((n64,), 0x5A5A5A5A, dtype=torch.int64, device="cuda")
+        with m.Batch(cfg, 0) as b:
+            b.load(wl).run(first, count)
+            b.summarize_sharded_into(buf.data_ptr(), n64 * 8, rank, world, seed_base, n_total)
+            res, _, _ = b.results()
+        want = D.sharded_summary_from_results(res, first, rank, world, seed_base, n_total)
+        assert np.array_equal(buf.cpu().numpy(), want), (seed_base, n_total, rank, world)
+        assert np.array_equal(res["trace_hash"], oracle.run_many(cfg, wl, first, count)["trace_hash"])
+    # a rank whose shard is empty never ran: zeros + "no failure" in its slot
+    with m.Batch(cfg, 0) as b:
+        b.load(wl)
+        buf = torch.full((sum(D.sharded_layout(2, 3)),), 7, dtype=torch.int64, device="cuda")
+        b.summarize_sharded_into(buf.data_ptr(), buf.numel() * 8, 2, 3, 41, 2)
+        h = buf.cpu().numpy()
+        assert h[8 + 2] == -1 and (np.delete(h, 10) == 0).all()
+
+
+def test_resume_needs_a_checkpoint_of_the_current_run():
+    # a burst run leaves a checkpoint; a later run-to-completion launch (other size, other program) must not let
+    # msim_batch_resume reload the stale image
+    from madsim_b200 import _native as N
+
+    with m.Batch(m.Config(), 0) as b:
+        b.load(m.Workload.raft(duration_ms=1000)).run(0, 64, max_events_per_seed=500)
+        b.resume(500)
+        b.run(0, 300)  # run to completion: no checkpoint
+        ref, _, _ = b.results()
+        with pytest.raises(m.MsimError) as e:
+            b.resume(100)
+        assert e.value.code == N.ESTATE
+        b.load(m.Workload.pingpong(rounds=5))
+        with pytest.raises(m.MsimError) as e:
+            b.resume(100)
+        assert e.value.code == N.ESTATE
+        got, _, _ = b.run(0, 300).results()
+        assert (got["status"] == m.ST_PASS).all()
+
+
+def test_builder_jobs_shards_over_the_visible_gpus(oracle):
+    # MADSIM_TEST_JOBS (builder.rs:134-150): here the GPUs of the box; one GPU = one shard, same results either way
+    wl = m.Workload.raft(duration_ms=1500, faults=7)
+    res, st = m.Builder(seed=11, count=257, jobs=8).run(wl)
+    assert st["n_seeds"] == 257 and st["n_pass"] == 257
+    assert np.array_equal(res["trace_hash"], oracle.run_many(m.Config(), wl, 11, 257)["trace_hash"])
+
+
+@pytest.mark.parametrize("wl,S,L", [(m.Workload.stream(), 112, 4), (m.Workload.chaos(rounds=12, panics=2), 140, 5),
+                                    (m.Workload.raft(duration_ms=2500, faults=7), 28, 7), (m.Workload.etcd(timeout_rate=0.1), 50, 2),
+                                    (m.Workload.tonic(rounds=4), 20, 3), (m.Workload.signal(behavior=1), 100, 32)],
+                         ids=["stream", "chaos", "raft", "etcd", "tonic", "signal"])
+def test_lockstep_multilane_kernel_matches_oracle(oracle, wl, S, L):
+    # msim_step_kernel_ml: a warp's lanes walk the phases of the event step together (votes between the phases);
+    # per seed the result must not depend on how lanes are grouped
+    cfg = m.Config(packet_loss_rate=0.02)
+    got, _, st = run_gpu(cfg, wl, 3, 700, S=S, L=L | m.GEOMETRY_LOCKSTEP)
+    assert_same(oracle.run_many(cfg, wl, 3, 700), got, "lock-step kernel")
+    assert st["lanes_per_warp"] == L
 
 
 def test_capacity_overflow_is_reported_not_silent():
@@ -324,7 +442,7 @@ def test_sharded_run_single_rank_and_device_summary():
     res, bm, st = run.batch.results()
     assert out["n_seeds"] == 1000 and out["n_fail"] == st["n_fail"] and out["ev_pop"] == st["ev_pop"]
     assert out["first_fail_seed"] == (None if st["n_fail"] == 0 else st["first_fail_seed"])
-    assert np.array_equal(bitmap.cpu().numpy().view(np.uint32), bm)
+    assert np.array_equal(bitmap, bm)
     run.close()
 
 

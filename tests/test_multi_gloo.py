@@ -37,22 +37,22 @@ def _worker(rank, world, port, seed_base, n_total, q):
     wl = m.Workload.raft(duration_ms=1500, bug=1, faults=7)
     first, count = D.shard(seed_base, n_total, rank, world)
     res = o.run_many(m.Config(), wl, first, count, jobs=2) if count else np.zeros(0, dtype=m.SEED_RESULT_DTYPE)
-    c, bm = D.summary_from_results(res, first)
-    counters = torch.from_numpy(c.view(np.int64).copy())
-    bitmap = torch.from_numpy(bm.view(np.int32).copy())
-    out, gbm = D.reduce_summary(counters, bitmap, first, seed_base, n_total)
+    # what msim_batch_summarize_sharded writes on the device, restated on the host; then the ONE all-reduce
+    buf = torch.from_numpy(D.sharded_summary_from_results(res, first, rank, world, seed_base, n_total))
+    D.reduce_summary(buf, n_total, world)
+    out, gbm = D.finish_summary(buf.numpy(), n_total, world)
     if rank == 0:
-        q.put((out, gbm.numpy().view(np.uint32).tolist()))
+        q.put((out, gbm.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_total", [(2, 150), (3, 100)])
-def test_sharded_reduction_equals_single_process(oracle, world, n_total):
+@pytest.mark.parametrize("world,n_total,seed_base", [(2, 150, 40), (3, 100, 40), (3, 2, 41), (2, 70, 2**64 - 200)],
+                         ids=["ws2", "ws3", "ws3-empty-shard", "ws2-seeds-above-2^63"])
+def test_sharded_reduction_equals_single_process(oracle, world, n_total, seed_base):
     import madsim_b200 as m
     from madsim_b200 import dist as D
 
-    seed_base = 40
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -68,6 +68,7 @@ def test_sharded_reduction_equals_single_process(oracle, world, n_total):
     c, bm = D.summary_from_results(ref, seed_base)
     assert out["ev_pop"] == int(c[0]) and out["ev_fire"] == int(c[1]) and out["draws"] == int(c[2])
     assert out["n_pass"] == int(c[3]) and out["n_fail"] == int(c[4]) and out["n_seeds"] == n_total
-    assert out["n_fail"] > 0, "the double-vote bug must be caught in this range"
-    assert out["first_fail_seed"] == int(c[6])
+    if n_total > 50:
+        assert out["n_fail"] > 0, "the double-vote bug must be caught in this range"
+    assert out["first_fail_seed"] == (int(c[6]) if int(c[4]) else None)
     assert gbm == bm.tolist()

@@ -388,7 +388,7 @@ int state_bytes_of(uint32_t workload, uint64_t flags = 0) {
     case MSIM_WL_CHAOS: return Layout<WL_Chaos::Caps>::BYTES;
     case MSIM_WL_STREAM: return Layout<WL_Stream::Caps>::BYTES;
     case MSIM_WL_ETCD: return Layout<WL_Etcd::Caps>::BYTES;
-    case MSIM_WL_TONIC: return (flags & 8) ? Layout<WL_TonicBig::Caps>::BYTES : Layout<WL_Tonic::Caps>::BYTES;
+    case MSIM_WL_TONIC: return tonic_variant(flags, [](auto wl) { return (int)Layout<typename decltype(wl)::Caps>::BYTES; });
     case MSIM_WL_SIGNAL: return Layout<WL_Signal::Caps>::BYTES;
   }
   return -1;
@@ -506,7 +506,7 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
     case MSIM_WL_STREAM: e = launch_wl<WL_Stream>(a, grid, block, b->smem, b->stream); break;
     case MSIM_WL_ETCD: e = launch_wl<WL_Etcd>(a, grid, block, b->smem, b->stream); break;
     case MSIM_WL_TONIC:
-      e = (a.P.p[2] & 8) ? launch_wl<WL_TonicBig>(a, grid, block, b->smem, b->stream) : launch_wl<WL_Tonic>(a, grid, block, b->smem, b->stream);
+      e = tonic_variant(a.P.p[2], [&](auto wl) { return launch_wl<decltype(wl)>(a, grid, block, b->smem, b->stream); });
       break;
     case MSIM_WL_SIGNAL: e = launch_wl<WL_Signal>(a, grid, block, b->smem, b->stream); break;
     default: return set_err(MSIM_EINVAL, "unknown workload");

@@ -19,7 +19,11 @@ namespace msim {
 
 /// BIG: the capacities of the request-timeout schedule (flag 8): every pending poll inside time::timeout adds a
 /// timer that lingers 1-5 s, and `delay` response tasks live 10 s.
-template <bool BIG>
+/// STREAMING: the program also makes server- / client-streaming and bidi calls (flag 2).  The plain unary program
+/// (BASELINE config 5) is its own instantiation: none of the streaming state machines, no Sender::closed() waits,
+/// no split connection ends, two queued payloads per direction instead of four — 25 seeds per CTA instead of 20
+/// and a hot loop a third smaller (the kernels are instruction-fetch bound).
+template <bool BIG, bool STREAMING = true>
 struct WL_TonicT {
   enum : int { S_HANDLED = 0, S_CNT, S_ROUND, S_C, S_FAILURES, S_END };  // wl_s scalars
   enum : int { F_REPLIES = 0, F_STARTS, F_NFIELD };           // wl_w per client node
@@ -29,10 +33,10 @@ struct WL_TonicT {
     static constexpr bool USES_JOIN = false;
     static constexpr bool USES_KILL = true;
     static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
-    static constexpr bool USES_CLOSED = true;   // does any task await Sender::closed()?
-    static constexpr bool USES_SPLIT = true;    // does any task give the Sender half of its connection to another task?
-    static constexpr bool USES_TIMEOUT = true;   // does any task wrap awaits in time::timeout (beyond call_timeout)?
-    static constexpr int NCONN = BIG ? 64 : 32, NCQ = 4, NACC = 32;  // a client-streaming call queues header + 3 items at a slow server
+    static constexpr bool USES_CLOSED = STREAMING;  // does any task await Sender::closed()? (the streaming response tasks)
+    static constexpr bool USES_SPLIT = STREAMING;   // does any task give the Sender half of its connection to another task? (bidi)
+    static constexpr bool USES_TIMEOUT = BIG;    // time::timeout around the unary calls: only the request-timeout schedule (flag 8 = the BIG variant)
+    static constexpr int NCONN = BIG ? 64 : 32, NCQ = STREAMING ? 4 : 2, NACC = 32;  // a client-streaming call queues header + 3 items at a slow server
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_RSP_BIDI, K_SENDER };
   enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u, DELAY_NAME = 0x616c6564u };
@@ -55,7 +59,7 @@ struct WL_TonicT {
   static MSIM_HD int call_failed(E& e, int t, u32 code) {
     const bool deadline = e.ret == -3 && code == 71 && e.t_a(t) == DELAY_NAME;  // what `delay` must end in
     if (!deadline && !(e.P->p[2] & FLAG_SERVER_CRASH)) return panic(e, code);
-    if (e.t_handle(t) != NONE8) {
+    if (Caps::USES_SPLIT && e.t_handle(t) != NONE8) {
       if (e.t_handle(t) & 0x80)
         e.join_detach(e.t_handle(t) & 0x7f);
       else
@@ -64,7 +68,7 @@ struct WL_TonicT {
     }
     e.conn_drop_end(t);
     e.sock_unref(t);
-    e.t_dl2(t) = E::NONE64;  // the Timeout future is gone either way
+    if (Caps::USES_TIMEOUT) e.t_dl2(t) = E::NONE64;  // the Timeout future is gone either way
     if (deadline)
       e.wl_w(F_REPLIES, e.t_node(t))++;
     else
@@ -84,7 +88,8 @@ struct WL_TonicT {
     using L = typename E::L;
     const Params& P = *e.P;
     const u32 n_clients = P.n_nodes - 1;
-    for (;;) switch (e.t_kind(t) * 32 + e.t_pc(t)) {
+    // kinds K_RSP_STREAM.. exist only in the streaming program: masking the kind tells the compiler so (their cases go)
+    for (;;) switch ((STREAMING ? (u32)e.t_kind(t) : ((u32)e.t_kind(t) & 3u)) * 32 + e.t_pc(t)) {
         // ---- wl_tonic_main ----
         case K_MAIN * 32 + 0:
           e.t_pc(t) = 1;
@@ -171,7 +176,8 @@ struct WL_TonicT {
             continue;
           }
           e.t_pc(t) = 2;  // spawn the response task with tx (and the request)
-          e.ya = (((e.rv1 & CLIENT_STREAMING) && (e.rv1 & SERVER_STREAMING)) ? (u32)K_RSP_BIDI
+          e.ya = (!STREAMING ? (u32)K_RSP
+                  : ((e.rv1 & CLIENT_STREAMING) && (e.rv1 & SERVER_STREAMING)) ? (u32)K_RSP_BIDI
                   : (e.rv1 & CLIENT_STREAMING) ? (u32)K_RSP_CSTREAM
                   : (e.rv1 & SERVER_STREAMING) ? (u32)K_RSP_STREAM
                                                : (u32)K_RSP) | SPAWN_CONN, e.yb = e.t_node(t), e.yc = e.rv0, e.yd = e.t_b(t), e.xa = e.rv1, e.xb = 0;
@@ -335,8 +341,8 @@ struct WL_TonicT {
           return RQ_GEN_RANGE;
         case K_CLIENT * 32 + 4:  // Grpc::unary / server_streaming -> connect_ep: Endpoint::connect
           e.t_a(t) = e.ret64 == 0 ? (u32)ERROR_NAME : (u32)NAME;
-          e.t_c(t) = ((P.p[2] & FLAG_STREAMING_MIX) && e.ret64 >= 1 && e.ret64 <= 6) ? (u32)e.ret64 : 0u;  // 1..3: lots_of_replies, 4: lots_of_greetings, 5..6: bidi_hello
-          if ((P.p[2] & FLAG_TIMEOUTS) && e.t_c(t) == 0) {  // with_timeout (client.rs:246-258): unary calls only
+          e.t_c(t) = (STREAMING && (P.p[2] & FLAG_STREAMING_MIX) && e.ret64 >= 1 && e.ret64 <= 6) ? (u32)e.ret64 : 0u;  // 1..3: lots_of_replies, 4: lots_of_greetings, 5..6: bidi_hello
+          if (Caps::USES_TIMEOUT && (P.p[2] & FLAG_TIMEOUTS) && e.t_c(t) == 0) {  // with_timeout (client.rs:246-258): unary calls only
             u64 tmo = NS_PER_SEC;  // Endpoint::timeout(1 s)
             if (e.ret64 == 7 || e.ret64 == 8) e.t_a(t) = DELAY_NAME;
             if (e.ret64 == 8) tmo = 5 * NS_PER_SEC;  // Request::set_timeout overrides the channel's
@@ -358,12 +364,12 @@ struct WL_TonicT {
           return RQ_CONNECT1;
         case K_CLIENT * 32 + 7:
           if (e.ret < 0) return call_failed(e, t, 71);
-          if (e.t_c(t) >= 5) {  // bidi: spawn the task that sends the requests; it takes the Sender
+          if (STREAMING && e.t_c(t) >= 5) {  // bidi: spawn the task that sends the requests; it takes the Sender
             e.t_pc(t) = 15;
             e.ya = K_SENDER | SPAWN_CONN_TX | SPAWN_JOINABLE, e.yb = e.t_node(t), e.yc = e.t_b(t), e.yd = 0, e.xa = e.xb = 0;
             return RQ_SPAWN;
           }
-          if (e.t_c(t) == 4) {  // client streaming: the stream-start header, then hello_stream's items
+          if (STREAMING && e.t_c(t) == 4) {  // client streaming: the stream-start header, then hello_stream's items
             e.t_c(t) = 32;      // 32 + items sent
             e.t_a(t) = 0;       // fold of the names sent
             e.t_pc(t) = 11;
@@ -371,7 +377,7 @@ struct WL_TonicT {
             return RQ_CH_SEND;
           }
           e.t_pc(t) = 8;
-          e.yb = e.t_a(t), e.yc = e.t_b(t) | (e.t_c(t) ? (u32)SERVER_STREAMING : 0u);
+          e.yb = e.t_a(t), e.yc = e.t_b(t) | ((STREAMING && e.t_c(t)) ? (u32)SERVER_STREAMING : 0u);
           return RQ_CH_SEND;
         case K_CLIENT * 32 + 8:
           if (e.ret < 0) return call_failed(e, t, 71);
@@ -381,7 +387,7 @@ struct WL_TonicT {
           if (e.ret < 0) return call_failed(e, t, 71);
           u32 node = e.t_node(t);
           u32 st = e.rv0, reply = e.rv1;
-          if (e.t_c(t)) {  // the header of a server-streaming call
+          if (STREAMING && e.t_c(t)) {  // the header of a server-streaming call
             if (st != ST_OK) return panic(e, 75);
             if (e.t_c(t) == 3) {  // drop the response stream at once (tests/test.rs:204-230)
               e.conn_drop_end(t);
@@ -398,7 +404,7 @@ struct WL_TonicT {
           }
           e.conn_drop_end(t);  // rx, tx, then the last BindGuard reference
           e.sock_unref(t);
-          e.t_dl2(t) = E::NONE64;  // the call completed inside its timeout
+          if (Caps::USES_TIMEOUT) e.t_dl2(t) = E::NONE64;  // the call completed inside its timeout
           if (e.t_a(t) == DELAY_NAME) return panic(e, 80);  // delay must end in DeadlineExceeded
           if (e.t_a(t) == ERROR_NAME) {
             if (st != ST_INVALID_ARGUMENT) return panic(e, 72);
@@ -412,6 +418,7 @@ struct WL_TonicT {
           return RQ_SLEEP_FOR;
         }
         case K_CLIENT * 32 + 10: {  // Streaming::message(): three replies, then the EOF status
+          if (!STREAMING) return panic(e, 0xbad);  // streaming calls only
           if (e.ret < 0) return call_failed(e, t, 71);
           u32 node = e.t_node(t), i = e.t_c(t) - 16;
           if (i < 3) {
@@ -429,9 +436,11 @@ struct WL_TonicT {
           return RQ_SLEEP_FOR;
         }
         case K_CLIENT * 32 + 11:  // header sent (tx.send(..).await?), then: yield item i; sleep(1 s)
+          if (!STREAMING) return panic(e, 0xbad);  // streaming calls only
           if (e.ret < 0) return call_failed(e, t, 71);
           // fallthrough
         case K_CLIENT * 32 + 12: {
+          if (!STREAMING) return panic(e, 0xbad);  // streaming calls only
           u32 i = e.t_c(t) - 32;
           if (i >= 3) {  // the request stream ended: send_request_stream returns, its Sender drops
             e.conn_drop_tx(t);
@@ -444,6 +453,7 @@ struct WL_TonicT {
           return RQ_CH_SEND;
         }
         case K_CLIENT * 32 + 13:
+          if (!STREAMING) return panic(e, 0xbad);  // streaming calls only
           if (e.ret < 0) {  // the server closed the stream prematurely: stop sending
             e.t_c(t) = 35;
             e.t_pc(t) = 12;
@@ -454,6 +464,7 @@ struct WL_TonicT {
           e.xa = NS_PER_SEC;
           return RQ_SLEEP_FOR;
         case K_CLIENT * 32 + 14: {
+          if (!STREAMING) return panic(e, 0xbad);  // streaming calls only
           if (e.ret < 0) return call_failed(e, t, 71);
           u32 node = e.t_node(t);
           if (e.rv0 != ST_OK || e.rv1 != e.t_a(t) * 31u + node) return panic(e, 78);
@@ -466,18 +477,21 @@ struct WL_TonicT {
           return RQ_SLEEP_FOR;
         }
         case K_CLIENT * 32 + 15:  // a plain JoinHandle until the response stream is first polled
+          if (!STREAMING) return panic(e, 0xbad);  // streaming calls only
           e.t_handle(t) = (u8)((u32)e.ret | 0x80u);
           e.t_a(t) = e.t_c(t);  // 5, or 6 = drop the stream after the first reply
           e.t_c(t) = 0;         // replies read
           e.t_pc(t) = 16;
           return RQ_CH_RECV;
         case K_CLIENT * 32 + 16:  // the header: Result<Response<()>>
+          if (!STREAMING) return panic(e, 0xbad);  // streaming calls only
           if (e.ret < 0) return call_failed(e, t, 71);
           if (e.rv0 != ST_OK) return panic(e, 75);
           e.t_handle(t) = e.t_handle(t) & 0x7f;  // first poll of the response stream: `_task = task.cancel_on_drop()`
           e.t_pc(t) = 17;
           return RQ_CH_RECV;
         case K_CLIENT * 32 + 17: {  // while let Some(reply) = stream.message().await.unwrap()
+          if (!STREAMING) return panic(e, 0xbad);  // streaming calls only
           if (e.ret < 0) return call_failed(e, t, 71);
           u32 node = e.t_node(t);
           bool done = false;
@@ -505,7 +519,15 @@ struct WL_TonicT {
       }
   }
 };
-using WL_Tonic = WL_TonicT<false>;
-using WL_TonicBig = WL_TonicT<true>;
+using WL_TonicUnary = WL_TonicT<false, false>;  // flags without 2 and 8: BASELINE config 5
+using WL_Tonic = WL_TonicT<false, true>;        // + streaming calls (flag 2)
+using WL_TonicBig = WL_TonicT<true, true>;      // + request timeouts (flag 8)
+/// the instantiation that runs a given flags word (p[2]): f(WL{}) with the chosen program type
+template <class F>
+inline auto tonic_variant(u64 flags, F&& f) {
+  if (flags & 8) return f(WL_TonicBig{});
+  if (flags & 2) return f(WL_Tonic{});
+  return f(WL_TonicUnary{});
+}
 
 }  // namespace msim

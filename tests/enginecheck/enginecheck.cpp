@@ -160,7 +160,7 @@ extern "C" int enginecheck_run_ml(const msim_config* cfg, const msim_workload_de
     case MSIM_WL_STREAM: return run_wl_ml<WL_Stream>(P, seed_base, n, lanes, out);
     case MSIM_WL_ETCD: return run_wl_ml<WL_Etcd>(P, seed_base, n, lanes, out);
     case MSIM_WL_TONIC:
-      return (P.p[2] & 8) ? run_wl_ml<WL_TonicBig>(P, seed_base, n, lanes, out) : run_wl_ml<WL_Tonic>(P, seed_base, n, lanes, out);
+      return tonic_variant(P.p[2], [&](auto wl) { return run_wl_ml<decltype(wl)>(P, seed_base, n, lanes, out); });
     case MSIM_WL_SIGNAL: return run_wl_ml<WL_Signal>(P, seed_base, n, lanes, out);
   }
   return MSIM_EINVAL;
@@ -181,8 +181,7 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
     case MSIM_WL_STREAM: return run_wl<WL_Stream>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_ETCD: return run_wl<WL_Etcd>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
     case MSIM_WL_TONIC:
-      return (P.p[2] & 8) ? run_wl<WL_TonicBig>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr)
-                          : run_wl<WL_Tonic>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
+      return tonic_variant(P.p[2], [&](auto wl) { return run_wl<decltype(wl)>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr); });
     case MSIM_WL_SIGNAL: return run_wl<WL_Signal>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
   }
   return MSIM_EINVAL;
@@ -208,8 +207,7 @@ extern "C" int enginecheck_determinism_log(const msim_config* cfg, const msim_wo
     case MSIM_WL_STREAM: rc = run_wl<WL_Stream>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
     case MSIM_WL_ETCD: rc = run_wl<WL_Etcd>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
     case MSIM_WL_TONIC:
-      rc = (P.p[2] & 8) ? run_wl<WL_TonicBig>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr)
-                        : run_wl<WL_Tonic>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr);
+      rc = tonic_variant(P.p[2], [&](auto wl) { return run_wl<decltype(wl)>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); });
       break;
     case MSIM_WL_SIGNAL: rc = run_wl<WL_Signal>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
     default: return MSIM_EINVAL;

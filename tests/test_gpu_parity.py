@@ -386,7 +386,7 @@ def test_builder_jobs_shards_over_the_visible_gpus(oracle):
 
 @pytest.mark.parametrize("wl,S,L", [(m.Workload.stream(), 112, 4), (m.Workload.chaos(rounds=12, panics=2), 140, 5),
                                     (m.Workload.raft(duration_ms=2500, faults=7), 28, 7), (m.Workload.etcd(timeout_rate=0.1), 50, 2),
-                                    (m.Workload.tonic(rounds=4), 20, 3), (m.Workload.signal(behavior=1), 100, 32)],
+                                    (m.Workload.tonic(rounds=4), 18, 3), (m.Workload.signal(behavior=1), 100, 32)],
                          ids=["stream", "chaos", "raft", "etcd", "tonic", "signal"])
 def test_lockstep_multilane_kernel_matches_oracle(oracle, wl, S, L):
     # msim_step_kernel_ml: a warp's lanes walk the phases of the event step together (votes between the phases);

@@ -33,7 +33,11 @@ FIELDS = ("trace_hash", "elapsed_ns", "draws", "ev_pop", "ev_fire", "status", "f
 
 def main():
     cases = [c.split(":") for c in os.environ.get("CASES", "stream:16384,chaos:16384,signal:16384").split(",")]
-    geos = [tuple(int(x) for x in g.split(":")) for g in os.environ.get("GEOS", "28:1,56:2,112:4").split(",")]
+    # "S:L" lets the L lanes of a warp run free (the batch kernel); "S:Lk" sends them through the lock-step kernel
+    geos = []
+    for g in os.environ.get("GEOS", "28:1,56:2,112:4").split(","):
+        S, L = g.split(":")
+        geos.append((int(S), int(L.rstrip("k")) | (m.GEOMETRY_LOCKSTEP if L.endswith("k") else 0)))
     check = int(os.environ.get("CHECK", 256))
     out = []
     print(f"# {'wl':8s} {'seeds':>6s} {'S':>4s} {'L':>3s} {'warps':>5s} {'kernel_ms':>10s} {'Mev/s':>9s}  parity")
@@ -52,18 +56,21 @@ def main():
                         res, bitmap, st = b.results()
                         best = min(best, st["kernel_ms"])
             except Exception as e:  # geometry does not fit shared memory
-                print(f"  {name:8s} {n:6d} {S:4d} {L:3d}  -- {e}")
+                print(f"  {name:8s} {n:6d} {S:4d} {L & 0xff:3d}  -- {e}")
                 continue
             ev = int(st["ev_pop"] + st["ev_fire"])
             ok = None
             if ref is not None:
                 k = len(ref)
                 ok = all(np.array_equal(res[f][:k], ref[f]) for f in FIELDS)
-            rec = dict(wl=name, seeds=n, S=st["seeds_per_cta"], L=st["lanes_per_warp"], ctas=st["ctas"],
+            rec = dict(wl=name, seeds=n, S=st["seeds_per_cta"], L=st["lanes_per_warp"], lockstep=bool(L & m.GEOMETRY_LOCKSTEP),
+                       ctas=st["ctas"],
                        smem=st["smem_bytes"], kernel_ms=best, events=ev, mev_s=ev / best / 1e3, parity=ok,
                        n_cap=int((res["status"] == m.ST_FAIL_CAPACITY).sum()))
             warps = (rec["S"] + rec["L"] - 1) // rec["L"]
-            print(f"  {name:8s} {n:6d} {rec['S']:4d} {rec['L']:3d} {warps:5d} {best:10.3f} {rec['mev_s']:9.1f}  {ok}", flush=True)
+            tag = "k" if rec["lockstep"] else " "
+            print(f"  {name:8s} {n:6d} {rec['S']:4d} {rec['L']:3d}{tag} {warps:4d} {best:10.3f} {rec['mev_s']:9.1f}  {ok}  cap={rec['n_cap']}",
+                  flush=True)
             out.append(rec)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"ml_sweep_{os.environ.get('TAG', 'x')}.json"), "w"), indent=1)

@@ -108,6 +108,8 @@ typedef struct msim_config {
 #define MSIM_WL_TONIC 6     /* tonic-example Greeter under madsim-tonic + kill/restart chaos, BASELINE config 5 */
 #define MSIM_WL_SIGNAL 7    /* time::interval + MissedTickBehavior, signal::ctrl_c, Handle::send_ctrl_c (interval.rs, signal.rs) */
 #define MSIM_WL_ETCD 5      /* madsim-etcd-client SimServer + KV clients + linearizability check, BASELINE config 4 */
+#define MSIM_WL_ELECTION 8  /* madsim-etcd-client election API: campaign / proclaim / leader / observe / resign over the watcher
+                               (election.rs, service.rs:494-585, server.rs:71-95) — the reference's election() test            */
 
 /* parameter slots p[] per workload
  *  SLEEP    p0 = duration ns
@@ -131,6 +133,9 @@ typedef struct msim_config {
  *           DeadlineExceeded after 1 s / 5 s)
  *  SIGNAL   p0 = supervisor rounds (default 8), p1 = interval period ms (default 100),
  *           p2 = MissedTickBehavior (0 Burst, 1 Delay, 2 Skip), p3 = flags (1 = the worker installs a ctrl-c handler; default 1)
+ *  ELECTION n_nodes = 4 (server, two candidates, an observer); p0 = seconds the first leader holds before it revokes its
+ *           lease (default 30), p1 = SimServer::timeout_rate as IEEE f32 bits (default 0: any timed-out call fails the
+ *           test, as its unwrap() does in the reference); user[] = {leader changes observed, final revision, checksum, requests}
  *  CHAOS    p0 = rounds, p1 = period ms, p2 = worker panics on its first p2 starts (restart_on_panic)
  *                                                         */
 #define MSIM_RAFT_FAULT_CLOG_NODE 1u

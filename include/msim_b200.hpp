@@ -125,6 +125,15 @@ struct Workload {
     w.desc.n_nodes = clients + 1, w.desc.p[0] = ops, w.desc.p[2] = bits, w.desc.p[3] = bug, w.desc.p[7] = lease_admin ? 1 : 0;
     return w;
   }
+  /// madsim-etcd-client's election API as its own election() test drives it (tests/test.rs:129-232)
+  static Workload election(uint64_t hold_s = 30, float timeout_rate = 0.0f) {
+    Workload w;
+    check(msim_workload_default(MSIM_WL_ELECTION, &w.desc));
+    uint32_t bits;
+    std::memcpy(&bits, &timeout_rate, 4);
+    w.desc.p[0] = hold_s, w.desc.p[1] = bits;
+    return w;
+  }
   /// time::interval + MissedTickBehavior (0 Burst, 1 Delay, 2 Skip), signal::ctrl_c, Handle::send_ctrl_c
   static Workload signal(uint64_t rounds = 8, uint64_t period_ms = 100, uint32_t behavior = 0, bool catch_ctrl_c = true) {
     Workload w;

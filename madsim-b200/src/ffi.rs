@@ -33,6 +33,7 @@ pub const MSIM_WL_STREAM: u32 = 4;
 pub const MSIM_WL_ETCD: u32 = 5;
 pub const MSIM_WL_TONIC: u32 = 6;
 pub const MSIM_WL_SIGNAL: u32 = 7;
+pub const MSIM_WL_ELECTION: u32 = 8;
 
 /// `struct msim_config` — madsim::Config{ net{ packet_loss_rate, send_latency } } + Runtime knobs
 #[repr(C)]

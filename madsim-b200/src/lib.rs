@@ -142,6 +142,10 @@ impl Workload {
     pub fn tonic() -> Self {
         Workload(Self::defaults(ffi::MSIM_WL_TONIC))
     }
+    /// madsim-etcd-client's election API (campaign / proclaim / leader / observe / resign) as its `election()` test drives it
+    pub fn election() -> Self {
+        Workload(Self::defaults(ffi::MSIM_WL_ELECTION))
+    }
     pub fn chaos() -> Self {
         Workload(Self::defaults(ffi::MSIM_WL_CHAOS))
     }

@@ -34,6 +34,7 @@ from ._native import (  # noqa: F401
     ST_RUNNING,
     STATUS_NAMES,
     WL_CHAOS,
+    WL_ELECTION,
     WL_PINGPONG,
     WL_RAFT,
     WL_SLEEP,

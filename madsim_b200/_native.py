@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("MSIM_B200_LIB") or os.path.join(_HERE, "libmsim_b200.
 
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, ESTATE, ERANGE = 0, -1, -2, -3, -4, -5, -6
 ST_RUNNING, ST_PASS, ST_FAIL_ASSERT, ST_FAIL_DEADLOCK, ST_FAIL_TIME_LIMIT, ST_FAIL_CAPACITY = range(6)
-WL_SLEEP, WL_PINGPONG, WL_RAFT, WL_CHAOS, WL_STREAM, WL_ETCD, WL_TONIC, WL_SIGNAL = range(8)
+WL_SLEEP, WL_PINGPONG, WL_RAFT, WL_CHAOS, WL_STREAM, WL_ETCD, WL_TONIC, WL_SIGNAL, WL_ELECTION = range(9)
 EV_NAMES = {1: "POLL", 2: "DROP", 3: "PARK", 4: "SKIP", 5: "WAKE", 6: "DELIVER", 7: "RESTART"}
 STATUS_NAMES = {0: "RUNNING", 1: "PASS", 2: "FAIL_ASSERT", 3: "FAIL_DEADLOCK", 4: "FAIL_TIME_LIMIT", 5: "FAIL_CAPACITY"}
 RAFT_FAULT_CLOG_NODE, RAFT_FAULT_CLOG_LINK, RAFT_FAULT_CLOCK_JUMP = 1, 2, 4

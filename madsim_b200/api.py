@@ -137,11 +137,21 @@ class Workload:
         supervisor sends ctrl-c to / restarts (time/interval.rs, signal.rs, Handle::send_ctrl_c)."""
         return Workload(N.WL_SIGNAL, 1, [rounds, period_ms, behavior, int(catch), 0, 0, 0, 0])
 
+    @staticmethod
+    def election(hold_s: int = 30, timeout_rate: float = 0.0) -> "Workload":
+        """madsim-etcd-client's election API — campaign / proclaim / leader / observe / resign over the server's
+        watcher — as the reference's own `election()` test drives it (tests/test.rs:129-232): a first leader that
+        holds `hold_s` seconds before it revokes its lease, a second candidate waiting in campaign(), an observer."""
+        import struct
+
+        bits = struct.unpack("<I", struct.pack("<f", timeout_rate))[0]
+        return Workload(N.WL_ELECTION, 4, [hold_s, bits, 0, 0, 0, 0, 0, 0])
+
     def to_c(self) -> N.MsimWorkloadDesc:
         return N.MsimWorkloadDesc(self.workload, self.n_nodes, (C.c_uint64 * 8)(*[int(x) for x in self.p]))
 
     def name(self) -> str:
-        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos", 4: "stream", 5: "etcd", 6: "tonic", 7: "signal"}.get(self.workload, "?")
+        return {0: "sleep", 1: "pingpong", 2: "raft", 3: "chaos", 4: "stream", 5: "etcd", 6: "tonic", 7: "signal", 8: "election"}.get(self.workload, "?")
 
 
 class SimulationFailure(AssertionError):

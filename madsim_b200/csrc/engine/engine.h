@@ -182,7 +182,9 @@ struct Layout {
   static constexpr int NTS = C::USES_SPLIT ? C::NT : 0;
   static constexpr int B_T_CONNHALF = B_T_CONN + (C::NCONN ? C::NT : 0);  // [NTS] halves of the end this future owns: 1 Sender, 2 Receiver
   static constexpr int B_T_HANDLE = B_T_CONNHALF + NTS;    // [NTS] task whose FallibleTask (cancel_on_drop) this future holds, or NONE8
-  static constexpr int B_CH_HEAD = B_T_HANDLE + NTS;       // [ND] FIFO head / length
+  static constexpr int NT2 = C::USES_CONN2 ? C::NT : 0;
+  static constexpr int B_T_CONN2 = B_T_HANDLE + NTS;       // [NT2] a second connection end the future holds (parked: conn_swap)
+  static constexpr int B_CH_HEAD = B_T_CONN2 + NT2;        // [ND] FIFO head / length
   static constexpr int B_CH_LEN = B_CH_HEAD + ND;
   static constexpr int B_CH_PHASE = B_CH_LEN + ND;         // [ND] 0 idle, 1 back-off sleep, 2 arrival sleep
   static constexpr int B_CH_SRC = B_CH_PHASE + ND;         // [ND] test_link source node
@@ -234,6 +236,7 @@ struct Engine {
   MSIM_HD u8& t_sockgen(int t) const { return b(L::B_T_SOCKGEN, t); }
   MSIM_HD u8& t_msg(int t) const { return b(L::B_T_MSG, t); }
   MSIM_HD u8& t_conn(int t) const { return b(L::B_T_CONN, t); }
+  MSIM_HD u8& t_conn2(int t) const { return b(L::B_T_CONN2, t); }
   MSIM_HD u8& t_connhalf(int t) const { return b(L::B_T_CONNHALF, t); }
   MSIM_HD u8& t_handle(int t) const { return b(L::B_T_HANDLE, t); }
   MSIM_HD u32& t_spawn(int t) const { return w(L::W_T_SPAWN, t); }
@@ -578,6 +581,10 @@ struct Engine {
         t_handle(t) = NONE8;
       }
       if (C::NCONN) conn_drop_end(t);
+      if (C::USES_CONN2 && t_conn2(t) != NONE8) {  // the parked end: declared earlier, dropped later
+        conn_swap(t);
+        conn_drop_end(t);
+      }
       sock_unref(t);
       t_wait(t) = W_NONE;
       t_flags(t) = f & ~TF_ALIVE;
@@ -625,6 +632,7 @@ MSIM_NOUNROLL
     t_sock(t) = NONE8;
     t_msg(t) = NONE8;
     if (C::NCONN) t_conn(t) = NONE8;
+    if (C::USES_CONN2) t_conn2(t) = NONE8;
     if (C::USES_SPLIT) t_connhalf(t) = 3, t_handle(t) = NONE8;
     if (C::USES_TIMEOUT) t_dl2(t) = NONE64;
     t_spawn(t) = idx;
@@ -1044,6 +1052,26 @@ MSIM_NOUNROLL
     t_conn(t) = NONE8;
     conn_drop_half(e, C::USES_SPLIT ? t_connhalf(t) : 3);
   }
+  /// A future that holds TWO connection ends (an ObserveStream kept open while another call is made, election.rs:79-86)
+  /// works on one at a time: conn_swap exchanges the active end with the parked one.  No await point.
+  MSIM_HD void conn_swap(int t) {
+    if (!C::USES_CONN2) return;
+    u8 a = t_conn(t);
+    t_conn(t) = t_conn2(t);
+    t_conn2(t) = a;
+  }
+  /// Sender::closed() inside a hand-written select (a state machine that waits for something the engine does not know,
+  /// e.g. a watcher event): true = the peer dropped its Receiver; otherwise this task is the one closed() will wake
+  MSIM_HD bool closed_or_register(int t) {
+    int d = t_conn(t);
+    if (!(ch_flags(d) & CH_RX_ALIVE)) return true;
+    if (C::USES_CLOSED) w(L::W_CH_CLOSED_WAITER, d) = ((u32)t << 20) | t_gen(t);
+    return false;
+  }
+  MSIM_HD void closed_unregister(int t) {  // the closed() future is dropped with its select
+    if (C::USES_CLOSED && t_conn(t) != NONE8) w(L::W_CH_CLOSED_WAITER, t_conn(t)) = NONE32;
+  }
+  MSIM_HD u32 waker_of(int t) const { return ((u32)t << 20) | t_gen(t); }
   /// Dropping only the Sender of the end a task holds (a request stream that ended: client.rs:171-196)
   MSIM_HD void conn_drop_tx(int t) {
     if (C::USES_SPLIT) t_connhalf(t) = t_connhalf(t) & ~1;

@@ -62,6 +62,10 @@ inline int workload_defaults(uint32_t workload, msim_workload_desc* d) {
       d->p[0] = 8;
       d->p[1] = 2000;
       return 0;
+    case MSIM_WL_ELECTION:
+      d->n_nodes = 4;
+      d->p[0] = 30;
+      return 0;
   }
   return MSIM_EINVAL;
 }
@@ -343,6 +347,20 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
         return MSIM_EINVAL;
       }
       break;
+    case MSIM_WL_ELECTION: {
+      if (P.n_nodes == 0) P.n_nodes = 4;
+      float rate;
+      u32 bits = (u32)wl.p[1];
+      std::memcpy(&rate, &bits, 4);
+      // the observer counts two keys about 20 s in, leases last 60 s (tests/test.rs:154-232)
+      if (P.n_nodes != 4 || wl.p[0] < 20 || wl.p[0] > 50 || !(rate >= 0.0f && rate <= 1.0f)) {
+        if (err) *err = "election: 4 nodes, 20 <= hold seconds <= 50, 0 <= timeout_rate <= 1";
+        return MSIM_EINVAL;
+      }
+      P.p[5] = rate == 1.0f ? 1 : 0;  // Bernoulli::new(timeout_rate as f64) (service.rs:166)
+      P.p[6] = rate == 1.0f ? 0 : (u64)((double)rate * 18446744073709551616.0);
+      break;
+    }
     default:
       if (err) *err = "unknown workload";
       return MSIM_EINVAL;

@@ -381,17 +381,7 @@ cudaError_t launch_wl(const KernelArgs& a, dim3 grid, dim3 block, size_t smem, c
 }
 
 int state_bytes_of(uint32_t workload, uint64_t flags = 0) {
-  switch (workload) {
-    case MSIM_WL_SLEEP: return Layout<WL_Sleep::Caps>::BYTES;
-    case MSIM_WL_PINGPONG: return Layout<WL_PingPong::Caps>::BYTES;
-    case MSIM_WL_RAFT: return Layout<WL_Raft::Caps>::BYTES;
-    case MSIM_WL_CHAOS: return Layout<WL_Chaos::Caps>::BYTES;
-    case MSIM_WL_STREAM: return Layout<WL_Stream::Caps>::BYTES;
-    case MSIM_WL_ETCD: return Layout<WL_Etcd::Caps>::BYTES;
-    case MSIM_WL_TONIC: return tonic_variant(flags, [](auto wl) { return (int)Layout<typename decltype(wl)::Caps>::BYTES; });
-    case MSIM_WL_SIGNAL: return Layout<WL_Signal::Caps>::BYTES;
-  }
-  return -1;
+  return with_workload(workload, flags, -1, [](auto wl) { return (int)Layout<typename decltype(wl)::Caps>::BYTES; });
 }
 
 }  // namespace
@@ -497,20 +487,10 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
   if (a.dynamic && n_grid > (uint32_t)b->sm_count) n_grid = (uint32_t)b->sm_count;  // 1 CTA per SM (shared memory)
   b->grid_launched = n_grid;
   dim3 grid(n_grid), block(b->threads);
-  cudaError_t e;
-  switch (b->wl.workload) {
-    case MSIM_WL_SLEEP: e = launch_wl<WL_Sleep>(a, grid, block, b->smem, b->stream); break;
-    case MSIM_WL_PINGPONG: e = launch_wl<WL_PingPong>(a, grid, block, b->smem, b->stream); break;
-    case MSIM_WL_RAFT: e = launch_wl<WL_Raft>(a, grid, block, b->smem, b->stream); break;
-    case MSIM_WL_CHAOS: e = launch_wl<WL_Chaos>(a, grid, block, b->smem, b->stream); break;
-    case MSIM_WL_STREAM: e = launch_wl<WL_Stream>(a, grid, block, b->smem, b->stream); break;
-    case MSIM_WL_ETCD: e = launch_wl<WL_Etcd>(a, grid, block, b->smem, b->stream); break;
-    case MSIM_WL_TONIC:
-      e = tonic_variant(a.P.p[2], [&](auto wl) { return launch_wl<decltype(wl)>(a, grid, block, b->smem, b->stream); });
-      break;
-    case MSIM_WL_SIGNAL: e = launch_wl<WL_Signal>(a, grid, block, b->smem, b->stream); break;
-    default: return set_err(MSIM_EINVAL, "unknown workload");
-  }
+  const cudaError_t unknown = cudaErrorInvalidDeviceFunction;
+  cudaError_t e = with_workload(b->wl.workload, a.P.p[2], unknown,
+                                [&](auto wl) { return launch_wl<decltype(wl)>(a, grid, block, b->smem, b->stream); });
+  if (e == unknown) return set_err(MSIM_EINVAL, "unknown workload");
   if (e != cudaSuccess) return set_err(MSIM_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   b->launches++;
   return MSIM_OK;

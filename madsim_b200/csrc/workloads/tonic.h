@@ -36,6 +36,7 @@ struct WL_TonicT {
     static constexpr bool USES_CLOSED = STREAMING;  // does any task await Sender::closed()? (the streaming response tasks)
     static constexpr bool USES_SPLIT = STREAMING;   // does any task give the Sender half of its connection to another task? (bidi)
     static constexpr bool USES_TIMEOUT = BIG;    // time::timeout around the unary calls: only the request-timeout schedule (flag 8 = the BIG variant)
+    static constexpr bool USES_CONN2 = false;    // does any task hold two connection ends at once?
     static constexpr int NCONN = BIG ? 64 : 32, NCQ = STREAMING ? 4 : 2, NACC = 32;  // a client-streaming call queues header + 3 items at a slow server
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_RSP_BIDI, K_SENDER };

@@ -124,6 +124,16 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
       case MSIM_WL_CHAOS:
         rt.block_on(wl_chaos_main(wl->p[0], wl->p[1], u32(wl->p[2]), &user));
         break;
+      case MSIM_WL_ELECTION: {
+        ElectionParams ep;
+        ep.hold_s = wl->p[0];
+        u32 bits = u32(wl->p[1]);
+        std::memcpy(&ep.timeout_rate, &bits, 4);
+        if (!(ep.timeout_rate >= 0.0f && ep.timeout_rate <= 1.0f) || ep.hold_s < 20 || ep.hold_s > 50) return MSIM_EINVAL;  // the observer counts two keys ~20 s in; leases last 60 s
+        rt.block_on(wl_election_main(ep, &user));
+        rt.teardown();
+        break;
+      }
       default:
         return MSIM_EINVAL;
     }

@@ -746,6 +746,36 @@ int main() {
   });
   run_case("etcd::kv (madsim-etcd-client/tests/test.rs:9-62)", [] { etcd_case(etcd_kv_client); });
   run_case("etcd::lease grant / leases / keep_alive / time_to_live / expiry / revoke / not found (tests/test.rs:64-128)", [] { etcd_case(etcd_lease_client); });
+  run_case("etcd::election campaign / proclaim / leader / observe / resign (madsim-etcd-client/tests/test.rs:129-232)", [] {
+    // the program IS the reference test (oracle/workloads_election.hpp): its assertions are panics; several seeds, and
+    // shorter holds, must all end with the observer having seen 1, 1.1, 1.2, 2 and the store at revision 9
+    for (u64 seed : {0ull, 1ull, 7ull, 123456789ull}) {
+      for (u64 hold : {30ull, 20ull}) {
+        Runtime rt(seed, Config{});
+        std::array<u32, 4> user{};
+        ElectionParams p;
+        p.hold_s = hold;
+        rt.block_on(wl_election_main(p, &user));
+        CHECK(user[0] == 4 && user[1] == 9 && user[3] == 15);
+        rt.teardown();
+      }
+    }
+    // a server that times requests out makes some `unwrap()` of the test panic — as it would in the reference
+    int panics = 0;
+    for (u64 seed = 0; seed < 20; seed++) {
+      Runtime rt(seed, Config{});
+      std::array<u32, 4> user{};
+      ElectionParams p;
+      p.timeout_rate = 0.2f;
+      try {
+        rt.block_on(wl_election_main(p, &user));
+      } catch (Panic&) {
+        panics++;
+      }
+      rt.teardown();
+    }
+    CHECK(panics > 0);
+  });
   run_case("tonic::basic unary + invalid_argument (tonic-example/tests/test.rs:22-70)", [] {
     Runtime rt;
     SocketAddr a{ip4(10, 0, 0, 1), 50051};

@@ -408,3 +408,4 @@ inline Async<u32> wl_stream_main(u64 msgs, u64 think_ns, u32 faults, std::array<
 #include "workloads_etcd.hpp"
 #include "workloads_tonic.hpp"
 #include "workloads_signal.hpp"
+#include "workloads_election.hpp"

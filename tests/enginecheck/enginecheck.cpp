@@ -152,18 +152,7 @@ extern "C" int enginecheck_run_ml(const msim_config* cfg, const msim_workload_de
   int rc = make_params(*cfg, *wl, &P, &err);
   if (rc) return rc;
   if (lanes == 0) lanes = 1;
-  switch (wl->workload) {
-    case MSIM_WL_SLEEP: return run_wl_ml<WL_Sleep>(P, seed_base, n, lanes, out);
-    case MSIM_WL_PINGPONG: return run_wl_ml<WL_PingPong>(P, seed_base, n, lanes, out);
-    case MSIM_WL_RAFT: return run_wl_ml<WL_Raft>(P, seed_base, n, lanes, out);
-    case MSIM_WL_CHAOS: return run_wl_ml<WL_Chaos>(P, seed_base, n, lanes, out);
-    case MSIM_WL_STREAM: return run_wl_ml<WL_Stream>(P, seed_base, n, lanes, out);
-    case MSIM_WL_ETCD: return run_wl_ml<WL_Etcd>(P, seed_base, n, lanes, out);
-    case MSIM_WL_TONIC:
-      return tonic_variant(P.p[2], [&](auto wl) { return run_wl_ml<decltype(wl)>(P, seed_base, n, lanes, out); });
-    case MSIM_WL_SIGNAL: return run_wl_ml<WL_Signal>(P, seed_base, n, lanes, out);
-  }
-  return MSIM_EINVAL;
+  return with_workload(wl->workload, P.p[2], (int)MSIM_EINVAL, [&](auto w) { return run_wl_ml<decltype(w)>(P, seed_base, n, lanes, out); });
 }
 
 extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed_base, uint64_t n,
@@ -173,18 +162,9 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
   std::string err;
   int rc = make_params(*cfg, *wl, &P, &err);
   if (rc) return rc;
-  switch (wl->workload) {
-    case MSIM_WL_SLEEP: return run_wl<WL_Sleep>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
-    case MSIM_WL_PINGPONG: return run_wl<WL_PingPong>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
-    case MSIM_WL_RAFT: return run_wl<WL_Raft>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
-    case MSIM_WL_CHAOS: return run_wl<WL_Chaos>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
-    case MSIM_WL_STREAM: return run_wl<WL_Stream>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
-    case MSIM_WL_ETCD: return run_wl<WL_Etcd>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
-    case MSIM_WL_TONIC:
-      return tonic_variant(P.p[2], [&](auto wl) { return run_wl<decltype(wl)>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr); });
-    case MSIM_WL_SIGNAL: return run_wl<WL_Signal>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
-  }
-  return MSIM_EINVAL;
+  return with_workload(wl->workload, P.p[2], (int)MSIM_EINVAL, [&](auto w) {
+    return run_wl<decltype(w)>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
+  });
 }
 
 /// The determinism log (rand.rs:64-89) as the replay kernel produces it, from the host build of the same engine.
@@ -199,19 +179,8 @@ extern "C" int enginecheck_determinism_log(const msim_config* cfg, const msim_wo
   std::memcpy(buf.data(), hdr, 8);
   P.dlog = buf.data();
   size_t ntr = 0;
-  switch (wl->workload) {
-    case MSIM_WL_SLEEP: rc = run_wl<WL_Sleep>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
-    case MSIM_WL_PINGPONG: rc = run_wl<WL_PingPong>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
-    case MSIM_WL_RAFT: rc = run_wl<WL_Raft>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
-    case MSIM_WL_CHAOS: rc = run_wl<WL_Chaos>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
-    case MSIM_WL_STREAM: rc = run_wl<WL_Stream>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
-    case MSIM_WL_ETCD: rc = run_wl<WL_Etcd>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
-    case MSIM_WL_TONIC:
-      rc = tonic_variant(P.p[2], [&](auto wl) { return run_wl<decltype(wl)>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); });
-      break;
-    case MSIM_WL_SIGNAL: rc = run_wl<WL_Signal>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); break;
-    default: return MSIM_EINVAL;
-  }
+  rc = with_workload(wl->workload, P.p[2], (int)MSIM_EINVAL,
+                     [&](auto w) { return run_wl<decltype(w)>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); });
   std::memcpy(hdr, buf.data(), 8);
   if (n) *n = hdr[0];
   if (out) std::memcpy(out, buf.data() + 8, hdr[0] < cap ? hdr[0] : cap);
@@ -219,15 +188,5 @@ extern "C" int enginecheck_determinism_log(const msim_config* cfg, const msim_wo
 }
 
 extern "C" int enginecheck_state_bytes(uint32_t workload) {
-  switch (workload) {
-    case MSIM_WL_SLEEP: return Layout<WL_Sleep::Caps>::BYTES;
-    case MSIM_WL_PINGPONG: return Layout<WL_PingPong::Caps>::BYTES;
-    case MSIM_WL_RAFT: return Layout<WL_Raft::Caps>::BYTES;
-    case MSIM_WL_CHAOS: return Layout<WL_Chaos::Caps>::BYTES;
-    case MSIM_WL_STREAM: return Layout<WL_Stream::Caps>::BYTES;
-    case MSIM_WL_ETCD: return Layout<WL_Etcd::Caps>::BYTES;
-    case MSIM_WL_TONIC: return Layout<WL_Tonic::Caps>::BYTES;
-    case MSIM_WL_SIGNAL: return Layout<WL_Signal::Caps>::BYTES;
-  }
-  return -1;
+  return with_workload(workload, 2, -1, [](auto w) { return (int)Layout<typename decltype(w)::Caps>::BYTES; });
 }

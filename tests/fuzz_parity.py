@@ -23,7 +23,9 @@ def rand_cfg(rnd):
 
 
 def rand_wl(rnd):
-    k = rnd.choice(["pingpong", "raft", "raft", "chaos", "stream", "etcd", "etcd", "tonic", "tonic", "signal"])
+    k = rnd.choice(["pingpong", "raft", "raft", "chaos", "stream", "etcd", "etcd", "tonic", "tonic", "signal", "election"])
+    if k == "election":
+        return Workload.election(hold_s=rnd.randint(20, 50), timeout_rate=rnd.choice([0, 0, 0.05, 0.3, 1.0]))
     if k == "pingpong":
         return Workload.pingpong(rounds=rnd.randint(0, 60), think_ns=rnd.choice([0, MS, 10 * MS]))
     if k == "raft":

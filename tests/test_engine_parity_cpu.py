@@ -57,6 +57,12 @@ CASES = [
     ("etcd-lease-admin-timeouts", m.Config(packet_loss_rate=0.1), m.Workload.etcd(lease_admin=True, timeout_rate=0.1), 0, 96),
     ("etcd-lease-admin-3clients-bugs", m.Config(), m.Workload.etcd(lease_admin=True, clients=3, ops=30, bug=3, lease_ttl_s=2), 0, 64),
     ("etcd-always-timeout", m.Config(), m.Workload.etcd(ops=3, timeout_rate=1.0), 0, 16),
+    # madsim-etcd-client election API over the watcher: the reference's election() test (tests/test.rs:129-232), SURVEY §8(f) row 3
+    ("election", m.Config(), m.Workload.election(), 0, 64),
+    ("election-hold20-slow-links", m.Config(send_latency_ns=(1 * m.MS, 300 * m.MS)), m.Workload.election(hold_s=20), 10, 64),
+    ("election-server-timeouts", m.Config(), m.Workload.election(timeout_rate=0.1), 0, 96),
+    ("election-timeouts-loss-buggify", m.Config(packet_loss_rate=0.05, buggify=True), m.Workload.election(timeout_rate=0.3, hold_s=40), 0, 96),
+    ("election-always-timeout", m.Config(), m.Workload.election(timeout_rate=1.0), 0, 16),
     # tonic-example Greeter under madsim-tonic + kill/restart chaos (BASELINE config 5)
     ("tonic", m.Config(), m.Workload.tonic(), 0, 32),
     ("tonic-restart-only-1client", m.Config(), m.Workload.tonic(clients=1, restart_only=True), 0, 32),
@@ -98,7 +104,8 @@ def test_multilane_phase_loop_matches_oracle(oracle, name, cfg, wl, base, n):
 
 DLOG_CASES = [c for c in CASES if c[0] in ("sleep", "pingpong-buggify-medium", "pingpong-loss", "raft-faults", "raft-faults-bug-loss",
                                             "stream-partitions-loss20", "etcd-timeouts-3clients", "etcd-lease-admin-timeouts",
-                                            "tonic-request-timeouts-everything", "signal-skip-ctrlc-kills", "chaos-long-panics")]
+                                            "tonic-request-timeouts-everything", "signal-skip-ctrlc-kills", "chaos-long-panics",
+                                            "election-server-timeouts")]
 
 
 @pytest.mark.parametrize("name,cfg,wl,base,n", DLOG_CASES, ids=[c[0] for c in DLOG_CASES])
@@ -128,7 +135,8 @@ def test_burst_checkpoint_equals_run_to_completion(oracle):
 
 
 @pytest.mark.parametrize("wl", [m.Workload.etcd(timeout_rate=0.1), m.Workload.tonic(rounds=4), m.Workload.signal(behavior=2),
-                                m.Workload.stream(messages=60)], ids=["etcd", "tonic", "signal", "stream"])
+                                m.Workload.stream(messages=60), m.Workload.election(timeout_rate=0.05)],
+                         ids=["etcd", "tonic", "signal", "stream", "election"])
 def test_burst_checkpoint_covers_channel_and_signal_state(oracle, wl):
     # connections, accept queues, leases, ctrl-c waiters all live in the state block: k-event bursts == one run
     cfg = m.Config(packet_loss_rate=0.05) if wl.workload != m.WL_TONIC else m.Config()

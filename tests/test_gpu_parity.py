@@ -105,6 +105,11 @@ CASES = [
     ("etcd-lease-admin-timeouts", m.Config(packet_loss_rate=0.1), m.Workload.etcd(lease_admin=True, timeout_rate=0.1), 0, 400),
     ("etcd-lease-admin-3clients-bugs", m.Config(), m.Workload.etcd(lease_admin=True, clients=3, ops=30, bug=3, lease_ttl_s=2), 0, 300),
     ("etcd-always-timeout-buggify", m.Config(buggify=True), m.Workload.etcd(ops=3, timeout_rate=1.0), 0, 64),
+    ("election-reference-test", m.Config(), m.Workload.election(), 0, 500),
+    ("election-hold20-slow-links", m.Config(send_latency_ns=(1 * m.MS, 300 * m.MS)), m.Workload.election(hold_s=20), 10, 300),
+    ("election-server-timeouts", m.Config(), m.Workload.election(timeout_rate=0.1), 0, 500),
+    ("election-timeouts-loss-buggify", m.Config(packet_loss_rate=0.05, buggify=True), m.Workload.election(timeout_rate=0.3, hold_s=40), 0, 300),
+    ("election-always-timeout", m.Config(), m.Workload.election(timeout_rate=1.0), 0, 40),
     ("tonic-kill-restart-chaos", m.Config(), m.Workload.tonic(), 0, 300),
     ("tonic-restart-only-1client", m.Config(), m.Workload.tonic(clients=1, restart_only=True), 0, 200),
     ("tonic-loss1-client-panics", m.Config(packet_loss_rate=0.01), m.Workload.tonic(), 0, 200),
@@ -223,7 +228,8 @@ def test_config5_tonic_32768_seeds_kill_restart_chaos(oracle):
 
 
 @pytest.mark.parametrize("wl", [m.Workload.etcd(timeout_rate=0.1), m.Workload.tonic(rounds=4), m.Workload.signal(behavior=2),
-                                m.Workload.stream(messages=60)], ids=["etcd", "tonic", "signal", "stream"])
+                                m.Workload.stream(messages=60), m.Workload.election(timeout_rate=0.05)],
+                         ids=["etcd", "tonic", "signal", "stream", "election"])
 def test_burst_checkpoint_covers_channel_and_signal_state(wl):
     # static (burst) launches through the HBM checkpoint == the dynamic run-to-completion launch
     cfg = m.Config(packet_loss_rate=0.05) if wl.workload != m.WL_TONIC else m.Config()
@@ -309,7 +315,7 @@ def test_builder_check_determinism_and_pass(oracle):
 DLOG_CASES = [c for c in CASES if c[0] in ("sleep", "pingpong-buggify-medium-latency", "pingpong-loss-deadlocks", "raft-faults",
                                             "stream-partitions-loss20", "etcd-timeouts-3clients", "etcd-lease-admin-timeouts",
                                             "tonic-request-timeouts-everything", "signal-interval-skip-ctrlc-kills",
-                                            "chaos-restart-on-panic")]
+                                            "chaos-restart-on-panic", "election-server-timeouts")]
 
 
 @pytest.mark.parametrize("name,cfg,wl,base,n", DLOG_CASES, ids=[c[0] for c in DLOG_CASES])
@@ -386,8 +392,9 @@ def test_builder_jobs_shards_over_the_visible_gpus(oracle):
 
 @pytest.mark.parametrize("wl,S,L", [(m.Workload.stream(), 112, 4), (m.Workload.chaos(rounds=12, panics=2), 140, 5),
                                     (m.Workload.raft(duration_ms=2500, faults=7), 28, 7), (m.Workload.etcd(timeout_rate=0.1), 50, 2),
-                                    (m.Workload.tonic(rounds=4), 18, 3), (m.Workload.signal(behavior=1), 100, 32)],
-                         ids=["stream", "chaos", "raft", "etcd", "tonic", "signal"])
+                                    (m.Workload.tonic(rounds=4), 18, 3), (m.Workload.signal(behavior=1), 100, 32),
+                                    (m.Workload.election(timeout_rate=0.05), 60, 4)],
+                         ids=["stream", "chaos", "raft", "etcd", "tonic", "signal", "election"])
 def test_lockstep_multilane_kernel_matches_oracle(oracle, wl, S, L):
     # msim_step_kernel_ml: a warp's lanes walk the phases of the event step together (votes between the phases);
     # per seed the result must not depend on how lanes are grouped

@@ -130,13 +130,17 @@ typedef struct msim_config {
  *           4 = halfway through the supervisor kills the SERVER: calls in flight break, later ones are refused,
  *           the clients count failures (user[3]) instead of panicking;
  *           8 = unary calls run inside time::timeout (channel timeout 1 s) and some call `delay`, which must end in
- *           DeadlineExceeded after 1 s / 5 s)
+ *           DeadlineExceeded after 1 s / 5 s;
+ *           16 = GreeterServer::with_interceptor and every GreeterClient::with_interceptor turn every second request down
+ *           (Status::unavailable; the client's before anything reaches the network) and some calls name a service the
+ *           server does not have (Unimplemented) — tests/test.rs:280-363; not together with 2 or 8)
  *  SIGNAL   p0 = supervisor rounds (default 8), p1 = interval period ms (default 100),
  *           p2 = MissedTickBehavior (0 Burst, 1 Delay, 2 Skip), p3 = flags (1 = the worker installs a ctrl-c handler; default 1)
  *  ELECTION n_nodes = 4 (server, two candidates, an observer); p0 = seconds the first leader holds before it revokes its
  *           lease (default 30), p1 = SimServer::timeout_rate as IEEE f32 bits (default 0: any timed-out call fails the
  *           test, as its unwrap() does in the reference); user[] = {leader changes observed, final revision, checksum, requests}
- *  CHAOS    p0 = rounds, p1 = period ms, p2 = worker panics on its first p2 starts (restart_on_panic)
+ *  CHAOS    p0 = rounds, p1 = period ms, p2 = worker panics on its first p2 starts (restart_on_panic),
+ *           p3 = k > 0: restart_on_panic_matching("0") .. ("k-1") instead; the worker panics with its start count as message
  *                                                         */
 #define MSIM_RAFT_FAULT_CLOG_NODE 1u
 #define MSIM_RAFT_FAULT_CLOG_LINK 2u

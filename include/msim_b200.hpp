@@ -143,10 +143,10 @@ struct Workload {
   }
   /// tonic-example Greeter under madsim-tonic + kill/restart chaos of the client nodes
   static Workload tonic(uint32_t clients = 6, uint64_t rounds = 10, uint64_t think_ns = 100000000, bool restart_only = false,
-                        bool streaming = false, bool server_crash = false, bool timeouts = false) {
+                        bool streaming = false, bool server_crash = false, bool timeouts = false, bool interceptors = false) {
     Workload w;
     check(msim_workload_default(MSIM_WL_TONIC, &w.desc));
-    w.desc.n_nodes = clients + 1, w.desc.p[0] = rounds, w.desc.p[1] = think_ns, w.desc.p[2] = (restart_only ? 1 : 0) | (streaming ? 2 : 0) | (server_crash ? 4 : 0) | (timeouts ? 8 : 0);
+    w.desc.n_nodes = clients + 1, w.desc.p[0] = rounds, w.desc.p[1] = think_ns, w.desc.p[2] = (restart_only ? 1 : 0) | (streaming ? 2 : 0) | (server_crash ? 4 : 0) | (timeouts ? 8 : 0) | (interceptors ? 16 : 0);
     return w;
   }
 };

@@ -101,10 +101,12 @@ class Workload:
         )
 
     @staticmethod
-    def chaos(rounds: int = 8, period_ms: int = 2000, panics: int = 0) -> "Workload":
+    def chaos(rounds: int = 8, period_ms: int = 2000, panics: int = 0, matching: int = 0) -> "Workload":
         """kill / restart / pause / resume supervisor schedule (task/mod.rs:858-1016); with
-        `panics` > 0 the worker panics on its first starts under restart_on_panic (:939-963)."""
-        return Workload(N.WL_CHAOS, 1, [rounds, period_ms, panics, 0, 0, 0, 0, 0])
+        `panics` > 0 the worker panics on its first starts under restart_on_panic (:939-963); with `matching` = k the node
+        is built with restart_on_panic_matching("0") .. ("k-1") instead and the worker panics with its start count as
+        the message (:965-983): the panic number k (if there is one) is not matched and fails the seed."""
+        return Workload(N.WL_CHAOS, 1, [rounds, period_ms, panics, matching, 0, 0, 0, 0])
 
     @staticmethod
     def stream(messages: int = 200, think_ns: int = 5 * MS, faults: int = 1) -> "Workload":
@@ -124,12 +126,14 @@ class Workload:
 
     @staticmethod
     def tonic(clients: int = 6, rounds: int = 10, think_ns: int = 100 * MS, restart_only: bool = False,
-              streaming: bool = False, server_crash: bool = False, timeouts: bool = False) -> "Workload":
+              streaming: bool = False, server_crash: bool = False, timeouts: bool = False, interceptors: bool = False) -> "Workload":
         """tonic-example Greeter service under madsim-tonic (a fresh endpoint + handshake + connection per
         unary call) while a supervisor kills / restarts the client nodes (BASELINE config 5); with `streaming`
         the clients also make server-streaming (lots_of_replies, sometimes dropping the response stream) and
-        client-streaming (lots_of_greetings) and bidi (bidi_hello, sometimes dropped after one reply) calls."""
-        return Workload(N.WL_TONIC, clients + 1, [rounds, think_ns, int(restart_only) | 2 * int(streaming) | 4 * int(server_crash) | 8 * int(timeouts), 0, 0, 0, 0, 0])
+        client-streaming (lots_of_greetings) and bidi (bidi_hello, sometimes dropped after one reply) calls; with
+        `interceptors` both sides run a with_interceptor closure that turns every second request down and some calls
+        name a service the server does not have (tests/test.rs:280-363)."""
+        return Workload(N.WL_TONIC, clients + 1, [rounds, think_ns, int(restart_only) | 2 * int(streaming) | 4 * int(server_crash) | 8 * int(timeouts) | 16 * int(interceptors), 0, 0, 0, 0, 0])
 
     @staticmethod
     def signal(rounds: int = 8, period_ms: int = 100, behavior: int = 0, catch: bool = True) -> "Workload":

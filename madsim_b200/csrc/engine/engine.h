@@ -68,7 +68,7 @@ enum : int {
   RQ_RECV,          // ep.recv_from_raw(tag xa)                           -> rv0, rv1, rfrom, rw
   RQ_CALL,          // ep.call_timeout(ya = dst, req tag xa, {yb, yc}, timeout xb ns) -> ret, rv0, rv1
   RQ_SPAWN,         // task::spawn: ya = kind | SPAWN_*; yb = node; locals a = yc, b = yd, c = lo32(xa), dl1 = xb -> ret
-  RQ_CREATE_NODE,   // Handle::create_node().ip().init().build(): ya = NODE_* flags     -> ret = node id
+  RQ_CREATE_NODE,   // Handle::create_node().ip().init().build(): ya = NODE_* flags, yb = restart_on_panic_matching mask (NODE_PANIC_MATCHING) -> ret = node id
   RQ_GEN_RANGE,     // thread_rng().gen_range(xa..xb) (u64)                -> ret64
   RQ_JOIN,          // JoinHandle(ya = task slot).await                   -> ret (1 ok / 2 cancelled), rv0 = output
   RQ_ADVANCE,       // time::advance(xa ns)
@@ -86,7 +86,7 @@ enum : int {
   RQ_TIMEOUT_END,
 };
 enum : u32 { SPAWN_EP = 0x100, SPAWN_JOINABLE = 0x200, SPAWN_CONN = 0x400, SPAWN_CONN_TX = 0x800 };  // clone the Endpoint / keep a JoinHandle / move the connection end / move only its Sender
-enum : u32 { NODE_IP = 1, NODE_INIT = 2, NODE_RESTART_ON_PANIC = 4 };
+enum : u32 { NODE_IP = 1, NODE_INIT = 2, NODE_RESTART_ON_PANIC = 4, NODE_PANIC_MATCHING = 8 };
 enum : int { CALL_OK = 1, CALL_TIMEOUT = 2 };
 
 /// Compile-time layout of one seed's state block for capacities `C` (element offsets per section).
@@ -154,7 +154,9 @@ struct Layout {
   static constexpr int NCC = C::USES_CTRLC ? C::NNODE : 0;     // ctrl-c state exists only where it is awaited
   static constexpr int W_N_CTRLC = W_ACC_WAITER + NSA;          // [NCC] NodeInfo::ctrl_c: installed<<31 | watch version
   static constexpr int W_N_CTRLC_WAITER = W_N_CTRLC + NCC;      // [NCC] the receiver parked in changed() (slot<<20|gen) or NONE32
-  static constexpr int NW = W_N_CTRLC_WAITER + NCC;
+  static constexpr int NPM = C::USES_PMATCH ? C::NNODE : 0;      // restart_on_panic_matching exists only where a program sets it
+  static constexpr int W_N_PMATCH = W_N_CTRLC_WAITER + NCC;     // [NPM] bit c set: a panic with code Caps::PMATCH_BASE + c restarts the node
+  static constexpr int NW = W_N_PMATCH + NPM;
   // ---- u8 section ----
   static constexpr int B_RQ = 0;                        // [NT] ready "queue": a Vec popped at a random index
   static constexpr int B_T_KIND = B_RQ + C::NT;
@@ -798,7 +800,7 @@ MSIM_NOUNROLL
   MSIM_HD bool is_exit(int n) const { return n_flags(n) & NF_KILLED; }
   /// Handle::create_node + NodeBuilder::build (runtime/mod.rs:405-418): ids start at 1; the init
   /// closure runs (spawns the init task) at build time
-  MSIM_HD int create_node_inl(u32 flags) {
+  MSIM_HD int create_node_inl(u32 flags, u32 match_mask) {
     u32 n = w(L::W_NEXT_NODE);
     if (n >= (u32)C::NNODE) {
       fail_cap(MSIM_CAP_TASKS);
@@ -808,12 +810,13 @@ MSIM_NOUNROLL
     n_flags(n) = NF_EXISTS | ((flags & NODE_IP) ? NF_HAS_IP : 0) | ((flags & NODE_RESTART_ON_PANIC) ? NF_RESTART_ON_PANIC : 0);
     n_epoch(n) = 0;
     if (C::USES_CTRLC) w(L::W_N_CTRLC, n) = 0, w(L::W_N_CTRLC_WAITER, n) = NONE32;
+    if (C::USES_PMATCH) w(L::W_N_PMATCH, n) = (flags & NODE_PANIC_MATCHING) ? match_mask : 0u;  // NodeBuilder::restart_on_panic_matching
     int kind = (flags & NODE_INIT) ? WL::init_kind((int)n) : -1;
     if (kind >= 0) spawn((u32)kind, n, TF_INIT);
     return (int)n;
   }
-  MSIM_HD int create_node(u32 flags) {
-    return cold([flags](Engine& e_) { return e_.create_node_inl(flags); });
+  MSIM_HD int create_node(u32 flags, u32 match_mask) {
+    return cold([flags, match_mask](Engine& e_) { return e_.create_node_inl(flags, match_mask); });
   }
 
   // ---------------- network (net/network.rs, net/mod.rs, net/endpoint.rs) ----------------
@@ -1604,7 +1607,7 @@ MSIM_NOUNROLL
           t_wait(t) = W_RECV_RX;
           break;
         case RQ_CREATE_NODE:
-          ret = create_node(ya);
+          ret = create_node(ya, yb);
           if (ret < 0) return POLL_PENDING;
           break;
         case RQ_SPAWN: {
@@ -1735,8 +1738,15 @@ MSIM_NOUNROLL
   }
   /// run_all_ready's panic policy (task/mod.rs:289-317): restart_on_panic nodes are killed and
   /// restarted after gen_range(1s..10s); anything else fails the test
+  /// `restart_on_panic_matching.iter().any(|s| error_msg.contains(s))` (task/mod.rs:298-303): device panics carry a code,
+  /// not a message, so a pattern is the code of the panic it matches (bit c of the node's mask = Caps::PMATCH_BASE + c)
+  MSIM_HD bool panic_matches(int n) const {
+    if (!C::USES_PMATCH) return false;
+    u32 c = w(L::W_PANIC_CODE) - (u32)C::PMATCH_BASE;
+    return c < 32 && ((w(L::W_N_PMATCH, n) >> c) & 1);
+  }
   MSIM_HD void panicked_inl(int n) {
-    if (n_flags(n) & NF_RESTART_ON_PANIC) {
+    if ((n_flags(n) & NF_RESTART_ON_PANIC) || panic_matches(n)) {
       u64 delay = sample_inclusive_u64(NS_PER_SEC, 10 * NS_PER_SEC - 1);  // UniformDuration Medium
       kill(n);
       timer_push(now + delay, timer_payload(TK_RESTART, n, 0));

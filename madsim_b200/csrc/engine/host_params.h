@@ -330,8 +330,8 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
     }
     case MSIM_WL_TONIC:
       if (P.n_nodes == 0) P.n_nodes = 7;
-      if (P.n_nodes < 2 || P.n_nodes > 7 || wl.p[2] > 15) {
-        if (err) *err = "tonic: need 1..6 client nodes, flags <= 15";
+      if (P.n_nodes < 2 || P.n_nodes > 7 || wl.p[2] > 31 || ((wl.p[2] & 16) && (wl.p[2] & 10))) {
+        if (err) *err = "tonic: need 1..6 client nodes, flags <= 31, flag 16 (interceptors) without 2 and 8";
         return MSIM_EINVAL;
       }
       break;
@@ -342,8 +342,8 @@ inline int make_params(const msim_config& c, const msim_workload_desc& wl, Param
       }
       break;
     case MSIM_WL_CHAOS:
-      if (wl.p[1] == 0) {
-        if (err) *err = "chaos: period must be > 0";
+      if (wl.p[1] == 0 || wl.p[3] > 10 || (wl.p[3] && wl.p[2] > 10)) {
+        if (err) *err = "chaos: period must be > 0; matching mode (p3) takes at most 10 patterns and 10 panics";
         return MSIM_EINVAL;
       }
       break;

@@ -21,10 +21,13 @@ struct WL_Chaos {
     static constexpr bool USES_SPLIT = false;   // does any task give the Sender half of its connection to another task?
     static constexpr bool USES_TIMEOUT = false;  // does any task wrap awaits in time::timeout (beyond call_timeout)?
     static constexpr bool USES_CONN2 = false;    // does any task hold two connection ends at once?
+    static constexpr bool USES_PMATCH = true;    // p3: restart_on_panic_matching("0") .. ("p3 - 1") instead of restart_on_panic
+    static constexpr unsigned PMATCH_BASE = 100;  // the panic code bit 0 of a restart_on_panic_matching mask stands for
     static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 { K_MAIN = 0, K_WORKER = 1 };
   static constexpr u32 MAIN_KIND = K_MAIN;
+  static constexpr u32 PANIC_MATCH_BASE = Caps::PMATCH_BASE;  // panic!("{}", starts - 1) (task/mod.rs:965-983) carries code 100 + starts - 1
   static MSIM_HD int init_kind(int) { return K_WORKER; }
 
   template <class E>
@@ -36,7 +39,7 @@ struct WL_Chaos {
         case K_WORKER * 16 + 0:
           e.wl_s(1)++;  // starts
           if ((u64)e.wl_s(1) <= e.P->p[2]) {  // restart_on_panic (task/mod.rs:939-963)
-            e.ya = 23;
+            e.ya = e.P->p[3] ? PANIC_MATCH_BASE + e.wl_s(1) - 1 : 23u;  // matching mode: panic!("{}", starts - 1)
             return RQ_PANIC;
           }
           // fallthrough
@@ -52,7 +55,13 @@ struct WL_Chaos {
         // ---- wl_chaos_main ----
         case K_MAIN * 16 + 0:  // node = create_node().init(chaos_worker).build()
           e.t_pc(t) = 1;
-          e.ya = NODE_INIT | (e.P->p[2] ? NODE_RESTART_ON_PANIC : 0);
+          if (e.P->p[3]) {  // .restart_on_panic_matching("0") .. ("p3 - 1") (task/mod.rs:965-983)
+            e.ya = NODE_INIT | NODE_PANIC_MATCHING;
+            e.yb = (1u << e.P->p[3]) - 1;
+          } else {
+            e.ya = NODE_INIT | (e.P->p[2] ? NODE_RESTART_ON_PANIC : 0);
+            e.yb = 0;
+          }
           return RQ_CREATE_NODE;
         case K_MAIN * 16 + 1:
           e.t_c(t) = (u32)e.ret;  // node id

@@ -25,6 +25,8 @@ struct WL_Signal {
     static constexpr bool USES_SPLIT = false;   // does any task give the Sender half of its connection to another task?
     static constexpr bool USES_TIMEOUT = false;  // does any task wrap awaits in time::timeout (beyond call_timeout)?
     static constexpr bool USES_CONN2 = false;    // does any task hold two connection ends at once?
+    static constexpr bool USES_PMATCH = false;   // does any node use restart_on_panic_matching?
+    static constexpr unsigned PMATCH_BASE = 0;  // the panic code bit 0 of a restart_on_panic_matching mask stands for
     static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 { K_MAIN = 0, K_WORKER, K_CATCH };

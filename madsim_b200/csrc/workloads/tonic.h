@@ -23,13 +23,16 @@ namespace msim {
 /// (BASELINE config 5) is its own instantiation: none of the streaming state machines, no Sender::closed() waits,
 /// no split connection ends, two queued payloads per direction instead of four — 25 seeds per CTA instead of 20
 /// and a hot loop a third smaller (the kernels are instruction-fetch bound).
-template <bool BIG, bool STREAMING = true>
+/// INTERCEPT: the interceptor / unknown-service schedule (flag 16; tests/test.rs:280-363): GreeterServer::with_interceptor
+/// and every GreeterClient::with_interceptor turn every second request down with Status::unavailable — the client's
+/// before anything reaches the network —, and pick 9 calls a service the server does not have (Unimplemented).
+template <bool BIG, bool STREAMING = true, bool INTERCEPT = false>
 struct WL_TonicT {
-  enum : int { S_HANDLED = 0, S_CNT, S_ROUND, S_C, S_FAILURES, S_END };  // wl_s scalars
-  enum : int { F_REPLIES = 0, F_STARTS, F_NFIELD };           // wl_w per client node
+  enum : int { S_HANDLED = 0, S_CNT, S_ROUND, S_C, S_FAILURES, S_SERVER_CALLS, S_END };  // wl_s scalars
+  enum : int { F_REPLIES = 0, F_STARTS, F_ICOUNT, F_NFIELD };           // wl_w per client node
   struct Caps {
     static constexpr int NT = BIG ? 80 : 32, TQ = BIG ? 768 : 64, NMSG = 2, NSOCK = 24, NREG = 1, NMBOX = 1, NNODE = 8, NPARK = 1;
-    static constexpr int WQ = 0, WW = F_NFIELD, WS = S_END;
+    static constexpr int WQ = 0, WW = INTERCEPT ? F_NFIELD : F_ICOUNT, WS = INTERCEPT ? S_END : S_SERVER_CALLS;  // the interceptor counters exist only in that variant
     static constexpr bool USES_JOIN = false;
     static constexpr bool USES_KILL = true;
     static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?
@@ -37,12 +40,15 @@ struct WL_TonicT {
     static constexpr bool USES_SPLIT = STREAMING;   // does any task give the Sender half of its connection to another task? (bidi)
     static constexpr bool USES_TIMEOUT = BIG;    // time::timeout around the unary calls: only the request-timeout schedule (flag 8 = the BIG variant)
     static constexpr bool USES_CONN2 = false;    // does any task hold two connection ends at once?
+    static constexpr bool USES_PMATCH = false;   // does any node use restart_on_panic_matching?
+    static constexpr unsigned PMATCH_BASE = 0;  // the panic code bit 0 of a restart_on_panic_matching mask stands for
     static constexpr int NCONN = BIG ? 64 : 32, NCQ = STREAMING ? 4 : 2, NACC = 32;  // a client-streaming call queues header + 3 items at a slow server
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_RSP_BIDI, K_SENDER };
-  enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u, DELAY_NAME = 0x616c6564u };
-  enum : u32 { ST_OK = 0, ST_INVALID_ARGUMENT = 1, ST_EOF = 2, ST_TRAILER = 3 };
-  enum : u32 { SERVER_STREAMING = 1u << 31, CLIENT_STREAMING = 1u << 30, FLAG_RESTART_ONLY = 1, FLAG_STREAMING_MIX = 2, FLAG_SERVER_CRASH = 4, FLAG_TIMEOUTS = 8 };
+  enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u, DELAY_NAME = 0x616c6564u, UNKNOWN_SERVICE = 0x6e6b6e75u };
+  enum : u32 { ST_OK = 0, ST_INVALID_ARGUMENT = 1, ST_EOF = 2, ST_TRAILER = 3, ST_UNAVAILABLE = 4, ST_UNIMPLEMENTED = 5 };
+  static constexpr u32 STATUS_ONLY = 1u << 29;  // the spawned task only sends the status in its first local (server.rs:259-272)
+  enum : u32 { SERVER_STREAMING = 1u << 31, CLIENT_STREAMING = 1u << 30, FLAG_RESTART_ONLY = 1, FLAG_STREAMING_MIX = 2, FLAG_SERVER_CRASH = 4, FLAG_TIMEOUTS = 8, FLAG_INTERCEPT = 16 };
   static constexpr u32 MAIN_KIND = K_MAIN;
   static constexpr u32 SERVER_ADDR = (IPK_NODE << 24) | (1u << 16) | 50051u;  // 10.0.0.1:50051
   /// NodeBuilder::init(|| tonic_client(c)) — what Handle::restart re-runs
@@ -145,7 +151,7 @@ struct WL_TonicT {
         case K_MAIN * 32 + 8: {
           u32 replies = 0, starts = 0;
           for (u32 c = 0; c < n_clients; c++) replies += e.wl_w(F_REPLIES, 2 + c), starts += e.wl_w(F_STARTS, 2 + c);
-          if (!(P.p[2] & FLAG_TIMEOUTS) && e.wl_s(S_HANDLED) < replies) return panic(e, 74);
+          if (!(P.p[2] & (FLAG_TIMEOUTS | FLAG_INTERCEPT)) && e.wl_s(S_HANDLED) < replies) return panic(e, 74);
           e.w(L::W_USER0) = replies;
           e.w(L::W_USER1) = starts;
           e.w(L::W_USER2) = e.wl_s(S_HANDLED);
@@ -177,6 +183,17 @@ struct WL_TonicT {
             continue;
           }
           e.t_pc(t) = 2;  // spawn the response task with tx (and the request)
+          if (INTERCEPT && (P.p[2] & FLAG_INTERCEPT)) {
+            u32 status = ST_OK;
+            if (e.rv0 == UNKNOWN_SERVICE)
+              status = ST_UNIMPLEMENTED;  // self.services.get_mut(svc_name) is None
+            else if (++e.wl_s(S_SERVER_CALLS) % 2 == 0)
+              status = ST_UNAVAILABLE;  // InterceptedService::call runs the closure here, in the serve loop
+            if (status != ST_OK) {
+              e.ya = K_RSP | SPAWN_CONN, e.yb = e.t_node(t), e.yc = status, e.yd = e.t_b(t), e.xa = STATUS_ONLY, e.xb = 0;
+              return RQ_SPAWN;
+            }
+          }
           e.ya = (!STREAMING ? (u32)K_RSP
                   : ((e.rv1 & CLIENT_STREAMING) && (e.rv1 & SERVER_STREAMING)) ? (u32)K_RSP_BIDI
                   : (e.rv1 & CLIENT_STREAMING) ? (u32)K_RSP_CSTREAM
@@ -186,6 +203,11 @@ struct WL_TonicT {
 
         // ---- tonic_response_task ----
         case K_RSP * 32 + 0:
+          if (INTERCEPT && (e.t_c(t) & STATUS_ONLY)) {  // no such service / turned down by the interceptor
+            e.t_pc(t) = 1;
+            e.yb = e.t_a(t), e.yc = 0;
+            return RQ_CH_SEND;
+          }
           e.wl_s(S_HANDLED)++;
           if (e.t_a(t) == DELAY_NAME) {  // AnotherGreeter::delay: sleep(10 s) inside rsp_future.await
             e.t_pc(t) = 2;
@@ -333,6 +355,7 @@ struct WL_TonicT {
           if (e.ret < 0) return call_failed(e, t, 70);
           e.conn_drop_end(t);
           e.sock_unref(t);
+          if (INTERCEPT) e.wl_w(F_ICOUNT, e.t_node(t)) = 0;  // a (re)started node builds a new client: its closure starts at 0
           e.t_b(t) = 0;  // seq
           e.t_pc(t) = 3;
           // fallthrough
@@ -343,6 +366,17 @@ struct WL_TonicT {
         case K_CLIENT * 32 + 4:  // Grpc::unary / server_streaming -> connect_ep: Endpoint::connect
           e.t_a(t) = e.ret64 == 0 ? (u32)ERROR_NAME : (u32)NAME;
           e.t_c(t) = (STREAMING && (P.p[2] & FLAG_STREAMING_MIX) && e.ret64 >= 1 && e.ret64 <= 6) ? (u32)e.ret64 : 0u;  // 1..3: lots_of_replies, 4: lots_of_greetings, 5..6: bidi_hello
+          if (INTERCEPT && (P.p[2] & FLAG_INTERCEPT)) {
+            u32 node = e.t_node(t);
+            if (++e.wl_w(F_ICOUNT, node) % 2 == 0) {  // request.intercept(..)? fails before connect1 (client.rs:65)
+              e.wl_w(F_REPLIES, node)++;
+              e.t_b(t)++;
+              e.t_pc(t) = 3;
+              e.xa = P.p[1];
+              return RQ_SLEEP_FOR;
+            }
+            if (e.ret64 == 9) e.t_a(t) = UNKNOWN_SERVICE;
+          }
           if (Caps::USES_TIMEOUT && (P.p[2] & FLAG_TIMEOUTS) && e.t_c(t) == 0) {  // with_timeout (client.rs:246-258): unary calls only
             u64 tmo = NS_PER_SEC;  // Endpoint::timeout(1 s)
             if (e.ret64 == 7 || e.ret64 == 8) e.t_a(t) = DELAY_NAME;
@@ -407,6 +441,11 @@ struct WL_TonicT {
           e.sock_unref(t);
           if (Caps::USES_TIMEOUT) e.t_dl2(t) = E::NONE64;  // the call completed inside its timeout
           if (e.t_a(t) == DELAY_NAME) return panic(e, 80);  // delay must end in DeadlineExceeded
+          if (INTERCEPT && e.t_a(t) == UNKNOWN_SERVICE) {
+            if (st != ST_UNIMPLEMENTED) return panic(e, 93);
+          } else if (INTERCEPT && (P.p[2] & FLAG_INTERCEPT) && st == ST_UNAVAILABLE) {
+            // the server's interceptor turned this one down
+          } else
           if (e.t_a(t) == ERROR_NAME) {
             if (st != ST_INVALID_ARGUMENT) return panic(e, 72);
           } else if (st != ST_OK || reply != NAME * 31u + node) {
@@ -520,7 +559,8 @@ struct WL_TonicT {
       }
   }
 };
-using WL_TonicUnary = WL_TonicT<false, false>;  // flags without 2 and 8: BASELINE config 5
+using WL_TonicUnary = WL_TonicT<false, false>;  // flags without 2, 8, 16: BASELINE config 5
+using WL_TonicIntercept = WL_TonicT<false, false, true>;  // + interceptors and an unknown service (flag 16; excludes 2 and 8)
 using WL_Tonic = WL_TonicT<false, true>;        // + streaming calls (flag 2)
 using WL_TonicBig = WL_TonicT<true, true>;      // + request timeouts (flag 8)
 /// the instantiation that runs a given flags word (p[2]): f(WL{}) with the chosen program type
@@ -528,6 +568,7 @@ template <class F>
 inline auto tonic_variant(u64 flags, F&& f) {
   if (flags & 8) return f(WL_TonicBig{});
   if (flags & 2) return f(WL_Tonic{});
+  if (flags & 16) return f(WL_TonicIntercept{});
   return f(WL_TonicUnary{});
 }
 

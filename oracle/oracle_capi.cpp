@@ -105,7 +105,7 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
         tp.rounds = wl->p[0];
         tp.think_ns = wl->p[1];
         tp.flags = u32(wl->p[2]);
-        if (tp.n_clients < 1 || tp.n_clients > 6 || tp.flags > 15) return MSIM_EINVAL;
+        if (tp.n_clients < 1 || tp.n_clients > 6 || tp.flags > 31 || ((tp.flags & 16) && (tp.flags & 10))) return MSIM_EINVAL;
         rt.block_on(wl_tonic_main(tp, &user));
         rt.teardown();
         break;
@@ -122,7 +122,8 @@ int run_one(const msim_config* c, const msim_workload_desc* wl, u64 seed, msim_s
         break;
       }
       case MSIM_WL_CHAOS:
-        rt.block_on(wl_chaos_main(wl->p[0], wl->p[1], u32(wl->p[2]), &user));
+        if (wl->p[3] > 10 || (wl->p[3] && wl->p[2] > 10)) return MSIM_EINVAL;  // matching mode: single-digit panic messages
+        rt.block_on(wl_chaos_main(wl->p[0], wl->p[1], u32(wl->p[2]), &user, u32(wl->p[3])));
         break;
       case MSIM_WL_ELECTION: {
         ElectionParams ep;

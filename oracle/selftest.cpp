@@ -407,6 +407,38 @@ static void etcd_case(F client) {
   rt.teardown();
 }
 
+// ---- tonic-example/tests/test.rs:280-315 unimplemented_service(), :317-363 interceptor() ----
+static Async<Unit> tonic_unimplemented_client(SocketAddr server) {
+  co_await sleep(1 * SEC);
+  (co_await tonic_connect_ep(server)).unwrap();  // GreeterClient::connect
+  Payload q;
+  q.v[0] = TONIC_UNKNOWN_SERVICE;  // the server only has AnotherGreeter: "/helloworld.Greeter/SayHello" is nobody's
+  auto r = co_await tonic_unary(server, q);
+  CHECK(r.is_ok() && r.ok->v[0] == TONIC_UNIMPLEMENTED);  // error.code() == Code::Unimplemented
+  r = co_await tonic_unary(server, q);
+  CHECK(r.is_ok() && r.ok->v[0] == TONIC_UNIMPLEMENTED);
+  co_return {};
+}
+static Async<Unit> tonic_interceptor_client(SocketAddr server) {
+  co_await sleep(1 * SEC);
+  (co_await tonic_connect_ep(server)).unwrap();
+  u32 i = 0;  // GreeterClient::with_interceptor(channel, move |req| { i += 1; if i % 2 == 0 { Err(unavailable) } else { Ok(req) } })
+  auto say_hello = [&]() -> Async<u32> {
+    if (++i % 2 == 0) co_return u32(TONIC_UNAVAILABLE);
+    Payload q;
+    q.v[0] = TONIC_NAME;
+    auto r = co_await tonic_unary(server, q);
+    CHECK(r.is_ok());
+    co_return r.ok->v[0];
+  };
+  CHECK(co_await say_hello() == TONIC_OK);           // (1, 1)
+  CHECK(co_await say_hello() == TONIC_UNAVAILABLE);  // (2, 1)
+  CHECK(co_await say_hello() == TONIC_UNAVAILABLE);  // (3, 2)
+  CHECK(co_await say_hello() == TONIC_UNAVAILABLE);  // (4, 2)
+  CHECK(co_await say_hello() == TONIC_OK);           // (5, 3)
+  co_return {};
+}
+
 // ---- tonic-example/tests/test.rs:22-70 basic() (unary part), :139-151 invalid_address() ----
 static Async<Unit> tonic_basic_client(SocketAddr server) {
   co_await sleep(1 * SEC);
@@ -819,6 +851,30 @@ int main() {
     server.spawn(tonic_serve(a, st));
     auto h = cl.spawn(tonic_timeout_client(a));
     rt.block_on(join_unwrap(std::move(h)));
+    rt.teardown();
+  });
+  run_case("tonic::unimplemented_service (tests/test.rs:280-315)", [] {
+    Runtime rt;
+    SocketAddr a{ip4(10, 0, 0, 1), 50051};
+    auto server = rt.create_node().ip(a.ip).build();
+    auto cl = rt.create_node().ip(ip4(10, 0, 0, 2)).build();
+    auto st = std::make_shared<TonicStats>();
+    server.spawn(tonic_serve(a, st, true));
+    auto h = cl.spawn(tonic_unimplemented_client(a));
+    rt.block_on(join_unwrap(std::move(h)));
+    CHECK(st->handled == 0 && st->server_calls == 0);  // no service was called, no interceptor ran
+    rt.teardown();
+  });
+  run_case("tonic::interceptor on both sides (tests/test.rs:317-363)", [] {
+    Runtime rt;
+    SocketAddr a{ip4(10, 0, 0, 1), 50051};
+    auto server = rt.create_node().ip(a.ip).build();
+    auto cl = rt.create_node().ip(ip4(10, 0, 0, 2)).build();
+    auto st = std::make_shared<TonicStats>();
+    server.spawn(tonic_serve(a, st, true));
+    auto h = cl.spawn(tonic_interceptor_client(a));
+    rt.block_on(join_unwrap(std::move(h)));
+    CHECK(st->server_calls == 3 && st->handled == 2);
     rt.teardown();
   });
   run_case("tonic::invalid_address (tests/test.rs:139-151)", [] {

@@ -275,21 +275,28 @@ inline Async<u32> wl_raft_main(std::shared_ptr<RaftCluster> c, RaftOutcome* out)
 struct ChaosState {
   u32 flag = 0, starts = 0;
 };
-inline Async<Unit> chaos_worker(std::shared_ptr<ChaosState> st, u64 period_ns, u32 panics) {
+inline Async<Unit> chaos_worker(std::shared_ptr<ChaosState> st, u64 period_ns, u32 panics, u32 matching) {
   st->starts++;
-  if (st->starts <= panics) panic("chaos worker boom", 23);  // restart_on_panic (task/mod.rs:939-963)
+  if (st->starts <= panics) {  // restart_on_panic (task/mod.rs:939-963) / _matching (:965-983): panic!("{}", starts - 1)
+    if (matching) panic(std::to_string(st->starts - 1), 100 + st->starts - 1);
+    panic("chaos worker boom", 23);
+  }
   for (;;) {
     co_await sleep(period_ns);
     st->flag += 2;
   }
 }
-inline Async<u32> wl_chaos_main(u64 rounds, u64 period_ms, u32 panics, std::array<u32, 4>* user) {
+inline Async<u32> wl_chaos_main(u64 rounds, u64 period_ms, u32 panics, std::array<u32, 4>* user, u32 matching = 0) {
   auto& rt = current_runtime();
   auto st = std::make_shared<ChaosState>();
   u64 period = period_ms * MS;
   auto nb = rt.create_node();
-  nb.init([st, period, panics]() { return chaos_worker(st, period, panics); });
-  if (panics) nb.restart_on_panic();
+  nb.init([st, period, panics, matching]() { return chaos_worker(st, period, panics, matching); });
+  if (matching) {  // .restart_on_panic_matching("0") .. ("matching - 1"): single digits, so `contains` is equality
+    for (u32 i = 0; i < matching; i++) nb.restart_on_panic_matching(std::to_string(i));
+  } else if (panics) {
+    nb.restart_on_panic();
+  }
   auto node = nb.build();
   u64 id = node.id();
   GlobalRng& rng = thread_rng();

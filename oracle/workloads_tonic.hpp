@@ -22,10 +22,11 @@ namespace msim_oracle {
 
 constexpr u32 TONIC_NAME = 0x696e6f54u;   // "Toni"
 constexpr u32 TONIC_ERROR = 0x6f727265u;  // "erro"
-enum : u32 { TONIC_OK = 0, TONIC_INVALID_ARGUMENT = 1, TONIC_EOF = 2, TONIC_TRAILER = 3 };
+enum : u32 { TONIC_OK = 0, TONIC_INVALID_ARGUMENT = 1, TONIC_EOF = 2, TONIC_TRAILER = 3, TONIC_UNAVAILABLE = 4, TONIC_UNIMPLEMENTED = 5 };
 constexpr u32 TONIC_SERVER_STREAMING = 1u << 31;  // the `server_streaming: bool` of the first message (client.rs:128)
 constexpr u32 TONIC_CLIENT_STREAMING = 1u << 30;  // the first message is the stream-start header Box<()> (client.rs:170-176)
-enum : u32 { TONIC_RESTART_ONLY = 1, TONIC_STREAMING_MIX = 2, TONIC_SERVER_CRASH = 4, TONIC_TIMEOUTS = 8 };
+enum : u32 { TONIC_RESTART_ONLY = 1, TONIC_STREAMING_MIX = 2, TONIC_SERVER_CRASH = 4, TONIC_TIMEOUTS = 8, TONIC_INTERCEPT = 16 };
+constexpr u32 TONIC_UNKNOWN_SERVICE = 0x6e6b6e75u;  // "unkn": a path whose service the server does not have
 constexpr u32 TONIC_DELAY = 0x616c6564u;  // "dela": AnotherGreeter::delay sleeps 10 s before it answers (lib.rs:36-43)
 
 struct TonicParams {
@@ -37,16 +38,28 @@ struct TonicParams {
   // 8: the channel has a 1 s timeout (Endpoint::timeout, tests/test.rs:369-410 request_timeout): unary calls run
   //    inside time::timeout; picks 7 / 8 call `delay` with the channel's 1 s / a 5 s request timeout and must
   //    come back DeadlineExceeded (streaming calls are not wrapped here)
+  // 16: interceptors on both sides and an unknown service (tests/test.rs:280-363 unimplemented_service, interceptor):
+  //    the server's GreeterServer::with_interceptor and every client's GreeterClient::with_interceptor let every
+  //    second request through and answer the others Status::unavailable("intercepted") — the client's before any
+  //    network activity —; pick 9 calls a service the server does not have and must come back Unimplemented
   u32 flags = 0;  // 1: the supervisor never kills, only restarts (client_crash as written); 2: clients also make
                   // server-streaming calls (lots_of_replies), sometimes dropping the response stream at once
 };
 struct TonicStats {
   std::array<u32, 8> replies{}, starts{};
   u32 handled = 0, failures = 0;
+  u32 server_calls = 0;  // the `i` of the server-side interceptor closure (tests/test.rs:324-335)
 };
 inline u32 tonic_reply_for(u32 name, SocketAddr remote) { return name * 31u + (remote.ip & 0xff); }
 
 /// the task server.rs:268 spawns per request
+/// server.rs:259-272 (no such service) and an intercepted call: the spawned task only sends the error status
+inline Async<Unit> tonic_status_task(Connection conn, u32 status) {
+  Payload rsp;
+  rsp.v[0] = status;
+  (void)conn.tx.send(rsp);
+  co_return {};
+}
 inline Async<Unit> tonic_response_task(Connection conn, Payload request, std::shared_ptr<TonicStats> st) {
   st->handled++;
   u32 name = request.v[0];
@@ -152,7 +165,7 @@ inline Async<Unit> tonic_bidi_response_task(Connection conn, std::shared_ptr<Ton
   (void)conn.tx.send(trailer);
   co_return {};
 }
-inline Async<Unit> tonic_serve(SocketAddr addr, std::shared_ptr<TonicStats> st) {
+inline Async<Unit> tonic_serve(SocketAddr addr, std::shared_ptr<TonicStats> st, bool intercept = false) {
   Endpoint ep = std::move((co_await Endpoint::bind(addr)).unwrap());
   for (;;) {
     Connection conn = std::move((co_await ep.accept1()).unwrap());
@@ -164,6 +177,10 @@ inline Async<Unit> tonic_serve(SocketAddr addr, std::shared_ptr<TonicStats> st) 
       spawn(tonic_client_stream_response_task(std::move(conn), st));
     else if (msg.ok->v[1] & TONIC_SERVER_STREAMING)
       spawn(tonic_stream_response_task(std::move(conn), *msg.ok, st));
+    else if (intercept && msg.ok->v[0] == TONIC_UNKNOWN_SERVICE)  // self.services.get_mut(svc_name) is None
+      spawn(tonic_status_task(std::move(conn), TONIC_UNIMPLEMENTED));
+    else if (intercept && ++st->server_calls % 2 == 0)  // InterceptedService::call runs the closure HERE, in the serve loop
+      spawn(tonic_status_task(std::move(conn), TONIC_UNAVAILABLE));
     else
       spawn(tonic_response_task(std::move(conn), *msg.ok, st));
   }
@@ -321,11 +338,20 @@ inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::sh
     co_await sleep(p.think_ns);
   }
   GlobalRng& rng = thread_rng();
+  u32 icount = 0;  // the `i` of this client's interceptor closure: a restarted node builds a new client
   for (u32 seq = 0;; seq++) {
     Payload q;
     u64 pick = rng.gen_range_u64(0, 10);
     q.v[0] = pick == 0 ? TONIC_ERROR : TONIC_NAME;
     q.v[1] = seq;
+    if (p.flags & TONIC_INTERCEPT) {
+      if (++icount % 2 == 0) {  // request.intercept(..)? fails before connect1 (client.rs:65): nothing reaches the network
+        st->replies[c]++;
+        co_await sleep(p.think_ns);
+        continue;
+      }
+      if (pick == 9) q.v[0] = TONIC_UNKNOWN_SERVICE;
+    }
     if ((p.flags & TONIC_STREAMING_MIX) && pick >= 1 && pick <= 3) {  // lots_of_replies; pick 3 drops the stream at once
       auto sr = co_await tonic_server_streaming(server, q, pick == 3, tonic_reply_for(TONIC_NAME, me));
       if (sr.is_err()) {
@@ -390,7 +416,11 @@ inline Async<Unit> tonic_client(u32 c, SocketAddr server, TonicParams p, std::sh
       co_await sleep(p.think_ns);
       continue;
     }
-    if (q.v[0] == TONIC_ERROR) {
+    if (q.v[0] == TONIC_UNKNOWN_SERVICE) {
+      if (r.ok->v[0] != TONIC_UNIMPLEMENTED) panic("expected Unimplemented", 93);
+    } else if ((p.flags & TONIC_INTERCEPT) && r.ok->v[0] == TONIC_UNAVAILABLE) {
+      // the server's interceptor turned this one down
+    } else if (q.v[0] == TONIC_ERROR) {
       if (r.ok->v[0] != TONIC_INVALID_ARGUMENT) panic("expected invalid_argument", 72);
     } else if (r.ok->v[0] != TONIC_OK || r.ok->v[1] != tonic_reply_for(TONIC_NAME, me)) {
       panic("unexpected reply", 73);
@@ -405,7 +435,7 @@ inline Async<u32> wl_tonic_main(TonicParams p, std::array<u32, 4>* user) {
   SocketAddr server{ip4(10, 0, 0, 1), 50051};
   auto st = std::make_shared<TonicStats>();
   auto node0 = rt.create_node().ip(server.ip).build();
-  node0.spawn(tonic_serve(server, st));
+  node0.spawn(tonic_serve(server, st, (p.flags & TONIC_INTERCEPT) != 0));
   co_await sleep(1 * SEC);
   std::vector<u64> ids;
   for (u32 c = 0; c < p.n_clients; c++) {
@@ -429,7 +459,7 @@ inline Async<u32> wl_tonic_main(TonicParams p, std::array<u32, 4>* user) {
   co_await sleep(1 * SEC);
   u32 replies = 0, starts = 0;
   for (u32 c = 0; c < p.n_clients; c++) replies += st->replies[c], starts += st->starts[c];
-  if (!(p.flags & TONIC_TIMEOUTS) && st->handled < replies) panic("more replies than requests handled", 74);
+  if (!(p.flags & (TONIC_TIMEOUTS | TONIC_INTERCEPT)) && st->handled < replies) panic("more replies than requests handled", 74);
   (*user)[0] = replies;
   (*user)[1] = starts;
   (*user)[2] = st->handled;

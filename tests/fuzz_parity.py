@@ -35,13 +35,18 @@ def rand_wl(rnd):
                              rpc_timeout_ms=rnd.choice([20, 40, 80]), heartbeat_ms=rnd.choice([30, 50]),
                              election_ms=rnd.choice([(80, 160), (150, 300)]))
     if k == "chaos":
-        return Workload.chaos(rounds=rnd.randint(1, 12), period_ms=rnd.choice([100, 700, 2000]), panics=rnd.choice([0, 0, 1, 3]))
+        panics = rnd.choice([0, 0, 1, 3])
+        return Workload.chaos(rounds=rnd.randint(1, 12), period_ms=rnd.choice([100, 700, 2000]), panics=panics,
+                              matching=rnd.choice([0, 0, panics, max(panics - 1, 0)]))
     if k == "stream":
         return Workload.stream(messages=rnd.randint(0, 120), think_ns=rnd.choice([0, MS, 5 * MS]), faults=rnd.randint(0, 1))
     if k == "etcd":
         return Workload.etcd(clients=rnd.randint(1, 3), ops=rnd.randint(1, 40), think_ns=rnd.choice([0, 5 * MS, 50 * MS]),
                              timeout_rate=rnd.choice([0, 0, 0.1, 0.5, 1.0]), bug=rnd.randint(0, 3), lease_ttl_s=rnd.randint(0, 3),
                              lease_admin=rnd.random() < 0.5)
+    if k == "tonic" and rnd.random() < 0.25:
+        return Workload.tonic(clients=rnd.randint(1, 6), rounds=rnd.randint(0, 12), think_ns=rnd.choice([0, 10 * MS, 100 * MS]),
+                              restart_only=rnd.random() < 0.3, server_crash=rnd.random() < 0.4, interceptors=True)
     if k == "tonic":
         return Workload.tonic(clients=rnd.randint(1, 6), rounds=rnd.randint(0, 12), think_ns=rnd.choice([0, 10 * MS, 100 * MS]),
                               restart_only=rnd.random() < 0.3, streaming=rnd.random() < 0.5, server_crash=rnd.random() < 0.4, timeouts=rnd.random() < 0.3)

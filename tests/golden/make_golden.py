@@ -40,6 +40,7 @@ CASES = {
     "tonic_server_crash": (dict(), dict(kind="tonic", streaming=True, server_crash=True), list(range(6))),
     "tonic_request_timeouts": (dict(), dict(kind="tonic", streaming=True, timeouts=True), list(range(4))),
     "raft_cfg3_loss5": (dict(packet_loss_rate=0.05), dict(kind="raft", faults=7), list(range(4))),
+    "tonic_interceptors": (dict(), dict(kind="tonic", interceptors=True), list(range(4))),
     "election": (dict(), dict(kind="election"), list(range(6))),
     "election_timeouts": (dict(), dict(kind="election", timeout_rate=0.125, hold_s=25), list(range(8))),
 }

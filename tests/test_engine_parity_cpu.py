@@ -74,6 +74,8 @@ CASES = [
     ("tonic-request-timeouts", m.Config(), m.Workload.tonic(timeouts=True), 0, 64),
     ("tonic-request-timeouts-everything", m.Config(buggify=True), m.Workload.tonic(streaming=True, timeouts=True, server_crash=True, rounds=8), 0, 64),
     ("tonic-buggify-slow-server", m.Config(buggify=True), m.Workload.tonic(clients=3, rounds=5), 0, 160),
+    ("tonic-interceptors-unknown-service", m.Config(), m.Workload.tonic(interceptors=True), 0, 64),
+    ("tonic-interceptors-server-crash-buggify", m.Config(buggify=True), m.Workload.tonic(interceptors=True, server_crash=True, rounds=8, think_ns=0), 0, 64),
     # time::interval + MissedTickBehavior, signal::ctrl_c, Handle::send_ctrl_c
     ("signal-burst-catch", m.Config(), m.Workload.signal(behavior=0, rounds=12), 0, 100),
     ("signal-delay-catch", m.Config(), m.Workload.signal(behavior=1, rounds=12), 0, 100),
@@ -83,6 +85,9 @@ CASES = [
     ("chaos", m.Config(), m.Workload.chaos(), 0, 200),
     ("chaos-long-panics", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 200),
     ("chaos-always-panicking", m.Config(), m.Workload.chaos(rounds=4, period_ms=3000, panics=50), 0, 100),
+    # restart_on_panic_matching (task/mod.rs:298-303,965-983): every panic matched / the third one is not ("should panic with 2")
+    ("chaos-panic-matching-all", m.Config(), m.Workload.chaos(rounds=10, period_ms=700, panics=3, matching=3), 0, 100),
+    ("chaos-panic-matching-third-unmatched", m.Config(), m.Workload.chaos(rounds=10, period_ms=700, panics=3, matching=2), 0, 60),
 ]
 
 

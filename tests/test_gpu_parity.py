@@ -120,6 +120,8 @@ CASES = [
     ("tonic-request-timeouts", m.Config(), m.Workload.tonic(timeouts=True), 0, 200),
     ("tonic-request-timeouts-everything", m.Config(buggify=True), m.Workload.tonic(streaming=True, timeouts=True, server_crash=True, rounds=8), 0, 200),
     ("tonic-buggify-slow-server", m.Config(buggify=True), m.Workload.tonic(clients=3, rounds=5), 0, 200),
+    ("tonic-interceptors-unknown-service", m.Config(), m.Workload.tonic(interceptors=True), 0, 300),
+    ("tonic-interceptors-server-crash-buggify", m.Config(buggify=True), m.Workload.tonic(interceptors=True, server_crash=True, rounds=8, think_ns=0), 0, 200),
     ("tonic-16-rounds-slow-links", m.Config(send_latency_ns=(1 * m.MS, 400 * m.MS)), m.Workload.tonic(rounds=16, think_ns=0), 0, 200),
     ("signal-interval-burst-ctrlc-caught", m.Config(), m.Workload.signal(behavior=0, rounds=12), 0, 500),
     ("signal-interval-delay-ctrlc-caught", m.Config(), m.Workload.signal(behavior=1, rounds=12), 0, 500),
@@ -129,6 +131,8 @@ CASES = [
     ("chaos-kill-restart-pause", m.Config(), m.Workload.chaos(), 0, 500),
     ("chaos-restart-on-panic", m.Config(), m.Workload.chaos(rounds=30, period_ms=700, panics=3), 0, 500),
     ("chaos-always-panicking", m.Config(), m.Workload.chaos(rounds=4, period_ms=3000, panics=50), 0, 200),
+    ("chaos-panic-matching-all", m.Config(), m.Workload.chaos(rounds=10, period_ms=700, panics=3, matching=3), 0, 300),
+    ("chaos-panic-matching-third-unmatched", m.Config(), m.Workload.chaos(rounds=10, period_ms=700, panics=3, matching=2), 0, 200),
 ]
 
 

@@ -40,6 +40,12 @@
 #define MSIM_FN MSIM_HD_NOINLINE
 #endif
 
+// Which once-per-request runtime pieces a program runs out of line (Caps::COLD_*): bit 0 spawn, 1 task end, 2 channel link
+// test + connect1.  Programs set their own value; this is the default (and the knob of the code-size experiments).
+#ifndef MSIM_COLD_DEFAULT
+#define MSIM_COLD_DEFAULT 0
+#endif
+
 namespace msim {
 
 typedef uint8_t u8;

@@ -605,8 +605,14 @@ struct Engine {
   MSIM_HD void drop_runnable(int t) {
     cold([t](Engine& e_) { e_.drop_runnable_inl(t); });
   }
-  /// Spawner::spawn_inner (task/mod.rs:627-654): returns the slot or -1
+  /// Spawner::spawn_inner (task/mod.rs:627-654): returns the slot or -1.  Programs whose hot loop is larger than the
+  /// SM's instruction cache (profiles/r2_etcd, r2_tonic_unary: 63-67 % hit rate) run the once-per-request pieces —
+  /// spawn, the end of a task, the link test of a channel send, connect1 — out of line (Caps::COLD_*).
   MSIM_HD int spawn(u32 kind, u32 node, u8 extra_flags) {
+    if (C::COLD_SPAWN) return cold([kind, node, extra_flags](Engine& e_) { return e_.spawn_inl(kind, node, extra_flags); });
+    return spawn_inl(kind, node, extra_flags);
+  }
+  MSIM_HD int spawn_inl(u32 kind, u32 node, u8 extra_flags) {
     int t = -1;
 MSIM_NOUNROLL
     for (int wd = 0; wd < (C::NT + 63) / 64; wd++) {
@@ -757,7 +763,7 @@ MSIM_NOUNROLL
     n_flags(n) = n_flags(n) & ~(NF_KILLED | NF_PAUSED);
     if (C::USES_CTRLC) w(L::W_N_CTRLC, n) = 0, w(L::W_N_CTRLC_WAITER, n) = NONE32;  // the new NodeInfo has no handler
     int kind = WL::init_kind(n);
-    if (kind >= 0) spawn((u32)kind, n, TF_INIT);
+    if (kind >= 0) spawn_inl((u32)kind, n, TF_INIT);
   }
   MSIM_HD void restart(int n) {
     cold([n](Engine& e_) { e_.restart_inl(n); });
@@ -812,7 +818,7 @@ MSIM_NOUNROLL
     if (C::USES_CTRLC) w(L::W_N_CTRLC, n) = 0, w(L::W_N_CTRLC_WAITER, n) = NONE32;
     if (C::USES_PMATCH) w(L::W_N_PMATCH, n) = (flags & NODE_PANIC_MATCHING) ? match_mask : 0u;  // NodeBuilder::restart_on_panic_matching
     int kind = (flags & NODE_INIT) ? WL::init_kind((int)n) : -1;
-    if (kind >= 0) spawn((u32)kind, n, TF_INIT);
+    if (kind >= 0) spawn_inl((u32)kind, n, TF_INIT);
     return (int)n;
   }
   MSIM_HD int create_node(u32 flags, u32 match_mask) {
@@ -1006,12 +1012,20 @@ MSIM_NOUNROLL
   }
   /// channel()'s test_link closure: try_send(node, dst).map(|lat| now + lat)
   MSIM_HD u64 ch_test_link(int d) {
+    if (C::COLD_CH) return cold([d](Engine& e_) { return e_.ch_test_link_inl(d); });
+    return ch_test_link_inl(d);
+  }
+  MSIM_HD u64 ch_test_link_inl(int d) {
     u64 lat;
     int k = try_send(b(L::B_CH_SRC, d), w(L::W_CH_DST, d), lat);
     return k < 0 ? NONE64 : now + lat;
   }
   /// NetSim::connect1 after rand_delay.  0 ok / -1 ConnectionRefused
   MSIM_HD int connect1(int t, u32 dst) {
+    if (C::COLD_CH) return cold([t, dst](Engine& e_) { return e_.connect1_inl(t, dst); });
+    return connect1_inl(t, dst);
+  }
+  MSIM_HD int connect1_inl(int t, u32 dst) {
     int ks = t_sock(t);
     int node = b(L::B_SK_NODE, ks);
     u64 lat;
@@ -1238,7 +1252,7 @@ MSIM_NOUNROLL
     w(L::W_NEXT_NODE) = 1;
     w(L::W_RESUME) = NONE32;
     for (int k = 0; k < L::NSA; k++) w(L::W_ACC_WAITER, k) = NONE32;
-    int m = spawn(WL::MAIN_KIND, 0, TF_JOINABLE);
+    int m = spawn_inl(WL::MAIN_KIND, 0, TF_JOINABLE);
     w(L::W_MAIN_SLOT) = (u32)m;
     // check_determinism enables the rng log AFTER the Runtime is constructed (runtime/mod.rs:185-187): the base-time
     // draw above is not part of it
@@ -1701,15 +1715,22 @@ MSIM_NOUNROLL
     }
     return true;
   }
+  /// the future returned Ready: `future.await; h.exit()` for a node's init task, drop the future, complete the task
+  MSIM_HD void finish_ready_inl(int t) {
+    if (C::USES_KILL && MSIM_UNLIKELY(t_flags(t) & TF_INIT)) node_exit(t_node(t), t_epoch(t));
+    drop_future(t);
+    t_flags(t) = (t_flags(t) & ~(TF_RUNNING | TF_SCHEDULED)) | TF_COMPLETED;
+    notify_awaiter(t);
+    maybe_free(t);
+  }
   /// run_end: true = the poll was interrupted by time::advance (still RUNNING: it continues after the timers fired)
   MSIM_HD bool run_end(int t, int r) {
     if (MSIM_UNLIKELY(r == POLL_ADVANCE)) return true;
     if (r == POLL_READY) {
-      if (C::USES_KILL && MSIM_UNLIKELY(t_flags(t) & TF_INIT)) node_exit(t_node(t), t_epoch(t));  // `future.await; h.exit()`
-      drop_future(t);
-      t_flags(t) = (t_flags(t) & ~(TF_RUNNING | TF_SCHEDULED)) | TF_COMPLETED;
-      notify_awaiter(t);
-      maybe_free(t);
+      if (C::COLD_FINISH)
+        cold([t](Engine& e_) { e_.finish_ready_inl(t); });
+      else
+        finish_ready_inl(t);
     } else if (MSIM_UNLIKELY(r == POLL_PANIC)) {
       // async-task's guard: close, drop the future, notify the awaiter
       t_flags(t) = (t_flags(t) & ~(TF_RUNNING | TF_SCHEDULED)) | TF_CLOSED;

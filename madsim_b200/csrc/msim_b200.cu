@@ -380,8 +380,8 @@ cudaError_t launch_wl(const KernelArgs& a, dim3 grid, dim3 block, size_t smem, c
   return cudaGetLastError();
 }
 
-int state_bytes_of(uint32_t workload, uint64_t flags = 0) {
-  return with_workload(workload, flags, -1, [](auto wl) { return (int)Layout<typename decltype(wl)::Caps>::BYTES; });
+int state_bytes_of(uint32_t workload, const uint64_t* p = nullptr) {
+  return with_workload(workload, (const u64*)p, -1, [](auto wl) { return (int)Layout<typename decltype(wl)::Caps>::BYTES; });
 }
 
 }  // namespace
@@ -423,7 +423,7 @@ struct msim_batch {
 namespace {
 
 int choose_geometry(msim_batch* b, uint64_t n) {
-  int bytes = state_bytes_of(b->wl.workload, b->wl.p[2]);
+  int bytes = state_bytes_of(b->wl.workload, b->wl.p);
   if (bytes <= 0) return set_err(MSIM_EINVAL, "unknown workload");
   uint32_t s_max = (uint32_t)((b->max_smem - SMEM_HDR) / bytes);
   if (s_max == 0) return set_err(MSIM_EINVAL, "state block of one seed exceeds shared memory");
@@ -488,7 +488,7 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
   b->grid_launched = n_grid;
   dim3 grid(n_grid), block(b->threads);
   const cudaError_t unknown = cudaErrorInvalidDeviceFunction;
-  cudaError_t e = with_workload(b->wl.workload, a.P.p[2], unknown,
+  cudaError_t e = with_workload(b->wl.workload, (const u64*)a.P.p, unknown,
                                 [&](auto wl) { return launch_wl<decltype(wl)>(a, grid, block, b->smem, b->stream); });
   if (e == unknown) return set_err(MSIM_EINVAL, "unknown workload");
   if (e != cudaSuccess) return set_err(MSIM_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
@@ -645,7 +645,7 @@ int msim_workload_load(msim_batch* b, const msim_workload_desc* w) {
   std::string err;
   int rc = make_params(b->cfg, *w, &P, &err);
   if (rc) return set_err(rc, err);
-  if (state_bytes_of(w->workload, w->p[2]) <= 0) return set_err(MSIM_EINVAL, "workload not available on the device");
+  if (state_bytes_of(w->workload, w->p) <= 0) return set_err(MSIM_EINVAL, "workload not available on the device");
   b->wl = *w;
   b->wl.n_nodes = P.n_nodes;
   b->P = P;

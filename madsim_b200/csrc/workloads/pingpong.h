@@ -22,6 +22,7 @@ struct WL_PingPong {
     static constexpr bool USES_CONN2 = false;    // does any task hold two connection ends at once?
     static constexpr bool USES_PMATCH = false;   // does any node use restart_on_panic_matching?
     static constexpr unsigned PMATCH_BASE = 0;  // the panic code bit 0 of a restart_on_panic_matching mask stands for
+    static constexpr bool COLD_SPAWN = MSIM_COLD_DEFAULT & 1, COLD_FINISH = MSIM_COLD_DEFAULT & 2, COLD_CH = MSIM_COLD_DEFAULT & 4;  // once-per-request runtime pieces out of line
     static constexpr int NCONN = 0, NCQ = 1, NACC = 1;
   };
   enum : u32 { K_MAIN = 0, K_SERVER = 1, K_CLIENT = 2 };

@@ -42,6 +42,7 @@ struct WL_TonicT {
     static constexpr bool USES_CONN2 = false;    // does any task hold two connection ends at once?
     static constexpr bool USES_PMATCH = false;   // does any node use restart_on_panic_matching?
     static constexpr unsigned PMATCH_BASE = 0;  // the panic code bit 0 of a restart_on_panic_matching mask stands for
+    static constexpr bool COLD_SPAWN = MSIM_COLD_DEFAULT & 1, COLD_FINISH = MSIM_COLD_DEFAULT & 2, COLD_CH = MSIM_COLD_DEFAULT & 4;  // once-per-request runtime pieces out of line
     static constexpr int NCONN = BIG ? 64 : 32, NCQ = STREAMING ? 4 : 2, NACC = 32;  // a client-streaming call queues header + 3 items at a slow server
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_RSP_BIDI, K_SENDER };

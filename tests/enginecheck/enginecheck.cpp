@@ -152,7 +152,7 @@ extern "C" int enginecheck_run_ml(const msim_config* cfg, const msim_workload_de
   int rc = make_params(*cfg, *wl, &P, &err);
   if (rc) return rc;
   if (lanes == 0) lanes = 1;
-  return with_workload(wl->workload, P.p[2], (int)MSIM_EINVAL, [&](auto w) { return run_wl_ml<decltype(w)>(P, seed_base, n, lanes, out); });
+  return with_workload(wl->workload, P.p, (int)MSIM_EINVAL, [&](auto w) { return run_wl_ml<decltype(w)>(P, seed_base, n, lanes, out); });
 }
 
 extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed_base, uint64_t n,
@@ -162,7 +162,7 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
   std::string err;
   int rc = make_params(*cfg, *wl, &P, &err);
   if (rc) return rc;
-  return with_workload(wl->workload, P.p[2], (int)MSIM_EINVAL, [&](auto w) {
+  return with_workload(wl->workload, P.p, (int)MSIM_EINVAL, [&](auto w) {
     return run_wl<decltype(w)>(P, seed_base, n, S, max_events, out, trace_seed, tr, cap, n_tr);
   });
 }
@@ -179,7 +179,7 @@ extern "C" int enginecheck_determinism_log(const msim_config* cfg, const msim_wo
   std::memcpy(buf.data(), hdr, 8);
   P.dlog = buf.data();
   size_t ntr = 0;
-  rc = with_workload(wl->workload, P.p[2], (int)MSIM_EINVAL,
+  rc = with_workload(wl->workload, P.p, (int)MSIM_EINVAL,
                      [&](auto w) { return run_wl<decltype(w)>(P, seed, 1, 1, 0, result, ~0ull, nullptr, 0, &ntr); });
   std::memcpy(hdr, buf.data(), 8);
   if (n) *n = hdr[0];
@@ -188,5 +188,6 @@ extern "C" int enginecheck_determinism_log(const msim_config* cfg, const msim_wo
 }
 
 extern "C" int enginecheck_state_bytes(uint32_t workload) {
-  return with_workload(workload, 2, -1, [](auto w) { return (int)Layout<typename decltype(w)::Caps>::BYTES; });
+  static const u64 streaming[8] = {0, 0, 2, 0, 0, 0, 0, 1};
+  return with_workload(workload, streaming, -1, [](auto w) { return (int)Layout<typename decltype(w)::Caps>::BYTES; });
 }

@@ -228,21 +228,23 @@ class Batch:
         N.check(self._lib.msim_batch_sync(self._h))
         return self
 
-    def results(self, want_results: bool = True):
-        """→ (results ndarray[n] of SEED_RESULT_DTYPE or None, fail_bitmap uint32[ceil(n/32)], stats dict)"""
+    def results(self, want_results: bool = True, want_summary: bool = True):
+        """→ (results ndarray[n] of SEED_RESULT_DTYPE or None, fail_bitmap uint32[ceil(n/32)], stats dict).
+        want_summary=False skips the device summary (bitmap and stats come back None): for callers that already
+        hold the reduced summary of a sharded run."""
         n = self.n_seeds
         res = np.empty(n, dtype=SEED_RESULT_DTYPE) if want_results else None
-        bitmap = np.zeros((n + 31) // 32, dtype=np.uint32)
+        bitmap = np.zeros((n + 31) // 32, dtype=np.uint32) if want_summary else None
         st = N.MsimStats()
         N.check(
             self._lib.msim_batch_results(
                 self._h,
                 res.ctypes.data_as(C.c_void_p) if want_results else None,
-                bitmap.ctypes.data_as(C.c_void_p),
-                C.byref(st),
+                bitmap.ctypes.data_as(C.c_void_p) if want_summary else None,
+                C.byref(st) if want_summary else None,
             )
         )
-        stats = {k: getattr(st, k) for k, _ in N.MsimStats._fields_ if k != "reserved"}
+        stats = {k: getattr(st, k) for k, _ in N.MsimStats._fields_ if k != "reserved"} if want_summary else None
         return res, bitmap, stats
 
     def trace_hash(self) -> np.ndarray:

@@ -164,6 +164,50 @@ static Async<Unit> kdf_main(Runtime* rt, u64 node, std::shared_ptr<int> dropped)
   co_return {};
 }
 
+// task/mod.rs:1185-1252 spawn_in_future_drop_by_aborting_task / _by_killing_node: a value whose Drop spawns a task; the
+// future that owns it is dropped by the executor (abort / kill), under the dropped task's own context (:262-289)
+struct SpawnOnDrop {
+  std::shared_ptr<u64> dropping_node;  // where the task spawned in drop() found itself (0 = it never ran)
+  std::shared_ptr<bool> dropped;
+  bool armed = true;
+  SpawnOnDrop(std::shared_ptr<u64> n, std::shared_ptr<bool> d) : dropping_node(std::move(n)), dropped(std::move(d)) {}
+  SpawnOnDrop(SpawnOnDrop&& o) noexcept : dropping_node(std::move(o.dropping_node)), dropped(std::move(o.dropped)), armed(o.armed) {
+    o.armed = false;
+  }
+  static Async<Unit> note_node(std::shared_ptr<u64> out) {
+    *out = current_task()->node->id;
+    co_return {};
+  }
+  ~SpawnOnDrop() {
+    if (!armed) return;
+    spawn(note_node(dropping_node));
+    *dropped = true;
+  }
+};
+static Async<Unit> sod_holder(SpawnOnDrop a) {  // node.spawn(async move { drop(a) })
+  (void)a;
+  co_return {};
+}
+static Async<Unit> sod_abort_main(Runtime::NodeHandle node, std::shared_ptr<u64> dn, std::shared_ptr<bool> dropped) {
+  auto h = node.spawn(sod_holder(SpawnOnDrop(dn, dropped)));  // not polled yet: single-threaded runtime
+  h.abort();
+  auto r = co_await h;
+  ASSERT_PANIC(r.is_err() && r.err == Err::Cancelled);
+  co_await sleep(114514 * SEC);  // let the task spawned in A::drop run
+  ASSERT_PANIC(*dropped && *dn == node.id());  // ... under the node of the dropped task
+  co_return {};
+}
+static Async<Unit> sod_kill_main(Runtime* rt, Runtime::NodeHandle node, std::shared_ptr<u64> dn, std::shared_ptr<bool> dropped) {
+  auto h = node.spawn(sod_holder(SpawnOnDrop(dn, dropped)));
+  rt->kill(node.id());
+  auto r = co_await h;
+  ASSERT_PANIC(r.is_err() && r.err == Err::Cancelled);
+  ASSERT_PANIC(*dropped);
+  co_await sleep(114514 * SEC);
+  ASSERT_PANIC(*dn == 0);  // spawning on a killed node succeeds, but the task never runs
+  co_return {};
+}
+
 // task/mod.rs:1141-1155 join_cancelled
 static Async<Unit> jc_main(JoinHandle<Unit> h) {
   h.abort();
@@ -663,6 +707,33 @@ int main() {
     auto dropped = std::make_shared<int>(0);
     n.spawn(kdf_worker(DropProbe(dropped)));
     rt.block_on(kdf_main(&rt, n.id(), dropped));
+  });
+  run_case("task::spawn_in_future_drop_by_aborting_task (task/mod.rs:1185-1217)", [] {
+    Runtime rt;
+    auto n = rt.create_node().build();
+    rt.block_on(sod_abort_main(n, std::make_shared<u64>(0), std::make_shared<bool>(false)));
+  });
+  run_case("task::spawn_in_future_drop_by_killing_node (task/mod.rs:1219-1252)", [] {
+    Runtime rt;
+    auto n = rt.create_node().build();
+    rt.block_on(sod_kill_main(&rt, n, std::make_shared<u64>(0), std::make_shared<bool>(false)));
+  });
+  run_case("buggify::buggify (buggify.rs:39-63)", [] {
+    Runtime rt;
+    GlobalRng& g = rt.rand;
+    CHECK(!g.is_buggify_enabled());
+    CHECK(!g.buggify());  // disabled: false WITHOUT a draw
+    u64 d0 = g.draws();
+    g.enable_buggify();
+    CHECK(g.is_buggify_enabled() && g.draws() == d0);
+    int n25 = 0, n10 = 0;
+    for (int i = 0; i < 1000; i++) n25 += g.buggify();
+    for (int i = 0; i < 1000; i++) n10 += g.buggify_with_prob(0.1);
+    CHECK(n25 >= 200 && n25 < 300);  // 25 %
+    CHECK(n10 >= 50 && n10 < 150);   // 10 %
+    CHECK(g.draws() == d0 + 2000);   // one draw per call while enabled
+    g.disable_buggify();
+    CHECK(!g.is_buggify_enabled() && !g.buggify() && g.draws() == d0 + 2000);
   });
   run_case("task::join_cancelled", [] {
     Runtime rt;

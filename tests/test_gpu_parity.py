@@ -171,6 +171,10 @@ def test_config3_full_65536_seeds_properties():
     assert st["n_unfinished"] == 0
     assert (full["status"] == m.ST_FAIL_CAPACITY).sum() == 0, "no bounded table may overflow at the BASELINE size"
     assert (full["status"] == m.ST_PASS).all()
+    if host_threads() >= 16:  # the whole configuration against the oracle (9.6e8 events: ~10 s of host time)
+        import oracle_py
+
+        assert_same(oracle_py.run_many(cfg, wl, 0, 65536), full, "config 3, all 65536 seeds")
     again, _, _ = run_gpu(cfg, wl, 0, 65536, S=14, L=2)
     assert np.array_equal(full, again)
     parts = [run_gpu(cfg, wl, r * 8192, 8192)[0] for r in range(8)]
@@ -221,10 +225,10 @@ def test_config5_tonic_32768_seeds_kill_restart_chaos(oracle):
     cfg, wl = m.Config(), m.Workload.tonic()
     got, bm, st = run_gpu(cfg, wl, 0, 32768)
     assert st["n_unfinished"] == 0 and st["n_pass"] == 32768 and not bm.any()
-    # a window against the oracle: 8192 seeds (1.8e8 events) where the host has >= 16 threads, else 384
-    k = 8192 if host_threads() >= 16 else 384
-    ref = oracle.run_many(cfg, wl, 20000, k)
-    assert_same(ref, got[20000:20000 + k], "config 5")
+    # against the oracle: ALL 32768 seeds (7.4e8 events, ~10 s) where the host has >= 16 threads, else a 384-seed window
+    lo, k = (0, 32768) if host_threads() >= 16 else (20000, 384)
+    ref = oracle.run_many(cfg, wl, lo, k)
+    assert_same(ref, got[lo:lo + k], "config 5")
     starts, replies, handled = got["user"][:, 1], got["user"][:, 0], got["user"][:, 2]
     assert (starts >= 6).all() and (starts <= 16).all() and (handled >= replies).all() and (replies > 0).all()
     again, _, _ = run_gpu(cfg, wl, 0, 32768, S=9, L=2)

@@ -27,6 +27,7 @@ WL = {
     "raft2s": lambda: (m.Config(), m.Workload.raft(duration_ms=2000)),
     "raftf": lambda: (m.Config(), m.Workload.raft(faults=7)),
     "tonic": lambda: (m.Config(), m.Workload.tonic()),
+    "election": lambda: (m.Config(), m.Workload.election()),
 }
 FIELDS = ("trace_hash", "elapsed_ns", "draws", "ev_pop", "ev_fire", "status", "fail_code")
 

@@ -42,6 +42,15 @@
 
 // Which once-per-request runtime pieces a program runs out of line (Caps::COLD_*): bit 0 spawn, 1 task end, 2 channel link
 // test + connect1.  Programs set their own value; this is the default (and the knob of the code-size experiments).
+#ifndef MSIM_HEAP16_DEFAULT  // timer heap layout of programs whose Caps do not say: 16-byte records (1) or split arrays (0)
+#define MSIM_HEAP16_DEFAULT 1
+#endif
+#ifndef MSIM_HEAP_ASM_SEL
+#define MSIM_HEAP_ASM_SEL 1
+#endif
+#ifndef MSIM_COLD_LIGHT  // 0: every out-of-line call moves the whole register-cached state (kernel experiments)
+#define MSIM_COLD_LIGHT 1
+#endif
 #ifndef MSIM_COLD_DEFAULT
 #define MSIM_COLD_DEFAULT 0
 #endif

@@ -89,9 +89,17 @@ enum : u32 { SPAWN_EP = 0x100, SPAWN_JOINABLE = 0x200, SPAWN_CONN = 0x400, SPAWN
 enum : u32 { NODE_IP = 1, NODE_INIT = 2, NODE_RESTART_ON_PANIC = 4, NODE_PANIC_MATCHING = 8 };
 enum : int { CALL_OK = 1, CALL_TIMEOUT = 2 };
 
+/// Optional Caps members (absent = off).  HEAP16: timer heap entries are 16-byte {deadline, payload} records moved with
+/// one 128-bit shared-memory access instead of a u64 array + a u32 array (12 bytes per entry, two accesses).
+template <class C, class = void>
+struct caps_heap16 { static constexpr bool value = MSIM_HEAP16_DEFAULT; };
+template <class C>
+struct caps_heap16<C, std::void_t<decltype(C::HEAP16)>> { static constexpr bool value = C::HEAP16; };
+
 /// Compile-time layout of one seed's state block for capacities `C` (element offsets per section).
 template <class C>
 struct Layout {
+  static constexpr bool H16 = caps_heap16<C>::value;
   static_assert(C::NT <= 128, "task bitmap is 2 x u64");
   static_assert(C::NMSG <= 64, "message bitmap is 1 x u64");
   static_assert(C::NT < 255 && C::NMSG < 255 && C::NSOCK < 255, "u8 indices");
@@ -102,8 +110,8 @@ struct Layout {
   static constexpr int Q_DRAWS = 6;
   static constexpr int Q_TFREE = 7;    // 2: free-task bitmap
   static constexpr int Q_MFREE = 9;    // free-message bitmap
-  static constexpr int Q_HEAP_DL = 10;                      // [TQ] timer deadlines (implicit binary heap)
-  static constexpr int Q_T_DL0 = Q_HEAP_DL + C::TQ;         // [NT] Sleep deadline of the task's current await
+  static constexpr int Q_HEAP_DL = 10;                      // [TQ] timer deadlines (implicit binary heap); H16: [2*TQ] {deadline, payload} records
+  static constexpr int Q_T_DL0 = Q_HEAP_DL + (H16 ? 2 : 1) * C::TQ;  // [NT] Sleep deadline of the task's current await
   static constexpr int Q_T_DL1 = Q_T_DL0 + C::NT;           // [NT] timeout deadline / generic u64 local
   static constexpr int NTT = C::USES_TIMEOUT ? C::NT : 0;
   static constexpr int Q_T_DL2 = Q_T_DL1 + C::NT;           // [NTT] deadline of the time::timeout scope the future is inside, or NONE64
@@ -125,8 +133,8 @@ struct Layout {
     W_PK_LEN, W_BASE_SECS, W_NEXT_NODE, W_MAIN_SLOT, W_PANIC_CODE, W_RESUME, W_NSCALAR
   };
   static constexpr int W_CLOG_LINK = W_NSCALAR;                 // [NNODE] bit d set: link n->d clogged
-  static constexpr int W_HEAP_PL = W_CLOG_LINK + C::NNODE;      // [TQ]
-  static constexpr int W_T_SPAWN = W_HEAP_PL + C::TQ;           // [NT] spawn index (NONE32 = free slot)
+  static constexpr int W_HEAP_PL = W_CLOG_LINK + C::NNODE;      // [TQ] timer payloads (H16: inside the records, nothing here)
+  static constexpr int W_T_SPAWN = W_HEAP_PL + (H16 ? 0 : C::TQ);  // [NT] spawn index (NONE32 = free slot)
   static constexpr int W_T_AW = W_T_SPAWN + C::NT;              // [NT] awaiter (slot<<20|gen) or NONE32
   static constexpr int W_T_A = W_T_AW + C::NT;                  // [NT] locals
   static constexpr int W_T_B = W_T_A + C::NT;
@@ -260,36 +268,51 @@ struct Engine {
   /// kill / restart / create_node / bind / panic handling ... run OUT OF LINE: one copy per kernel keeps
   /// them off the hot loop's instruction-cache footprint.  The hot loop's registers are spilled to the
   /// state block around the call (store / load); the callee works on an Engine of its own.
-  template <class F>
+  /// Which register-cached fields a path needs: G_RNG r0-r3 + draws; G_QUEUES rq_len, heap_len, status, peak_timers;
+  /// G_CLOCK hash + event counters (`now` always travels as an argument).  A light call moves only its groups.
+  enum : int { G_RNG = 1, G_QUEUES = 2, G_CLOCK = 4, G_ALL = 7 };
+#if !defined(__CUDACC__)
+  int dbg_valid = G_ALL;  // host builds (tests/enginecheck): which groups this Engine holds — a light callee that reached a
+                          // full cold() would write garbage back, so store_g checks
+#endif
+  template <int G, class F>
   static MSIM_NI auto cold_run(unsigned char* sb_, const Params* P_, u64 now_, F f) {
     Engine e_;
     e_.sb = sb_;
     e_.P = P_;
+#if !defined(__CUDACC__)
+    e_.dbg_valid = 0;
+#endif
     e_.tr = nullptr;  // nothing on these paths appends trace records
     e_.tr_cap = 0;
     e_.tr_n = 0;
-    e_.load();
+    e_.template load_g<G>();
     e_.now = now_;
     if constexpr (std::is_void<decltype(f(e_))>::value) {
       f(e_);
-      e_.store();
+      e_.template store_g<G>();
     } else {
       auto r_ = f(e_);
-      e_.store();
+      e_.template store_g<G>();
+      return r_;
+    }
+  }
+  template <int G_, class F>
+  MSIM_HD auto cold_g(F f) {
+    constexpr int G = MSIM_COLD_LIGHT ? G_ : (int)G_ALL;
+    store_g<G>();
+    if constexpr (std::is_void<decltype(cold_run<G>(sb, P, now, f))>::value) {
+      cold_run<G>(sb, P, now, f);
+      load_g<G>();
+    } else {
+      auto r_ = cold_run<G>(sb, P, now, f);
+      load_g<G>();
       return r_;
     }
   }
   template <class F>
   MSIM_HD auto cold(F f) {
-    store();
-    if constexpr (std::is_void<decltype(cold_run(sb, P, now, f))>::value) {
-      cold_run(sb, P, now, f);
-      load();
-    } else {
-      auto r_ = cold_run(sb, P, now, f);
-      load();
-      return r_;
-    }
+    return cold_g<G_ALL>(f);
   }
 
   // ---------------- failure ----------------
@@ -438,8 +461,43 @@ struct Engine {
   }
 
   // ---------------- timer heap (naive_timer over Rust's BinaryHeap) ----------------
-  MSIM_HD u64& h_dl(int i) const { return q(L::Q_HEAP_DL, i); }
-  MSIM_HD u32& h_pl(int i) const { return w(L::W_HEAP_PL, i); }
+  struct HRec {
+    u64 dl;
+    u32 pl;
+  };
+  MSIM_HD u64& h_dl(int i) const { return q(L::Q_HEAP_DL, L::H16 ? 2 * i : i); }
+  MSIM_HD HRec h_get(int i) const {
+    if constexpr (L::H16) {
+#if defined(__CUDA_ARCH__)
+      ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&q(L::Q_HEAP_DL, 2 * i));
+      return HRec{v.x, (u32)v.y};
+#else
+      return HRec{q(L::Q_HEAP_DL, 2 * i), (u32)q(L::Q_HEAP_DL, 2 * i + 1)};
+#endif
+    } else {
+      return HRec{q(L::Q_HEAP_DL, i), w(L::W_HEAP_PL, i)};
+    }
+  }
+  MSIM_HD void h_set(int i, u64 dl, u32 pl) const {
+    if constexpr (L::H16) {
+#if defined(__CUDA_ARCH__)
+      *reinterpret_cast<ulonglong2*>(&q(L::Q_HEAP_DL, 2 * i)) = make_ulonglong2(dl, (u64)pl);
+#else
+      q(L::Q_HEAP_DL, 2 * i) = dl, q(L::Q_HEAP_DL, 2 * i + 1) = pl;
+#endif
+    } else {
+      q(L::Q_HEAP_DL, i) = dl, w(L::W_HEAP_PL, i) = pl;
+    }
+  }
+  /// entry `from` moves to slot `to`; its deadline is already known to the caller
+  MSIM_HD void h_move(int to, int from, u64 dl_from) const {
+    if constexpr (L::H16) {
+      HRec r = h_get(from);
+      h_set(to, r.dl, r.pl);
+    } else {
+      q(L::Q_HEAP_DL, to) = dl_from, w(L::W_HEAP_PL, to) = w(L::W_HEAP_PL, from);
+    }
+  }
   /// Timer::add = BinaryHeap::push: append, sift_up while STRICTLY earlier than the parent
   MSIM_HD void timer_push(u64 dl, u32 pl) {
     u32 pos = heap_len;
@@ -451,51 +509,74 @@ struct Engine {
     if (heap_len > peak_timers) peak_timers = heap_len;
     while (pos > 0) {
       u32 parent = (pos - 1) >> 1;
-      u64 pd = h_dl(parent);
-      if (dl >= pd) break;
-      h_dl(pos) = pd;
-      h_pl(pos) = h_pl(parent);
+      if constexpr (L::H16) {
+        HRec pr = h_get(parent);
+        if (dl >= pr.dl) break;
+        h_set(pos, pr.dl, pr.pl);
+      } else {
+        u64 pd = h_dl(parent);
+        if (dl >= pd) break;
+        h_move(pos, parent, pd);
+      }
       pos = parent;
     }
-    h_dl(pos) = dl;
-    h_pl(pos) = pl;
+    h_set(pos, dl, pl);
   }
   /// BinaryHeap::pop: move the last element to the root, sift_down_to_bottom (on equal
   /// deadlines the RIGHT child is promoted), then sift_up from the leaf.
   MSIM_HD void timer_pop(u64& dl, u32& pl) {
-    dl = h_dl(0);
-    pl = h_pl(0);
+    HRec root = h_get(0);
+    dl = root.dl;
+    pl = root.pl;
     u32 end = --heap_len;
     if (end == 0) return;
-    u64 edl = h_dl(end);
-    u32 epl = h_pl(end);
+    HRec e = h_get(end);
     u32 pos = 0, child = 1;
     while (end >= 2 && child <= end - 2) {
-      u64 dl_l = h_dl(child), dl_r = h_dl(child + 1);
-      if (dl_l >= dl_r) {
-        child++;
-        dl_l = dl_r;
+      if constexpr (L::H16) {
+        HRec l = h_get(child), r = h_get(child + 1);
+#if defined(__CUDA_ARCH__) && MSIM_HEAP_ASM_SEL
+        u64 m_dl;  // ONE 64-bit compare feeds all three selects (the compiler re-derives the deadline select as a min)
+        u32 m_pl, right;
+        asm("{\n\t.reg .pred p;\n\tsetp.ge.u64 p, %3, %4;\n\tselp.b64 %0, %4, %3, p;\n\tselp.b32 %1, %6, %5, p;\n\tselp.u32 %2, 1, 0, p;\n\t}"
+            : "=l"(m_dl), "=r"(m_pl), "=r"(right)
+            : "l"(l.dl), "l"(r.dl), "r"(l.pl), "r"(r.pl));
+        child += right;
+        h_set(pos, m_dl, m_pl);
+#else
+        bool right = l.dl >= r.dl;
+        child += right;
+        h_set(pos, right ? r.dl : l.dl, right ? r.pl : l.pl);
+#endif
+      } else {
+        u64 dl_l = h_dl(child), dl_r = h_dl(child + 1);
+        if (dl_l >= dl_r) {
+          child++;
+          dl_l = dl_r;
+        }
+        h_move(pos, child, dl_l);
       }
-      h_dl(pos) = dl_l;
-      h_pl(pos) = h_pl(child);
       pos = child;
       child = 2 * pos + 1;
     }
     if (child == end - 1) {
-      h_dl(pos) = h_dl(child);
-      h_pl(pos) = h_pl(child);
+      h_move(pos, child, h_dl(child));
       pos = child;
     }
     while (pos > 0) {
       u32 parent = (pos - 1) >> 1;
-      u64 pd = h_dl(parent);
-      if (edl >= pd) break;
-      h_dl(pos) = pd;
-      h_pl(pos) = h_pl(parent);
+      if constexpr (L::H16) {
+        HRec pr = h_get(parent);
+        if (e.dl >= pr.dl) break;
+        h_set(pos, pr.dl, pr.pl);
+      } else {
+        u64 pd = h_dl(parent);
+        if (e.dl >= pd) break;
+        h_move(pos, parent, pd);
+      }
       pos = parent;
     }
-    h_dl(pos) = edl;
-    h_pl(pos) = epl;
+    h_set(pos, e.dl, e.pl);
   }
   /// Timer::expire(limit): fire every timer with deadline <= limit, in heap order.
   /// `now` is NOT touched: advance_to_next_event fires callbacks under the old clock.
@@ -609,7 +690,7 @@ struct Engine {
   /// SM's instruction cache (profiles/r2_etcd, r2_tonic_unary: 63-67 % hit rate) run the once-per-request pieces —
   /// spawn, the end of a task, the link test of a channel send, connect1 — out of line (Caps::COLD_*).
   MSIM_HD int spawn(u32 kind, u32 node, u8 extra_flags) {
-    if (C::COLD_SPAWN) return cold([kind, node, extra_flags](Engine& e_) { return e_.spawn_inl(kind, node, extra_flags); });
+    if (C::COLD_SPAWN) return cold_g<G_QUEUES>([kind, node, extra_flags](Engine& e_) { return e_.spawn_inl(kind, node, extra_flags); });
     return spawn_inl(kind, node, extra_flags);
   }
   MSIM_HD int spawn_inl(u32 kind, u32 node, u8 extra_flags) {
@@ -1012,7 +1093,7 @@ MSIM_NOUNROLL
   }
   /// channel()'s test_link closure: try_send(node, dst).map(|lat| now + lat)
   MSIM_HD u64 ch_test_link(int d) {
-    if (C::COLD_CH) return cold([d](Engine& e_) { return e_.ch_test_link_inl(d); });
+    if (C::COLD_CH) return cold_g<G_RNG>([d](Engine& e_) { return e_.ch_test_link_inl(d); });
     return ch_test_link_inl(d);
   }
   MSIM_HD u64 ch_test_link_inl(int d) {
@@ -1022,7 +1103,7 @@ MSIM_NOUNROLL
   }
   /// NetSim::connect1 after rand_delay.  0 ok / -1 ConnectionRefused
   MSIM_HD int connect1(int t, u32 dst) {
-    if (C::COLD_CH) return cold([t, dst](Engine& e_) { return e_.connect1_inl(t, dst); });
+    if (C::COLD_CH) return cold_g<G_RNG | G_QUEUES>([t, dst](Engine& e_) { return e_.connect1_inl(t, dst); });
     return connect1_inl(t, dst);
   }
   MSIM_HD int connect1_inl(int t, u32 dst) {
@@ -1272,25 +1353,51 @@ MSIM_NOUNROLL
   }
   /// registers <- state block
   MSIM_HD void load() {
-    r0 = q(L::Q_RNG, 0), r1 = q(L::Q_RNG, 1), r2 = q(L::Q_RNG, 2), r3 = q(L::Q_RNG, 3);
+    load_g<G_ALL>();
     now = q(L::Q_NOW);
-    hash = q(L::Q_HASH);
-    draws = q(L::Q_DRAWS);
-    ev_pop = w(L::W_EV_POP), ev_fire = w(L::W_EV_FIRE);
-    heap_len = w(L::W_HEAP_LEN), rq_len = w(L::W_RQ_LEN);
-    status = w(L::W_STATUS);
-    peak_timers = w(L::W_PEAK_TIMERS);
+  }
+  template <int G>
+  MSIM_HD void load_g() {
+#if !defined(__CUDACC__)
+    dbg_valid |= G;
+#endif
+    if (G & G_RNG) {
+      r0 = q(L::Q_RNG, 0), r1 = q(L::Q_RNG, 1), r2 = q(L::Q_RNG, 2), r3 = q(L::Q_RNG, 3);
+      draws = q(L::Q_DRAWS);
+    }
+    if (G & G_CLOCK) {
+      hash = q(L::Q_HASH);
+      ev_pop = w(L::W_EV_POP), ev_fire = w(L::W_EV_FIRE);
+    }
+    if (G & G_QUEUES) {
+      heap_len = w(L::W_HEAP_LEN), rq_len = w(L::W_RQ_LEN);
+      status = w(L::W_STATUS);
+      peak_timers = w(L::W_PEAK_TIMERS);
+    }
   }
   /// registers -> state block
   MSIM_HD void store() {
-    q(L::Q_RNG, 0) = r0, q(L::Q_RNG, 1) = r1, q(L::Q_RNG, 2) = r2, q(L::Q_RNG, 3) = r3;
+    store_g<G_ALL>();
     q(L::Q_NOW) = now;
-    q(L::Q_HASH) = hash;
-    q(L::Q_DRAWS) = draws;
-    w(L::W_EV_POP) = ev_pop, w(L::W_EV_FIRE) = ev_fire;
-    w(L::W_HEAP_LEN) = heap_len, w(L::W_RQ_LEN) = rq_len;
-    w(L::W_STATUS) = status;
-    w(L::W_PEAK_TIMERS) = peak_timers;
+  }
+  template <int G>
+  MSIM_HD void store_g() {
+#if !defined(__CUDACC__)
+    if ((dbg_valid & G) != G) __builtin_trap();  // a light callee reached a heavier cold call
+#endif
+    if (G & G_RNG) {
+      q(L::Q_RNG, 0) = r0, q(L::Q_RNG, 1) = r1, q(L::Q_RNG, 2) = r2, q(L::Q_RNG, 3) = r3;
+      q(L::Q_DRAWS) = draws;
+    }
+    if (G & G_CLOCK) {
+      q(L::Q_HASH) = hash;
+      w(L::W_EV_POP) = ev_pop, w(L::W_EV_FIRE) = ev_fire;
+    }
+    if (G & G_QUEUES) {
+      w(L::W_HEAP_LEN) = heap_len, w(L::W_RQ_LEN) = rq_len;
+      w(L::W_STATUS) = status;
+      w(L::W_PEAK_TIMERS) = peak_timers;
+    }
   }
   MSIM_HD void result(SeedResult& r) {
     r.trace_hash = hash;
@@ -1728,7 +1835,7 @@ MSIM_NOUNROLL
     if (MSIM_UNLIKELY(r == POLL_ADVANCE)) return true;
     if (r == POLL_READY) {
       if (C::COLD_FINISH)
-        cold([t](Engine& e_) { e_.finish_ready_inl(t); });
+        cold_g<(C::USES_KILL ? G_ALL : G_QUEUES)>([t](Engine& e_) { e_.finish_ready_inl(t); });  // (node_exit is a full cold call)
       else
         finish_ready_inl(t);
     } else if (MSIM_UNLIKELY(r == POLL_PANIC)) {

@@ -176,7 +176,7 @@ typedef struct msim_stats {
   double kernel_ms;         /* device time of the step kernels of the last run (CUDA events)            */
   uint32_t launches;        /* kernels launched by the last run                                        */
   uint32_t seeds_per_cta, lanes_per_warp, ctas, smem_bytes;
-  uint32_t reserved;
+  uint32_t escalated;       /* seeds of the last run re-run on the large-capacity variant (capacity escalation)   */
 } msim_stats;
 
 typedef struct msim_batch msim_batch; /* opaque */
@@ -208,6 +208,13 @@ int msim_workload_load(msim_batch* b, const msim_workload_desc* w);
 int msim_batch_set_geometry(msim_batch* b, uint32_t seeds_per_cta, uint32_t lanes_per_warp);
 /* Optional: run on the caller's stream (a cudaStream_t, e.g. torch's current). */
 int msim_batch_set_stream(msim_batch* b, void* cuda_stream);
+/* Capacity escalation (default on).  The reference's executor grows its Vec / BinaryHeap / HashMap without bound
+ * (task/mod.rs:239-259, naive-timer, net/network.rs); a device seed lives in bounded tables and reports
+ * MSIM_ST_FAIL_CAPACITY when one overflows.  With escalation on, the seeds of a run-to-completion batch that
+ * overflowed run again on the program's large-capacity variant (tables 2-4x) before any result is read, and
+ * msim_batch_trace / msim_batch_determinism_log replay such a seed on that variant; msim_stats.escalated counts
+ * them.  A seed that overflows even the large tables keeps MSIM_ST_FAIL_CAPACITY.  on = 0: report, never re-run. */
+int msim_batch_set_capacity_escalation(msim_batch* b, int on);
 
 /* Builder::run seed sweep (builder.rs:129-150): seeds seed_base..seed_base+n.
  * max_events_per_seed = 0 → run every seed to completion in one launch (at most one

@@ -164,6 +164,11 @@ class Batch {
   Batch(const Batch&) = delete;
   Batch& operator=(const Batch&) = delete;
   msim_batch* get() const { return b_; }
+  /// seeds that overflow a bounded table re-run on the program's large-capacity variant (default on)
+  Batch& set_capacity_escalation(bool on) {
+    check(msim_batch_set_capacity_escalation(b_, on ? 1 : 0));
+    return *this;
+  }
 
  private:
   msim_batch* b_ = nullptr;

@@ -100,7 +100,7 @@ pub struct msim_stats {
     pub lanes_per_warp: u32,
     pub ctas: u32,
     pub smem_bytes: u32,
-    pub reserved: u32,
+    pub escalated: u32,
 }
 
 /// opaque `struct msim_batch`
@@ -121,6 +121,7 @@ extern "C" {
     pub fn msim_workload_load(b: *mut msim_batch, w: *const msim_workload_desc) -> c_int;
     pub fn msim_batch_set_geometry(b: *mut msim_batch, seeds_per_cta: u32, lanes_per_warp: u32) -> c_int;
     pub fn msim_batch_set_stream(b: *mut msim_batch, cuda_stream: *mut c_void) -> c_int;
+    pub fn msim_batch_set_capacity_escalation(b: *mut msim_batch, on: c_int) -> c_int;
     pub fn msim_batch_run(b: *mut msim_batch, seed_base: u64, n_seeds: u64, max_events_per_seed: u64) -> c_int;
     pub fn msim_batch_resume(b: *mut msim_batch, max_events_per_seed: u64) -> c_int;
     pub fn msim_batch_run_async(b: *mut msim_batch, seed_base: u64, n_seeds: u64, max_events_per_seed: u64) -> c_int;

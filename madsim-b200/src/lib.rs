@@ -186,6 +186,11 @@ impl Batch {
         check(unsafe { ffi::msim_workload_load(self.raw, &w.0) })?;
         Ok(self)
     }
+    /// seeds that overflow a bounded table re-run on the program's large-capacity variant (default on)
+    pub fn set_capacity_escalation(&mut self, on: bool) -> Result<&mut Self, Error> {
+        check(unsafe { ffi::msim_batch_set_capacity_escalation(self.raw, on as std::os::raw::c_int) })?;
+        Ok(self)
+    }
     /// seeds `seed_base .. seed_base + n`, each to completion
     pub fn run(&mut self, seed_base: u64, n: u64) -> Result<&mut Self, Error> {
         check(unsafe { ffi::msim_batch_run(self.raw, seed_base, n, 0) })?;

@@ -71,7 +71,7 @@ class MsimStats(C.Structure):
         ("lanes_per_warp", C.c_uint32),
         ("ctas", C.c_uint32),
         ("smem_bytes", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("escalated", C.c_uint32),
     ]
 
 
@@ -90,6 +90,7 @@ PROTOTYPES = {
     "msim_workload_load": (C.c_int, [C.c_void_p, C.POINTER(MsimWorkloadDesc)]),
     "msim_batch_set_geometry": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "msim_batch_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msim_batch_set_capacity_escalation": (C.c_int, [C.c_void_p, C.c_int]),
     "msim_batch_run": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "msim_batch_resume": (C.c_int, [C.c_void_p, C.c_uint64]),
     "msim_batch_run_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),

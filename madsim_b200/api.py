@@ -210,6 +210,12 @@ class Batch:
         N.check(self._lib.msim_batch_set_geometry(self._h, seeds_per_cta, lanes_per_warp))
         return self
 
+    def set_capacity_escalation(self, on: bool = True) -> "Batch":
+        """Re-run seeds that overflow a bounded table (ST_FAIL_CAPACITY) on the program's large-capacity variant
+        (default on; stats["escalated"] counts them).  Off: such seeds are reported and never re-run."""
+        N.check(self._lib.msim_batch_set_capacity_escalation(self._h, 1 if on else 0))
+        return self
+
     def set_stream(self, cuda_stream: int) -> "Batch":
         N.check(self._lib.msim_batch_set_stream(self._h, C.c_void_p(cuda_stream)))
         return self
@@ -244,7 +250,7 @@ class Batch:
                 C.byref(st) if want_summary else None,
             )
         )
-        stats = {k: getattr(st, k) for k, _ in N.MsimStats._fields_ if k != "reserved"} if want_summary else None
+        stats = {k: getattr(st, k) for k, _ in N.MsimStats._fields_} if want_summary else None
         return res, bitmap, stats
 
     def trace_hash(self) -> np.ndarray:
@@ -392,7 +398,7 @@ class Builder:
                 if stats is None:
                     stats = dict(st)
                 else:
-                    for k in ("n_seeds", "ev_pop", "ev_fire", "draws", "n_pass", "n_fail", "n_unfinished", "launches"):
+                    for k in ("n_seeds", "ev_pop", "ev_fire", "draws", "n_pass", "n_fail", "n_unfinished", "launches", "escalated"):
                         stats[k] += st[k]
                     stats["kernel_ms"] = max(stats["kernel_ms"], st["kernel_ms"])
         finally:

@@ -101,7 +101,6 @@ template <class C>
 struct Layout {
   static constexpr bool H16 = caps_heap16<C>::value;
   static_assert(C::NT <= 128, "task bitmap is 2 x u64");
-  static_assert(C::NMSG <= 64, "message bitmap is 1 x u64");
   static_assert(C::NT < 255 && C::NMSG < 255 && C::NSOCK < 255, "u8 indices");
   // ---- u64 section ----
   static constexpr int Q_RNG = 0;      // 4
@@ -109,8 +108,9 @@ struct Layout {
   static constexpr int Q_HASH = 5;
   static constexpr int Q_DRAWS = 6;
   static constexpr int Q_TFREE = 7;    // 2: free-task bitmap
-  static constexpr int Q_MFREE = 9;    // free-message bitmap
-  static constexpr int Q_HEAP_DL = 10;                      // [TQ] timer deadlines (implicit binary heap); H16: [2*TQ] {deadline, payload} records
+  static constexpr int MW = (C::NMSG + 63) / 64;
+  static constexpr int Q_MFREE = 9;    // MW: free-message bitmap (one word for every program's default tables)
+  static constexpr int Q_HEAP_DL = (Q_MFREE + MW + 1) & ~1;  // (even: the 16-byte heap records stay aligned)                    // [TQ] timer deadlines (implicit binary heap); H16: [2*TQ] {deadline, payload} records
   static constexpr int Q_T_DL0 = Q_HEAP_DL + (H16 ? 2 : 1) * C::TQ;  // [NT] Sleep deadline of the task's current await
   static constexpr int Q_T_DL1 = Q_T_DL0 + C::NT;           // [NT] timeout deadline / generic u64 local
   static constexpr int NTT = C::USES_TIMEOUT ? C::NT : 0;
@@ -207,6 +207,24 @@ struct Layout {
   static constexpr int W_BASE = 8 * NQ;                 // byte offset of the u32 section
   static constexpr int B_BASE = W_BASE + 4 * NW;        // ... of the u8 section
   static constexpr int BYTES = round_up(B_BASE + NB, 16);  // one seed; a CTA's block is S * BYTES
+};
+
+/// CAPACITY ESCALATION.  Every table of a seed's state block is bounded (Caps); a seed that overflows one ends with
+/// MSIM_ST_FAIL_CAPACITY instead of a wrong result.  BigWL<WL> is the same program over tables 2-4x the size (inside
+/// the index widths the engine packs: task / message slots in 8 bits, the task bitmap, 64 connections); the
+/// host re-runs the overflowed seeds of a batch on it (msim_b200.cu: escalate) — one seed per warp, the general
+/// kernel only, so the batch kernels and their occupancy are untouched.
+template <class C>
+struct BigOf : C {
+  static constexpr int cap_(int v, int m) { return v < m ? v : m; }
+  static constexpr int NT = cap_(4 * C::NT, 128), TQ = 4 * C::TQ, NMSG = cap_(4 * C::NMSG, 192);
+  static constexpr int NSOCK = cap_(2 * C::NSOCK, 64), NREG = cap_(4 * C::NREG, 64), NMBOX = cap_(4 * C::NMBOX, 64);
+  static constexpr int NPARK = cap_(4 * C::NPARK, NT);
+  static constexpr int NCONN = cap_(2 * C::NCONN, 64), NCQ = 2 * C::NCQ, NACC = cap_(2 * C::NACC, 64);
+};
+template <class WL>
+struct BigWL : WL {
+  using Caps = BigOf<typename WL::Caps>;
 };
 
 /// One lane's view of its seed.  `WL` supplies Caps + the state machines; `TRACE` = the variant that
@@ -910,17 +928,29 @@ MSIM_NOUNROLL
   MSIM_HD u8& sk_state(int k) const { return b(L::B_SK_STATE, k); }
   MSIM_HD u32 sk_gen(int k) const { return w(L::W_SK_PORTGEN, k) >> 16; }
   MSIM_HD u32 sk_port(int k) const { return w(L::W_SK_PORTGEN, k) & 0xffff; }
-  MSIM_HD int msg_alloc() {
-    u64 m = q(L::Q_MFREE);
-    if (MSIM_UNLIKELY(!m)) {
+  MSIM_HD int msg_alloc() {  // the lowest free slot
+    if constexpr (L::MW == 1) {
+      u64 m = q(L::Q_MFREE);
+      if (MSIM_UNLIKELY(!m)) {
+        fail_cap(MSIM_CAP_MSGS);
+        return -1;
+      }
+      int i = ffs64(m);
+      q(L::Q_MFREE) = m & (m - 1);
+      return i;
+    } else {  // the large-capacity variants
+      for (int wd = 0; wd < L::MW; wd++) {
+        u64 m = q(L::Q_MFREE, wd);
+        if (m) {
+          q(L::Q_MFREE, wd) = m & (m - 1);
+          return wd * 64 + ffs64(m);
+        }
+      }
       fail_cap(MSIM_CAP_MSGS);
       return -1;
     }
-    int i = ffs64(m);
-    q(L::Q_MFREE) = m & (m - 1);
-    return i;
   }
-  MSIM_HD void msg_free(int m) { q(L::Q_MFREE) |= 1ull << m; }
+  MSIM_HD void msg_free(int m) { q(L::Q_MFREE, L::MW == 1 ? 0 : m >> 6) |= 1ull << (m & 63); }
   MSIM_HD int sock_find(int node, u32 ipk, u32 port) const {
 MSIM_NOUNROLL
     for (int k = 0; k < C::NSOCK; k++)
@@ -1325,7 +1355,10 @@ MSIM_NOUNROLL
       int n = C::NT - wd * 64;
       q(L::Q_TFREE, wd) = n >= 64 ? ~0ull : ((1ull << n) - 1);
     }
-    q(L::Q_MFREE) = C::NMSG >= 64 ? ~0ull : ((1ull << C::NMSG) - 1);
+    for (int wd = 0; wd < L::MW; wd++) {
+      int n = C::NMSG - wd * 64;
+      q(L::Q_MFREE, wd) = n >= 64 ? ~0ull : ((1ull << n) - 1);
+    }
     // TimeRuntime::new (time/mod.rs:26-38): draw #1 of every runtime
     w(L::W_BASE_SECS) = (u32)gen_range_u64(0, 60ull * 60 * 24 * 365);
     // node 0 = "madsim-main" (task/mod.rs:187-198)

@@ -54,6 +54,8 @@ struct KernelArgs {
   uint32_t* next_seed;      // device counter of the seed queue (dynamic mode)
   uint32_t dynamic;         // 1: run-to-completion launch, every warp slot pulls the next seed when its own finishes
   uint32_t lockstep;        // 1: dynamic launch with L >= 2 through the lock-step (phase-aligned) kernel
+  uint32_t* cap_fail;       // device counter: seeds of this launch that ended with MSIM_ST_FAIL_CAPACITY
+  const uint32_t* seed_list;  // general kernel, dynamic: queue entry i is seed offset seed_list[i] (capacity escalation)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
         idx = atomicAdd(a.next_seed, 1u);
         if (idx >= a.n_seeds) break;
       }
+      if (GENERAL && a.seed_list) idx = a.seed_list[idx];  // escalation: the queue holds offsets into the batch
       if (GENERAL && a.resume) {
         e.load();
         if (a.trace) e.tr_n = *a.trace_n;
@@ -176,6 +179,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel(const __grid_
       SeedResult r;
       e.result(r);
       a.results[idx] = r;
+      if (MSIM_UNLIKELY(r.status == MSIM_ST_FAIL_CAPACITY)) atomicAdd(a.cap_fail, 1u);
       if (GENERAL && !a.dynamic) break;
     }
     if (GENERAL && a.trace) *a.trace_n = e.tr_n;
@@ -292,6 +296,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) msim_step_kernel_ml(const __gr
       SeedResult res;
       e.result(res);
       a.results[idx] = res;
+      if (MSIM_UNLIKELY(res.status == MSIM_ST_FAIL_CAPACITY)) atomicAdd(a.cap_fail, 1u);
       live = false;
     }
   }
@@ -380,8 +385,21 @@ cudaError_t launch_wl(const KernelArgs& a, dim3 grid, dim3 block, size_t smem, c
   return cudaGetLastError();
 }
 
-int state_bytes_of(uint32_t workload, const uint64_t* p = nullptr) {
-  return with_workload(workload, (const u64*)p, -1, [](auto wl) { return (int)Layout<typename decltype(wl)::Caps>::BYTES; });
+/// the large-capacity variant of a program (engine.h: BigWL) exists as the GENERAL kernel only
+template <class WL>
+cudaError_t launch_big(const KernelArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  auto k = msim_step_kernel<BigWL<WL>, true>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<grid, block, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+int state_bytes_of(uint32_t workload, const uint64_t* p = nullptr, bool big = false) {
+  return with_workload(workload, (const u64*)p, -1, [big](auto wl) {
+    using W = decltype(wl);
+    return big ? (int)Layout<typename BigWL<W>::Caps>::BYTES : (int)Layout<typename W::Caps>::BYTES;
+  });
 }
 
 }  // namespace
@@ -408,8 +426,17 @@ struct msim_batch {
   size_t d_results_cap = 0;
   unsigned char* d_blob = nullptr;
   size_t d_blob_cap = 0;
-  uint32_t* d_unfinished = nullptr;
-  uint32_t* h_unfinished = nullptr;  // pinned
+  uint32_t* d_unfinished = nullptr;  // [3] unfinished seeds, seed queue head, seeds that overflowed a table
+  uint32_t* h_unfinished = nullptr;  // pinned copy of the three, refreshed after every run-to-completion launch
+  bool escalation = true;            // re-run overflowed seeds on the large-capacity variant (msim_batch_set_capacity_escalation)
+  uint32_t escalated = 0;            // seeds of the last run that went through it
+  cudaEvent_t ev2 = nullptr, ev3 = nullptr;
+  bool esc_pending = false;          // the launch in flight is a run to completion: look at the overflow counter after it
+  // a scratch batch of escalate() / replay_one(): the large-capacity variant, optionally over a list of seed offsets of
+  // ANOTHER batch whose result array it writes into
+  bool big = false;
+  const uint32_t* d_seed_list = nullptr;
+  SeedResult* results_alias = nullptr;
   SeedResult* h_results = nullptr;   // pinned staging
   size_t h_results_cap = 0;
   unsigned long long* d_summary = nullptr;
@@ -423,7 +450,7 @@ struct msim_batch {
 namespace {
 
 int choose_geometry(msim_batch* b, uint64_t n) {
-  int bytes = state_bytes_of(b->wl.workload, b->wl.p);
+  int bytes = state_bytes_of(b->wl.workload, b->wl.p, b->big);
   if (bytes <= 0) return set_err(MSIM_EINVAL, "unknown workload");
   uint32_t s_max = (uint32_t)((b->max_smem - SMEM_HDR) / bytes);
   if (s_max == 0) return set_err(MSIM_EINVAL, "state block of one seed exceeds shared memory");
@@ -470,7 +497,7 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
   a.n_seeds = b->n_seeds;
   a.max_events = max_events;
   a.blob = b->has_checkpoint ? b->d_blob : nullptr;  // a stale image of an earlier run is never handed to a kernel
-  a.results = b->d_results;
+  a.results = b->results_alias ? b->results_alias : b->d_results;
   a.trace = d_trace;
   a.trace_n = d_trace_n;
   a.trace_cap = trace_cap;
@@ -479,17 +506,21 @@ int launch(msim_batch* b, uint64_t max_events, bool resume, msim_trace_rec* d_tr
   a.resume = resume ? 1 : 0;
   a.unfinished = b->d_unfinished;
   a.next_seed = b->d_unfinished + 1;
+  a.cap_fail = b->d_unfinished + 2;
+  a.seed_list = b->d_seed_list;
   // run-to-completion launches balance the load dynamically; bursts keep seed i in block i / S (the checkpoint layout)
   a.dynamic = (max_events == 0 && !resume && !d_trace && b->n_seeds < 0xffffffffull) ? 1 : 0;
   a.lockstep = (a.dynamic && b->user_lockstep && b->L >= 2) ? 1 : 0;
-  CUDA_TRY(cudaMemsetAsync(b->d_unfinished, 0, 2 * sizeof(uint32_t), b->stream));
+  CUDA_TRY(cudaMemsetAsync(b->d_unfinished, 0, 3 * sizeof(uint32_t), b->stream));
   uint32_t n_grid = b->n_blocks;
   if (a.dynamic && n_grid > (uint32_t)b->sm_count) n_grid = (uint32_t)b->sm_count;  // 1 CTA per SM (shared memory)
   b->grid_launched = n_grid;
   dim3 grid(n_grid), block(b->threads);
   const cudaError_t unknown = cudaErrorInvalidDeviceFunction;
-  cudaError_t e = with_workload(b->wl.workload, (const u64*)a.P.p, unknown,
-                                [&](auto wl) { return launch_wl<decltype(wl)>(a, grid, block, b->smem, b->stream); });
+  cudaError_t e = with_workload(b->wl.workload, (const u64*)a.P.p, unknown, [&](auto wl) {
+    using W = decltype(wl);
+    return b->big ? launch_big<W>(a, grid, block, b->smem, b->stream) : launch_wl<W>(a, grid, block, b->smem, b->stream);
+  });
   if (e == unknown) return set_err(MSIM_EINVAL, "unknown workload");
   if (e != cudaSuccess) return set_err(MSIM_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   b->launches++;
@@ -529,6 +560,68 @@ int ensure_buffers(msim_batch* b, uint64_t n, bool need_blob) {
   return MSIM_OK;
 }
 
+struct DevBuf {  // cudaMalloc'd scratch, released on every return path
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+struct BatchGuard {  // a scratch batch, destroyed on every return path
+  msim_batch* p;
+  ~BatchGuard() { msim_batch_destroy(p); }
+};
+
+/// Capacity escalation (engine.h: BigWL).  The seeds of the finished run that ended with MSIM_ST_FAIL_CAPACITY run again
+/// on the large-capacity variant of the program and their records replace the failed ones in the batch's result
+/// array; a seed that overflows even those tables keeps its MSIM_ST_FAIL_CAPACITY.  Rare by construction — the default
+/// tables take the BASELINE configurations without one overflow — so the path is plain: results to the host, the
+/// offsets of the failed seeds back, ONE launch of the general kernel (dynamic queue over the list, one seed per warp).
+int escalate(msim_batch* b) {
+  const uint64_t n = b->n_seeds;
+  if (n >= 0xffffffffull) return MSIM_OK;  // (such a run is not a dynamic launch either)
+  const int bytes = state_bytes_of(b->wl.workload, b->wl.p, true);
+  if (bytes <= 0 || bytes > b->max_smem - SMEM_HDR) return MSIM_OK;  // no larger variant fits an SM: the failures stand
+  CUDA_TRY(cudaMemcpyAsync(b->h_results, b->d_results, n * sizeof(SeedResult), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  std::vector<uint32_t> list;
+  for (uint64_t i = 0; i < n; i++)
+    if (b->h_results[i].status == MSIM_ST_FAIL_CAPACITY) list.push_back((uint32_t)i);
+  if (list.empty()) return MSIM_OK;
+  msim_batch* r = nullptr;
+  int rc = msim_batch_create(&b->cfg, b->device, &r);
+  if (rc) return rc;
+  BatchGuard guard{r};
+  rc = msim_workload_load(r, &b->wl);
+  if (rc) return rc;
+  r->escalation = false;
+  r->big = true;
+  DevBuf d_list;
+  CUDA_TRY(cudaMalloc(&d_list.p, list.size() * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemcpy(d_list.p, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  r->d_seed_list = (const uint32_t*)d_list.p;
+  r->results_alias = b->d_results;
+  r->seed_base = b->seed_base;
+  r->n_seeds = list.size();
+  uint64_t per_sm = (list.size() + r->sm_count - 1) / r->sm_count;
+  uint32_t s_max = (uint32_t)((r->max_smem - SMEM_HDR) / bytes);
+  if (s_max > (uint32_t)(MAX_THREADS / 32)) s_max = MAX_THREADS / 32;
+  r->user_S = (uint32_t)(per_sm < s_max ? per_sm : s_max);
+  r->user_L = 1;
+  rc = choose_geometry(r, r->n_seeds);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(r->ev0, r->stream));
+  rc = launch(r, 0, false, nullptr, nullptr, 0);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(r->ev1, r->stream));
+  CUDA_TRY(cudaStreamSynchronize(r->stream));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
+  b->kernel_ms += ms;
+  b->launches++;
+  b->escalated = (uint32_t)list.size();
+  return MSIM_OK;
+}
+
 int run_impl(msim_batch* b, uint64_t seed_base, uint64_t n, uint64_t max_events, bool sync) {
   if (!b) return set_err(MSIM_EINVAL, "null batch");
   if (!b->has_wl) return set_err(MSIM_ESTATE, "msim_workload_load must be called before msim_batch_run");
@@ -547,6 +640,10 @@ int run_impl(msim_batch* b, uint64_t seed_base, uint64_t n, uint64_t max_events,
   rc = launch(b, max_events, false, nullptr, nullptr, 0);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+  b->escalated = 0;
+  b->esc_pending = max_events == 0;
+  if (b->esc_pending)
+    CUDA_TRY(cudaMemcpyAsync(b->h_unfinished, b->d_unfinished, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
   b->ran = true;
   b->pending = true;
   if (sync) return msim_batch_sync(b);
@@ -616,8 +713,10 @@ int msim_batch_create(const msim_config* cfg, int device, msim_batch** out) {
   b->own_stream = true;
   CUDA_TRY(cudaEventCreate(&b->ev0));
   CUDA_TRY(cudaEventCreate(&b->ev1));
-  CUDA_TRY(cudaMalloc(&b->d_unfinished, 2 * sizeof(uint32_t)));
-  CUDA_TRY(cudaMallocHost(&b->h_unfinished, sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&b->d_unfinished, 3 * sizeof(uint32_t)));
+  CUDA_TRY(cudaMallocHost(&b->h_unfinished, 3 * sizeof(uint32_t)));
+  CUDA_TRY(cudaEventCreate(&b->ev2));
+  CUDA_TRY(cudaEventCreate(&b->ev3));
   guard.p = nullptr;
   *out = b;
   return MSIM_OK;
@@ -635,6 +734,8 @@ void msim_batch_destroy(msim_batch* b) {
   if (b->h_results) cudaFreeHost(b->h_results);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->ev2) cudaEventDestroy(b->ev2);
+  if (b->ev3) cudaEventDestroy(b->ev3);
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -666,6 +767,12 @@ int msim_batch_set_geometry(msim_batch* b, uint32_t seeds_per_cta, uint32_t lane
   return MSIM_OK;
 }
 
+int msim_batch_set_capacity_escalation(msim_batch* b, int on) {
+  if (!b) return set_err(MSIM_EINVAL, "null batch");
+  b->escalation = on != 0;
+  return MSIM_OK;
+}
+
 int msim_batch_set_stream(msim_batch* b, void* cuda_stream) {
   if (!b) return set_err(MSIM_EINVAL, "null batch");
   if (b->own_stream && b->stream) {
@@ -686,6 +793,10 @@ int msim_batch_sync(msim_batch* b) {
   CUDA_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   b->kernel_ms = ms;
   b->pending = false;
+  if (b->esc_pending) {
+    b->esc_pending = false;
+    if (b->escalation && b->h_unfinished[2] > 0) return escalate(b);
+  }
   return MSIM_OK;
 }
 
@@ -728,6 +839,8 @@ int msim_batch_summarize_device(msim_batch* b, void* d_out, size_t bytes) {
   size_t need = 8 * sizeof(unsigned long long) + words * sizeof(uint32_t);
   if (!d_out || bytes < need) return set_err(MSIM_ERANGE, "summary buffer too small");
   CUDA_TRY(cudaSetDevice(b->device));
+  int rc_sync = msim_batch_sync(b);  // the run is complete on the host's side (capacity escalation may follow it)
+  if (rc_sync) return rc_sync;
   unsigned long long init[8] = {0, 0, 0, 0, 0, 0, ~0ull, (unsigned long long)b->n_seeds};
   CUDA_TRY(cudaMemsetAsync(d_out, 0, need, b->stream));
   CUDA_TRY(cudaMemcpyAsync(d_out, init, sizeof(init), cudaMemcpyHostToDevice, b->stream));
@@ -757,6 +870,8 @@ int msim_batch_summarize_sharded(msim_batch* b, void* d_out, size_t bytes, uint3
   size_t need = (8 + (size_t)world) * sizeof(unsigned long long) + words * sizeof(uint32_t);
   if (!d_out || bytes < need) return set_err(MSIM_ERANGE, "summary buffer too small");
   CUDA_TRY(cudaSetDevice(b->device));
+  int rc_sync = msim_batch_sync(b);  // the run is complete on the host's side (capacity escalation may follow it)
+  if (rc_sync) return rc_sync;
   CUDA_TRY(cudaMemsetAsync(d_out, 0, need, b->stream));
   auto* counters = (unsigned long long*)d_out;
   auto* slot = counters + 8 + rank;
@@ -810,6 +925,7 @@ int msim_batch_results(msim_batch* b, msim_seed_result* out, uint32_t* fail_bitm
     stats->lanes_per_warp = b->L;
     stats->ctas = b->grid_launched ? b->grid_launched : b->n_blocks;
     stats->smem_bytes = (uint32_t)b->smem;
+    stats->escalated = b->escalated;
   }
   return MSIM_OK;
 }
@@ -828,30 +944,17 @@ int msim_batch_trace_hash(msim_batch* b, uint64_t* hash) {
 }
 
 namespace {
-struct DevBuf {  // cudaMalloc'd scratch, released on every return path
-  void* p = nullptr;
-  ~DevBuf() {
-    if (p) cudaFree(p);
-  }
-};
 /// Replays ONE seed in a scratch batch that shares config + workload, with the canonical trace and / or the
 /// determinism log switched on (both only exist in the GENERAL kernels).
-int replay_one(msim_batch* b, uint64_t seed, msim_trace_rec* tr_out, size_t tr_cap, size_t* tr_n, uint8_t* log_out,
-               size_t log_cap, size_t* log_n, bool want_log, msim_seed_result* result) {
-  if (!b || !b->has_wl) return set_err(MSIM_ESTATE, "msim_workload_load must be called first");
-  if (tr_cap > 0xffffffffull || log_cap > 0xfffffff0ull) return set_err(MSIM_ERANGE, "capacity too large");
-  CUDA_TRY(cudaSetDevice(b->device));
-  int rc = msim_batch_sync(b);
-  if (rc) return rc;
+int replay_pass(msim_batch* b, bool big, uint64_t seed, msim_trace_rec* tr_out, size_t tr_cap, size_t* tr_n, uint8_t* log_out,
+                size_t log_cap, size_t* log_n, bool want_log, msim_seed_result* result) {
   msim_batch* r = nullptr;
-  rc = msim_batch_create(&b->cfg, b->device, &r);
+  int rc = msim_batch_create(&b->cfg, b->device, &r);
   if (rc) return rc;
-  struct Guard {
-    msim_batch* p;
-    ~Guard() { msim_batch_destroy(p); }
-  } guard{r};
+  BatchGuard guard{r};
   rc = msim_workload_load(r, &b->wl);
   if (rc) return rc;
+  r->big = big;
   r->user_S = 1;
   r->user_L = 1;
   r->seed_base = seed;
@@ -882,9 +985,28 @@ int replay_one(msim_batch* b, uint64_t seed, msim_trace_rec* tr_out, size_t tr_c
     if (log_out && log_cap)
       CUDA_TRY(cudaMemcpy(log_out, (unsigned char*)d_log.p + 8, hdr[0] < log_cap ? hdr[0] : log_cap, cudaMemcpyDeviceToHost));
   }
-  if (result) CUDA_TRY(cudaMemcpy(result, r->d_results, sizeof(SeedResult), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(result, r->d_results, sizeof(SeedResult), cudaMemcpyDeviceToHost));
   if (tr_n) *tr_n = hn;
   if (log_n) *log_n = hdr[0];
+  return MSIM_OK;
+}
+int replay_one(msim_batch* b, uint64_t seed, msim_trace_rec* tr_out, size_t tr_cap, size_t* tr_n, uint8_t* log_out,
+               size_t log_cap, size_t* log_n, bool want_log, msim_seed_result* result) {
+  if (!b || !b->has_wl) return set_err(MSIM_ESTATE, "msim_workload_load must be called first");
+  if (tr_cap > 0xffffffffull || log_cap > 0xfffffff0ull) return set_err(MSIM_ERANGE, "capacity too large");
+  CUDA_TRY(cudaSetDevice(b->device));
+  int rc = msim_batch_sync(b);
+  if (rc) return rc;
+  msim_seed_result res;
+  rc = replay_pass(b, false, seed, tr_out, tr_cap, tr_n, log_out, log_cap, log_n, want_log, &res);
+  if (rc) return rc;
+  const int big_bytes = state_bytes_of(b->wl.workload, b->wl.p, true);
+  if (res.status == MSIM_ST_FAIL_CAPACITY && b->escalation && big_bytes > 0 && big_bytes <= b->max_smem - SMEM_HDR) {
+    // the same escalation a batch run applies: the replay of an overflowed seed comes from the large-capacity variant
+    rc = replay_pass(b, true, seed, tr_out, tr_cap, tr_n, log_out, log_cap, log_n, want_log, &res);
+    if (rc) return rc;
+  }
+  if (result) *result = res;
   return MSIM_OK;
 }
 }  // namespace

@@ -56,6 +56,12 @@ struct MpscState {
   // Sender::closed() waiters (tokio: notify_rx_closed.notify_waiters() when the receiver closes)
   std::vector<std::pair<u64, Waker>> closed_waiters;
   u64 next_closed_key = 1;
+  /// The queued items drop FRONT TO BACK, like the list of the Rust queue (tokio mpsc / concurrent-queue walk head -> tail).
+  /// std::deque's own destructor destroys the full middle buffers first, then the first and the last partial ones — with
+  /// more than ~33 queued connections (16-byte elements, 512-byte buffers) that is a different wake order of their peers.
+  ~MpscState() {
+    while (!q.empty()) q.pop_front();
+  }
   void close_rx() {
     rx_closed = true;
     auto ws = std::move(closed_waiters);

@@ -167,6 +167,23 @@ extern "C" int enginecheck_run(const msim_config* cfg, const msim_workload_desc*
   });
 }
 
+/// The same seeds on the large-capacity variant of the program (engine.h: BigWL — what capacity escalation re-runs
+/// overflowed seeds on).
+extern "C" int enginecheck_run_big(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed_base, uint64_t n,
+                                   msim_seed_result* out, uint64_t trace_seed, msim_trace_rec* tr, size_t cap, size_t* n_tr) {
+  Params P;
+  std::string err;
+  int rc = make_params(*cfg, *wl, &P, &err);
+  if (rc) return rc;
+  return with_workload(wl->workload, P.p, (int)MSIM_EINVAL, [&](auto w) {
+    return run_wl<BigWL<decltype(w)>>(P, seed_base, n, 1, 0, out, trace_seed, tr, cap, n_tr);
+  });
+}
+extern "C" int enginecheck_state_bytes_big(uint32_t workload) {
+  return with_workload(workload, (const u64*)nullptr, -1,
+                       [](auto w) { return (int)Layout<typename BigWL<decltype(w)>::Caps>::BYTES; });
+}
+
 /// The determinism log (rand.rs:64-89) as the replay kernel produces it, from the host build of the same engine.
 extern "C" int enginecheck_determinism_log(const msim_config* cfg, const msim_workload_desc* wl, uint64_t seed, uint8_t* out,
                                            size_t cap, size_t* n, msim_seed_result* result) {

@@ -5,6 +5,8 @@ identical.  `python tests/fuzz_parity.py <rng seed> <seconds>` runs it stand-alo
 runs a short fixed slice."""
 import os
 import random
+
+import numpy as np
 import sys
 import time
 
@@ -54,9 +56,10 @@ def rand_wl(rnd):
 
 
 def run(rng_seed: int, seconds: float, seeds_per_case: int = 12):
-    """→ (cases, seeds compared, seeds skipped for capacity); raises AssertionError on the first mismatch"""
+    """→ (cases, seeds compared, seeds skipped for capacity, seeds escalated to the large-capacity variant);
+    raises AssertionError on the first mismatch"""
     rnd = random.Random(rng_seed)
-    t0, cases, compared, skipped = time.time(), 0, 0, 0
+    t0, cases, compared, skipped, escalated = time.time(), 0, 0, 0, 0
     while time.time() - t0 < seconds:
         cfg, wl = rand_cfg(rnd), rand_wl(rnd)
         # programs that cannot end under this config need a time limit (an unreachable peer retries forever)
@@ -67,15 +70,18 @@ def run(rng_seed: int, seconds: float, seeds_per_case: int = 12):
         base = rnd.randint(0, 10**6)
         ref = o.run_many(cfg, wl, base, seeds_per_case)
         got, _ = o.engine_host(cfg, wl, base, seeds_per_case)
+        for i in np.nonzero(got["status"] == m.ST_FAIL_CAPACITY)[0]:  # what capacity escalation does on the device
+            got[i] = o.engine_host_big(cfg, wl, base + int(i), 1)[0]
+            escalated += 1
         ok = got["status"] != m.ST_FAIL_CAPACITY
         skipped += int((~ok).sum())
         compared += int(ok.sum())
         for i in range(seeds_per_case):
             assert not ok[i] or ref[i] == got[i], f"{wl} {cfg} seed {base + i}:\n oracle {ref[i]}\n engine {got[i]}"
         cases += 1
-    return cases, compared, skipped
+    return cases, compared, skipped, escalated
 
 
 if __name__ == "__main__":
-    print("cases %d, seeds compared %d, skipped (capacity) %d" % run(int(sys.argv[1]) if len(sys.argv) > 1 else 1,
+    print("cases %d, seeds compared %d, skipped (capacity, after escalation) %d, escalated %d" % run(int(sys.argv[1]) if len(sys.argv) > 1 else 1,
                                                                     float(sys.argv[2]) if len(sys.argv) > 2 else 60))

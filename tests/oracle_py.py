@@ -128,6 +128,23 @@ def engine_host(config: Config, wl: Workload, seed_base: int, n: int, seeds_per_
     return out, (buf[: min(nt.value, cap)].copy() if buf is not None else None)
 
 
+def engine_host_big(config: Config, wl: Workload, seed_base: int, n: int, trace_seed: int | None = None, cap: int = 1 << 20):
+    """Host build of the program's large-capacity variant (engine.h BigWL: what capacity escalation re-runs on).
+    → results ndarray, or (results, trace of `trace_seed`) when a trace is asked for"""
+    cfg, d = config.to_c(), wl.to_c()
+    out = np.empty(n, dtype=SEED_RESULT_DTYPE)
+    buf = np.empty(cap, dtype=TRACE_DTYPE) if trace_seed is not None else None
+    nt = C.c_size_t(0)
+    fn = enginecheck().enginecheck_run_big
+    fn.restype = C.c_int
+    rc = fn(C.byref(cfg), C.byref(d), C.c_uint64(seed_base), C.c_uint64(n), out.ctypes.data_as(C.c_void_p),
+            C.c_uint64(trace_seed if trace_seed is not None else 2**64 - 1),
+            buf.ctypes.data_as(C.c_void_p) if buf is not None else None, C.c_size_t(cap), C.byref(nt))
+    if rc != 0:
+        raise RuntimeError(f"enginecheck_run_big failed: {rc}")
+    return out if trace_seed is None else (out, buf[: min(nt.value, cap)].copy())
+
+
 def engine_host_ml(config: Config, wl: Workload, seed_base: int, n: int, lanes: int = 4) -> np.ndarray:
     """Host emulation of the multi-lane batch kernel's phase loop (tests/enginecheck run_wl_ml): `lanes`
     engines in lock step — CPU-side check that the phases execute exactly Engine::step()'s sequence."""

@@ -172,6 +172,39 @@ def test_capacity_overflow_is_reported_not_silent(oracle):
     assert (got["fail_code"][~ok] > 0).all()
 
 
+def test_large_capacity_variant_takes_the_overflowed_seeds(oracle):
+    # capacity escalation (engine.h BigWL): the seeds the default tables refuse run on tables 2-4x the size and must
+    # then agree with the oracle field for field; seeds the default tables hold give the same records on both variants
+    # (the case: rpc timeout below the round trip leaks every response into the mailbox, 300 ms of it)
+    cfg = m.Config()
+    wl = m.Workload.raft(duration_ms=300, rpc_timeout_ms=3, heartbeat_ms=20, election_ms=(40, 80), faults=4)
+    got, _ = oracle.engine_host(cfg, wl, 0, 16, seeds_per_block=4)
+    big = oracle.engine_host_big(cfg, wl, 0, 16)
+    ref = oracle.run_many(cfg, wl, 0, 16)
+    over = got["status"] == m.ST_FAIL_CAPACITY
+    assert over.any() and not over.all(), "the case is meant to overflow the default tables on SOME seeds"
+    for f in FIELDS:
+        assert np.array_equal(big[f], ref[f]), f
+        assert np.array_equal(got[f][~over], big[f][~over]), f
+
+
+@pytest.mark.parametrize("name,cfg,wl,n", [
+    ("pingpong", m.Config(), m.Workload.pingpong(rounds=50), 16),
+    ("chaos", m.Config(), m.Workload.chaos(), 16),
+    ("stream", m.Config(packet_loss_rate=0.2), m.Workload.stream(), 16),
+    ("etcd", m.Config(packet_loss_rate=0.1), m.Workload.etcd(), 8),
+    ("election", m.Config(), m.Workload.election(), 8),
+    ("tonic", m.Config(), m.Workload.tonic(), 4),
+    ("signal", m.Config(), m.Workload.signal(), 16),
+    ("sleep", m.Config(), m.Workload.sleep(), 4),
+])
+def test_large_capacity_variant_is_the_same_program(oracle, name, cfg, wl, n):
+    big = oracle.engine_host_big(cfg, wl, 7, n)
+    ref = oracle.run_many(cfg, wl, 7, n)
+    for f in FIELDS:
+        assert np.array_equal(big[f], ref[f]), (name, f)
+
+
 def test_leaky_config_overflows_loudly(oracle):
     # rpc timeout (3 ms) below the round trip: EVERY response arrives after its caller gave up and
     # stays in the mailbox forever (the reference leaks them too, endpoint.rs:335-350) → the bounded

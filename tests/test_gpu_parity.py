@@ -416,9 +416,70 @@ def test_capacity_overflow_is_reported_not_silent():
     cfg = m.Config()
     wl = m.Workload.raft(duration_ms=3000, rpc_timeout_ms=3, heartbeat_ms=20, election_ms=(40, 80), faults=4)
     res, bm, st = run_gpu(cfg, wl, 0, 32)
-    # MSIM_CAP_MAILBOX (5) or MSIM_CAP_MSGS (4): the leaked responses exhaust one of the two tables first
+    # MSIM_CAP_MAILBOX (5) or MSIM_CAP_MSGS (4): the leaked responses exhaust one of the two tables first — of the
+    # default variant AND of the large-capacity one every seed was escalated to (3 s of leaking)
     assert (res["status"] == m.ST_FAIL_CAPACITY).all() and np.isin(res["fail_code"], [4, 5]).all()
-    assert st["n_fail"] == 32 and bm[0] == 0xFFFFFFFF
+    assert st["n_fail"] == 32 and bm[0] == 0xFFFFFFFF and st["escalated"] == 32
+
+
+LEAKY_300MS = dict(kind="raft", duration_ms=300, rpc_timeout_ms=3, heartbeat_ms=20, election_ms=(40, 80), faults=4)
+
+
+def test_capacity_escalation_reruns_overflowed_seeds(oracle):
+    # 300 ms of the leaking configuration: about half the seeds overflow the default mailbox / message tables and none
+    # the large-capacity variant's.  Escalation off: those seeds say FAIL_CAPACITY.  On (the default): they run again
+    # on the large tables and EVERY seed of the batch agrees with the oracle; nothing else changes.
+    cfg, wl, n = m.Config(), make_wl(LEAKY_300MS), 96
+    ref = oracle.run_many(cfg, wl, 5, n)
+    with m.Batch(cfg, 0) as b:
+        b.load(wl).set_capacity_escalation(False).run(5, n)
+        off, _, st_off = b.results()
+    over = off["status"] == m.ST_FAIL_CAPACITY
+    assert 0 < over.sum() < n and st_off["escalated"] == 0
+    assert_same(ref[~over], off[~over], "escalation off, seeds the default tables hold")
+    got, bm, st = run_gpu(cfg, wl, 5, n)
+    assert st["escalated"] == int(over.sum()) and st["launches"] == 2
+    assert_same(ref, got, "escalation on")
+    assert st["n_pass"] == n and st["n_fail"] == 0 and not bm.any()
+    assert st["ev_pop"] == int(ref["ev_pop"].sum()) and st["draws"] == int(ref["draws"].sum())
+
+
+def test_capacity_escalation_before_the_device_summary(oracle):
+    # the async path of the multi-GPU sweep: run_async, then the device-side summary without reading results first
+    import torch
+
+    cfg, wl, n = m.Config(), make_wl(LEAKY_300MS), 64
+    ref = oracle.run_many(cfg, wl, 0, n)
+    with m.Batch(cfg, 0) as b:
+        b.load(wl).run(0, n, sync=False)
+        out = torch.zeros(sum(D.sharded_layout(n, 1)), dtype=torch.int64, device="cuda:0")
+        b.summarize_sharded_into(out.data_ptr(), out.numel() * 8, 0, 1, 0, n)
+        b.sync()
+        torch.cuda.synchronize()
+        s, bitmap = D.finish_summary(out.cpu().numpy(), n, 1)
+        res, _, st = b.results()
+    assert st["escalated"] > 0 and not bitmap.any()
+    assert s["n_pass"] == n and s["n_fail"] == 0 and s["ev_pop"] == int(ref["ev_pop"].sum())
+    assert_same(ref, res, "async run + sharded summary")
+
+
+def test_replay_of_an_overflowed_seed_comes_from_the_large_variant(oracle):
+    cfg, wl = m.Config(), make_wl(LEAKY_300MS)
+    with m.Batch(cfg, 0) as b:
+        b.load(wl).set_capacity_escalation(False).run(5, 96)
+        off, _, _ = b.results()
+        seed = 5 + int(np.nonzero(off["status"] == m.ST_FAIL_CAPACITY)[0][0])
+        tr_off, rec_off, _ = b.trace(seed)
+        assert rec_off["status"] == m.ST_FAIL_CAPACITY
+        b.set_capacity_escalation(True)
+        tr, rec, n_tr = b.trace(seed)
+        log, rec_l = b.determinism_log(seed)
+    res_o, tr_o, _, _ = oracle.run_seed(cfg, wl, seed, trace=True)
+    assert rec["status"] == m.ST_PASS and rec["trace_hash"] == res_o["trace_hash"]
+    assert n_tr == len(tr_o) and oracle.first_trace_diff(tr_o, tr) is None
+    assert len(tr_off) < len(tr_o) and np.array_equal(tr_o[: len(tr_off)], tr_off)  # the refused run is a prefix
+    log_o, _ = oracle.determinism_log(cfg, wl, seed, "oracle")
+    assert np.array_equal(log, log_o) and rec_l["status"] == m.ST_PASS
 
 
 def test_error_behaviour():

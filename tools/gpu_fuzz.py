@@ -19,7 +19,7 @@ from madsim_b200.api import SEC
 def main():
     rnd = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
     seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 60
-    t0, cases, compared, skipped = time.time(), 0, 0, 0
+    t0, cases, compared, skipped, escalated = time.time(), 0, 0, 0, 0
     by = {}
     while time.time() - t0 < seconds:
         cfg, wl = fz.rand_cfg(rnd), fz.rand_wl(rnd)
@@ -40,8 +40,9 @@ def main():
         cases += 1
         compared += int(ok.sum())
         skipped += int((~ok).sum())
+        escalated += int(st["escalated"])
         by[wl.name()] = by.get(wl.name(), 0) + 1
-    print(f"gpu fuzz: cases {cases}, seeds compared {compared}, skipped (capacity) {skipped}, by program {by}")
+    print(f"gpu fuzz: cases {cases}, seeds compared {compared}, skipped (capacity, after escalation) {skipped}, escalated {escalated}, by program {by}")
 
 
 if __name__ == "__main__":

@@ -214,13 +214,18 @@ struct Layout {
 /// the index widths the engine packs: task / message slots in 8 bits, the task bitmap, 64 connections); the
 /// host re-runs the overflowed seeds of a batch on it (msim_b200.cu: escalate) — one seed per warp, the general
 /// kernel only, so the batch kernels and their occupancy are untouched.
+template <class C, class = void>
+struct caps_big_scale { static constexpr int value = 1; };
+template <class C>
+struct caps_big_scale<C, std::void_t<decltype(C::BIG_SCALE)>> { static constexpr int value = C::BIG_SCALE; };
 template <class C>
 struct BigOf : C {
   static constexpr int cap_(int v, int m) { return v < m ? v : m; }
-  static constexpr int NT = cap_(4 * C::NT, 128), TQ = 4 * C::TQ, NMSG = cap_(4 * C::NMSG, 192);
-  static constexpr int NSOCK = cap_(2 * C::NSOCK, 64), NREG = cap_(4 * C::NREG, 64), NMBOX = cap_(4 * C::NMBOX, 64);
-  static constexpr int NPARK = cap_(4 * C::NPARK, NT);
-  static constexpr int NCONN = cap_(2 * C::NCONN, 64), NCQ = 2 * C::NCQ, NACC = cap_(2 * C::NACC, 64);
+  static constexpr int K = caps_big_scale<C>::value;  // programs whose default tables are cut to the BASELINE size say 2
+  static constexpr int NT = cap_(4 * K * C::NT, 128), TQ = 4 * K * C::TQ, NMSG = cap_(4 * K * C::NMSG, 192);
+  static constexpr int NSOCK = cap_(2 * K * C::NSOCK, 64), NREG = cap_(4 * K * C::NREG, 64), NMBOX = cap_(4 * K * C::NMBOX, 64);
+  static constexpr int NPARK = cap_(4 * K * C::NPARK, NT);
+  static constexpr int NCONN = cap_(2 * K * C::NCONN, 64), NCQ = 2 * C::NCQ, NACC = cap_(2 * K * C::NACC, 64);
 };
 template <class WL>
 struct BigWL : WL {

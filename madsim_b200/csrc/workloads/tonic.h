@@ -31,15 +31,15 @@ struct WL_TonicT {
   enum : int { S_HANDLED = 0, S_CNT, S_ROUND, S_C, S_FAILURES, S_SERVER_CALLS, S_END };  // wl_s scalars
   enum : int { F_REPLIES = 0, F_STARTS, F_ICOUNT, F_NFIELD };           // wl_w per client node
   struct Caps {
-    static constexpr bool HEAP16 = false;  // 16-byte timer records would cost one seed per CTA here (25 -> 24)
-#ifndef MSIM_TONIC_NT
-#define MSIM_TONIC_NT 32
-#define MSIM_TONIC_TQ 64
-#define MSIM_TONIC_NSOCK 24
-#define MSIM_TONIC_NCONN 32
-#define MSIM_TONIC_NACC 32
-#endif
-    static constexpr int NT = BIG ? 80 : MSIM_TONIC_NT, TQ = BIG ? 768 : MSIM_TONIC_TQ, NMSG = 2, NSOCK = BIG ? 24 : MSIM_TONIC_NSOCK, NREG = 1, NMBOX = 1, NNODE = 8, NPARK = 1;
+    static constexpr bool HEAP16 = false;  // split timer arrays: the 16-byte records measured no gain here (profiles/r2k_footprint_experiments.txt)
+    // The unary programs (config 5 and its interceptor variant) run on tables cut to what the BASELINE-size batch needs with
+    // a 1.5x margin (32 768 seeds of config 5 peak at 10 tasks / 11 timers; no overflow at 16 / 32 / 16 sockets / 24
+    // connections): 6 080 B per seed instead of 9 248, i.e. 28 warps per SM instead of 25 (+12 %, profiles/r2n).  A seed of
+    // some other parameter set that needs more re-runs on the large variant (capacity escalation), which for these
+    // programs is 8x / 4x the tables (BIG_SCALE), at least the size of the streaming program's.
+    static constexpr bool SMALL = !BIG && !STREAMING;
+    static constexpr int BIG_SCALE = SMALL ? 2 : 1;
+    static constexpr int NT = BIG ? 80 : SMALL ? 16 : 32, TQ = BIG ? 768 : SMALL ? 32 : 64, NMSG = 2, NSOCK = SMALL ? 16 : 24, NREG = 1, NMBOX = 1, NNODE = 8, NPARK = 1;
     static constexpr int WQ = 0, WW = INTERCEPT ? F_NFIELD : F_ICOUNT, WS = INTERCEPT ? S_END : S_SERVER_CALLS;  // the interceptor counters exist only in that variant
     static constexpr bool USES_JOIN = false;
     static constexpr bool USES_KILL = true;
@@ -51,7 +51,7 @@ struct WL_TonicT {
     static constexpr bool USES_PMATCH = false;   // does any node use restart_on_panic_matching?
     static constexpr unsigned PMATCH_BASE = 0;  // the panic code bit 0 of a restart_on_panic_matching mask stands for
     static constexpr bool COLD_SPAWN = MSIM_COLD_DEFAULT & 1, COLD_FINISH = MSIM_COLD_DEFAULT & 2, COLD_CH = MSIM_COLD_DEFAULT & 4;  // once-per-request runtime pieces out of line
-    static constexpr int NCONN = BIG ? 64 : MSIM_TONIC_NCONN, NCQ = STREAMING ? 4 : 2, NACC = BIG ? 32 : MSIM_TONIC_NACC;  // a client-streaming call queues header + 3 items at a slow server
+    static constexpr int NCONN = BIG ? 64 : SMALL ? 24 : 32, NCQ = STREAMING ? 4 : 2, NACC = SMALL ? 16 : 32;  // a client-streaming call queues header + 3 items at a slow server
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_RSP_BIDI, K_SENDER };
   enum : u32 { NAME = 0x696e6f54u, ERROR_NAME = 0x6f727265u, DELAY_NAME = 0x616c6564u, UNKNOWN_SERVICE = 0x6e6b6e75u };

@@ -399,7 +399,7 @@ def test_builder_jobs_shards_over_the_visible_gpus(oracle):
 
 
 @pytest.mark.parametrize("wl,S,L", [(m.Workload.stream(), 112, 4), (m.Workload.chaos(rounds=12, panics=2), 140, 5),
-                                    (m.Workload.raft(duration_ms=2500, faults=7), 28, 7), (m.Workload.etcd(timeout_rate=0.1), 50, 2),
+                                    (m.Workload.raft(duration_ms=2500, faults=7), 28, 7), (m.Workload.etcd(timeout_rate=0.1), 48, 2),
                                     (m.Workload.tonic(rounds=4), 18, 3), (m.Workload.signal(behavior=1), 100, 32),
                                     (m.Workload.election(timeout_rate=0.05), 60, 4)],
                          ids=["stream", "chaos", "raft", "etcd", "tonic", "signal", "election"])

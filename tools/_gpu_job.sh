@@ -1,11 +1,12 @@
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r2m_gputests.txt; cat gpurun_out/r2m_gputests.txt
-timeout 900 python tools/gpu_fuzz.py 8 150 > gpurun_out/r2m_gpu_fuzz.txt 2>&1; tail -3 gpurun_out/r2m_gpu_fuzz.txt
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/r2p_gputests.txt; cat gpurun_out/r2p_gputests.txt
+timeout 900 python tools/gpu_fuzz.py 9 90 > gpurun_out/r2p_gpu_fuzz.txt 2>&1; tail -2 gpurun_out/r2p_gpu_fuzz.txt
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python bench.py > gpurun_out/r2m_bench.json 2> gpurun_out/r2m_bench.err; python - <<'PY'
+python bench.py > gpurun_out/r2p_bench.json 2> gpurun_out/r2p_bench.err; python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r2m_bench.json').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/r2p_bench.json').read().strip().splitlines()[-1])
 print('value',d['value'],'ms',d['ms_per_step'],'e2e ms',d['e2e']['ms_per_step'],'launches',d['gpu_launches'])
 for c in d.get('configs',[]): print(c['config'],round(c['ms'],3),'ms',round(c['value']/1e9,3),'Gev/s',c['parity_vs_oracle'])
+print(d['roofline']); print(d['cpu_baseline']); print(d.get('clocks'))
 PY

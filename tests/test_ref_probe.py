@@ -21,7 +21,7 @@ def test_committed_probe_expectations_are_the_oracles(oracle):
     mod = _load()
     want = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_probe_expected.json")))["rows"]
     assert mod.expected() == want
-    assert len(want) == 36 and {r["workload"] for r in want} == {"sleep", "pingpong", "chaos", "raft", "raft_faults", "election"}
+    assert len(want) == 42 and {r["workload"] for r in want} == {"sleep", "pingpong", "chaos", "raft", "raft_faults", "election", "etcd"}
 
 
 def test_probe_xoshiro_model_matches_rand_xoshiro_vectors():
@@ -35,6 +35,7 @@ def test_probe_sources_use_only_the_public_reference_api():
     src = open(os.path.join(ROOT, "tools", "ref_probe", "src", "main.rs")).read()
     for needle in ("Runtime::with_seed_and_config", "Endpoint::bind", "Endpoint::connect", "handle.kill", "handle.restart",
                    "handle.pause", "handle.resume", "random::<u64>()", "call_timeout", "add_rpc_handler", "net.clog_node",
-                   "net.clog_link", "advance(", "el.campaign", "el.observe", "el.resign", "SimServer::builder()"):
+                   "net.clog_link", "advance(", "el.campaign", "el.observe", "el.resign", "SimServer::builder()", "kv.put(", "kv.txn(",
+                   "leases.grant(1"):
         assert needle in src
     assert "pub(crate)" not in src and "enable_log" not in src

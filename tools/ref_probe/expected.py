@@ -48,7 +48,7 @@ def expected():
 
     programs = {"sleep": m.Workload.sleep(10**9), "pingpong": m.Workload.pingpong(rounds=1000),
                 "chaos": m.Workload.chaos(rounds=8, period_ms=2000), "raft": m.Workload.raft(),
-                "raft_faults": m.Workload.raft(faults=7), "election": m.Workload.election()}
+                "raft_faults": m.Workload.raft(faults=7), "election": m.Workload.election(), "etcd": m.Workload.etcd()}
     rows = []
     for seed in SEEDS:
         for name, wl in programs.items():

@@ -12,7 +12,9 @@ use madsim::rand::{random, thread_rng, Rng};
 use madsim::runtime::{Handle, Runtime};
 use madsim::task::{spawn, NodeId};
 use madsim::time::{advance, sleep, Instant};
-use madsim_etcd_client::{Client, GetOptions, ProclaimOptions, ResignOptions, SimServer};
+use madsim_etcd_client::{
+    Client, Compare, CompareOp, GetOptions, LeaseGrantOptions, ProclaimOptions, PutOptions, ResignOptions, SimServer, Txn, TxnOp,
+};
 use serde::{Deserialize, Serialize};
 use std::net::SocketAddr;
 use std::sync::atomic::{AtomicU32, Ordering};
@@ -415,6 +417,91 @@ async fn wl_election(hold_s: u64) -> (u64, u64) {
     probe(t0)
 }
 
+// ---------------------------------------------------------------------------------------------
+// oracle/workloads_etcd.hpp wl_etcd_main with its default parameters (BASELINE config 4 at loss 0: 2 clients x 32
+// operations, 50 ms think time, lease 7 with ttl 1 granted by client 0, no injected timeouts): the crate's own SimServer
+// and KvClient / LeaseClient, one connection per request.  Which operation a client issues is drawn from the global RNG
+// exactly as the oracle's etcd_client does (gen_range(0..100), gen_range(0..5)); what the store answers does not move
+// the two numbers this probe prints (every answer is one message), the number and timing of requests does.
+const ETCD_NKEY: u64 = 5;
+const ETCD_LEASE_KEY: u64 = 4;
+const ETCD_LEASE_ID: i64 = 7;
+async fn etcd_client(c: u32, ops: u64, think: Duration) {
+    let client = Client::connect(["10.0.0.1:2379"], None).await.unwrap();
+    let mut kv = client.kv_client();
+    let mut leases = client.lease_client();
+    let mut last_seen = [0u32; ETCD_NKEY as usize];
+    let mut need_grant = c == 0;
+    for i in 0..ops {
+        let r = thread_rng().gen_range(0..100u64);
+        let key = thread_rng().gen_range(0..ETCD_NKEY);
+        let name = format!("k{key}");
+        let value = (c + 1) << 12 | (i as u32 + 1);
+        if need_grant {
+            let opt = LeaseGrantOptions::new().with_id(ETCD_LEASE_ID);
+            if leases.grant(1, Some(opt)).await.is_ok() {
+                need_grant = false;
+            }
+        } else if key == ETCD_LEASE_KEY {
+            if r < 50 {
+                let opt = PutOptions::new().with_lease(ETCD_LEASE_ID);
+                match kv.put(name, value.to_string(), Some(opt)).await {
+                    Ok(_) => last_seen[key as usize] = value,
+                    Err(_) => need_grant = c == 0, // lease not found: client 0 grants it again
+                }
+            } else if let Ok(got) = kv.get(name, None).await {
+                last_seen[key as usize] = got.kvs().first().map_or(0, |kv| kv.value_str().unwrap().parse().unwrap());
+            }
+        } else if r < 40 {
+            if kv.put(name, value.to_string(), None).await.is_ok() {
+                last_seen[key as usize] = value;
+            }
+        } else if r < 75 {
+            if let Ok(got) = kv.get(name, None).await {
+                last_seen[key as usize] = got.kvs().first().map_or(0, |kv| kv.value_str().unwrap().parse().unwrap());
+            }
+        } else if r < 85 {
+            if kv.delete(name, None).await.is_ok() {
+                last_seen[key as usize] = 0;
+            }
+        } else {
+            // compare-and-swap on the value this client saw last (a key it believes absent: create it if it is)
+            let expect = last_seen[key as usize];
+            let when = if expect == 0 {
+                Compare::version(name.clone(), CompareOp::Equal, 0)
+            } else {
+                Compare::value(name.clone(), CompareOp::Equal, expect.to_string())
+            };
+            let txn = Txn::new()
+                .when([when])
+                .and_then([TxnOp::put(name.clone(), value.to_string(), None)])
+                .or_else([TxnOp::get(name, None)]);
+            if let Ok(rsp) = kv.txn(txn).await {
+                if rsp.succeeded() {
+                    last_seen[key as usize] = value;
+                }
+            }
+        }
+        sleep(think).await;
+    }
+}
+async fn wl_etcd(n_clients: u32, ops: u64, think: Duration) -> (u64, u64) {
+    let t0 = Instant::now();
+    let handle = Handle::current();
+    let node = |ip: String| handle.create_node().ip(ip.parse().unwrap()).build();
+    let server = node("10.0.0.1".into());
+    let clients: Vec<_> = (0..n_clients).map(|c| node(format!("10.0.0.{}", 2 + c))).collect();
+    server.spawn(async move {
+        SimServer::builder().serve("10.0.0.1:2379".parse().unwrap()).await.unwrap();
+    });
+    sleep(Duration::from_secs(1)).await;
+    let tasks: Vec<_> = clients.iter().enumerate().map(|(c, n)| n.spawn(etcd_client(c as u32, ops, think))).collect();
+    for t in tasks {
+        t.await.unwrap();
+    }
+    probe(t0)
+}
+
 fn main() {
     for seed in SEEDS {
         let run = |name: &str, out: (u64, u64)| {
@@ -435,5 +522,7 @@ fn main() {
         run("raft_faults", rt.block_on(wl_raft(7))); // BASELINE config 3
         let rt = Runtime::with_seed_and_config(seed, madsim::Config::default());
         run("election", rt.block_on(wl_election(30)));
+        let rt = Runtime::with_seed_and_config(seed, madsim::Config::default());
+        run("etcd", rt.block_on(wl_etcd(2, 32, Duration::from_millis(50)))); // BASELINE config 4, loss 0
     }
 }

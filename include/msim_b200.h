@@ -213,7 +213,9 @@ int msim_batch_set_stream(msim_batch* b, void* cuda_stream);
  * MSIM_ST_FAIL_CAPACITY when one overflows.  With escalation on, the seeds of a run-to-completion batch that
  * overflowed run again on the program's large-capacity variant (tables 2-4x) before any result is read, and
  * msim_batch_trace / msim_batch_determinism_log replay such a seed on that variant; msim_stats.escalated counts
- * them.  A seed that overflows even the large tables keeps MSIM_ST_FAIL_CAPACITY.  on = 0: report, never re-run. */
+ * them.  A seed that overflows even the large tables keeps MSIM_ST_FAIL_CAPACITY.  on = 0: report, never re-run.
+ * on = 2: run EVERY seed of a run-to-completion batch on the large variant straight away (slower — the general kernel
+ * at the large variant's occupancy; for sweeps known to overflow, and how the tests cover the large variants).   */
 int msim_batch_set_capacity_escalation(msim_batch* b, int on);
 
 /* Builder::run seed sweep (builder.rs:129-150): seeds seed_base..seed_base+n.

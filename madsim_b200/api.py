@@ -210,10 +210,11 @@ class Batch:
         N.check(self._lib.msim_batch_set_geometry(self._h, seeds_per_cta, lanes_per_warp))
         return self
 
-    def set_capacity_escalation(self, on: bool = True) -> "Batch":
+    def set_capacity_escalation(self, on=True) -> "Batch":
         """Re-run seeds that overflow a bounded table (ST_FAIL_CAPACITY) on the program's large-capacity variant
-        (default on; stats["escalated"] counts them).  Off: such seeds are reported and never re-run."""
-        N.check(self._lib.msim_batch_set_capacity_escalation(self._h, 1 if on else 0))
+        (default on; stats["escalated"] counts them).  False / 0: such seeds are reported and never re-run.
+        2: every seed of a run-to-completion batch goes to the large variant straight away."""
+        N.check(self._lib.msim_batch_set_capacity_escalation(self._h, int(on)))
         return self
 
     def set_stream(self, cuda_stream: int) -> "Batch":

@@ -429,6 +429,7 @@ struct msim_batch {
   uint32_t* d_unfinished = nullptr;  // [3] unfinished seeds, seed queue head, seeds that overflowed a table
   uint32_t* h_unfinished = nullptr;  // pinned copy of the three, refreshed after every run-to-completion launch
   bool escalation = true;            // re-run overflowed seeds on the large-capacity variant (msim_batch_set_capacity_escalation)
+  bool always_big = false;           // mode 2 of the same call: every seed of a run to completion on the large variant
   uint32_t escalated = 0;            // seeds of the last run that went through it
   cudaEvent_t ev2 = nullptr, ev3 = nullptr;
   bool esc_pending = false;          // the launch in flight is a run to completion: look at the overflow counter after it
@@ -629,6 +630,11 @@ int run_impl(msim_batch* b, uint64_t seed_base, uint64_t n, uint64_t max_events,
   CUDA_TRY(cudaSetDevice(b->device));
   b->seed_base = seed_base;
   b->n_seeds = n;
+  b->big = false;
+  if (b->always_big && max_events == 0) {  // (bursts keep the default variant: the large one has no checkpoint use)
+    const int bytes = state_bytes_of(b->wl.workload, b->wl.p, true);
+    b->big = bytes > 0 && bytes <= b->max_smem - SMEM_HDR;
+  }
   int rc = choose_geometry(b, n);
   if (rc) return rc;
   rc = ensure_buffers(b, n, max_events != 0);
@@ -769,7 +775,9 @@ int msim_batch_set_geometry(msim_batch* b, uint32_t seeds_per_cta, uint32_t lane
 
 int msim_batch_set_capacity_escalation(msim_batch* b, int on) {
   if (!b) return set_err(MSIM_EINVAL, "null batch");
+  if (on < 0 || on > 2) return set_err(MSIM_EINVAL, "capacity escalation mode must be 0, 1 or 2");
   b->escalation = on != 0;
+  b->always_big = on == 2;
   return MSIM_OK;
 }
 
@@ -795,7 +803,7 @@ int msim_batch_sync(msim_batch* b) {
   b->pending = false;
   if (b->esc_pending) {
     b->esc_pending = false;
-    if (b->escalation && b->h_unfinished[2] > 0) return escalate(b);
+    if (b->escalation && !b->big && b->h_unfinished[2] > 0) return escalate(b);
   }
   return MSIM_OK;
 }

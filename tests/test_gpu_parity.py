@@ -444,6 +444,23 @@ def test_capacity_escalation_reruns_overflowed_seeds(oracle):
     assert st["ev_pop"] == int(ref["ev_pop"].sum()) and st["draws"] == int(ref["draws"].sum())
 
 
+@pytest.mark.parametrize("name,cfg,wl,n", [
+    ("sleep", m.Config(), m.Workload.sleep(), 64), ("pingpong", m.Config(packet_loss_rate=0.05), m.Workload.pingpong(rounds=60), 300),
+    ("raft", m.Config(), m.Workload.raft(duration_ms=3000, faults=7), 200), ("chaos", m.Config(), m.Workload.chaos(rounds=10, panics=2), 300),
+    ("stream", m.Config(packet_loss_rate=0.2), m.Workload.stream(), 300), ("etcd", m.Config(packet_loss_rate=0.1), m.Workload.etcd(timeout_rate=0.1), 200),
+    ("tonic", m.Config(), m.Workload.tonic(), 120), ("tonic-streaming", m.Config(), m.Workload.tonic(streaming=True, server_crash=True), 60),
+    ("tonic-timeouts", m.Config(), m.Workload.tonic(timeouts=True), 24), ("signal", m.Config(), m.Workload.signal(), 300),
+    ("election", m.Config(), m.Workload.election(timeout_rate=0.05), 200)])
+def test_large_capacity_variant_of_every_program_on_the_device(oracle, name, cfg, wl, n):
+    # mode 2: the whole batch on BigWL<program> (the kernels capacity escalation launches) — same records as the oracle
+    with m.Batch(cfg, 0) as b:
+        b.load(wl).set_capacity_escalation(2).run(11, n)
+        got, _, st = b.results()
+        small = m.state_bytes(wl.workload)
+    assert_same(oracle.run_many(cfg, wl, 11, n), got, f"large variant of {name}")
+    assert st["escalated"] == 0 and st["smem_bytes"] > small * st["seeds_per_cta"]
+
+
 def test_capacity_escalation_before_the_device_summary(oracle):
     # the async path of the multi-GPU sweep: run_async, then the device-side summary without reading results first
     import torch

@@ -1,6 +1,10 @@
 set -x
 mkdir -p gpurun_out
-nvidia-smi -L
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r2f_bench_n2.json 2> gpurun_out/r2f_bench_n2.err; tail -c 1500 gpurun_out/r2f_bench_n2.json; tail -5 gpurun_out/r2f_bench_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 --ref-seeds 1024 > gpurun_out/r2f_ref_n2.json 2> gpurun_out/r2f_ref_n2.err; tail -c 600 gpurun_out/r2f_ref_n2.json; tail -3 gpurun_out/r2f_ref_n2.err
-python -m pytest tests/test_gpu_parity.py -q -m gpu -k "jobs or cpp_host or sharded" 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/r2q_bench_n2.json 2> gpurun_out/r2q_bench_n2.err
+tail -3 gpurun_out/r2q_bench_n2.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2q_bench_n2.json').read().strip().splitlines()[-1])
+print('n_gpus',d['n_gpus'],'value',d['value'],'ms',d['ms_per_step'],'e2e ms',d['e2e']['ms_per_step'],'launches',d['gpu_launches'])
+for c in d.get('configs',[]): print(c['config'],round(c['ms'],3),'ms',round(c['value']/1e9,3),'Gev/s',c['parity_vs_oracle'])
+PY

@@ -209,6 +209,13 @@ struct Layout {
   static constexpr int BYTES = round_up(B_BASE + NB, 16);  // one seed; a CTA's block is S * BYTES
 };
 
+/// COLD_NOW_SMEM: around an out-of-line call the clock is written to / re-read from the state block instead of staying live in
+/// registers.  Pays where such a call sits on the hot path (ETCD's once-per-request spawn: +7 %), costs elsewhere (TONIC -6 %).
+template <class C, class = void>
+struct caps_cold_now_smem { static constexpr bool value = false; };
+template <class C>
+struct caps_cold_now_smem<C, std::void_t<decltype(C::COLD_NOW_SMEM)>> { static constexpr bool value = C::COLD_NOW_SMEM; };
+
 /// CAPACITY ESCALATION.  Every table of a seed's state block is bounded (Caps); a seed that overflows one ends with
 /// MSIM_ST_FAIL_CAPACITY instead of a wrong result.  BigWL<WL> is the same program over tables 2-4x the size (inside
 /// the index widths the engine packs: task / message slots in 8 bits, the task bitmap, 64 connections); the
@@ -324,12 +331,15 @@ struct Engine {
   MSIM_HD auto cold_g(F f) {
     constexpr int G = MSIM_COLD_LIGHT ? G_ : (int)G_ALL;
     store_g<G>();
+    if (caps_cold_now_smem<C>::value) q(L::Q_NOW) = now;  // the clock goes through the state block too instead of staying live in registers across the call
     if constexpr (std::is_void<decltype(cold_run<G>(sb, P, now, f))>::value) {
       cold_run<G>(sb, P, now, f);
       load_g<G>();
+      if (caps_cold_now_smem<C>::value) now = q(L::Q_NOW);
     } else {
       auto r_ = cold_run<G>(sb, P, now, f);
       load_g<G>();
+      if (caps_cold_now_smem<C>::value) now = q(L::Q_NOW);
       return r_;
     }
   }

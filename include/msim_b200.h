@@ -247,7 +247,8 @@ int msim_batch_summarize_sharded(msim_batch* b, void* d_out, size_t bytes, uint3
                                  uint64_t seed_base, uint64_t n_total);
 /* bytes of per-seed device state of a workload (capacity table in DESIGN.md)                */
 int msim_workload_state_bytes(uint32_t workload);
-/* device pointer of the result array (msim_seed_result[n_seeds]) for zero-copy consumers (torch / NCCL) */
+/* device pointer of the result array (msim_seed_result[n_seeds]) for zero-copy consumers (torch / NCCL); waits for the
+ * run on the host first (a capacity escalation may still have records to replace)                                  */
 int msim_batch_results_device(msim_batch* b, void** dptr, size_t* bytes);
 /* Full canonical trace of ONE seed: replays that seed on the device with the
  * trace ring enabled (replay is the reference's own debugging story:

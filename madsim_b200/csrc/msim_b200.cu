@@ -835,6 +835,8 @@ int msim_batch_resume(msim_batch* b, uint64_t max_events_per_seed) {
 
 int msim_batch_results_device(msim_batch* b, void** dptr, size_t* bytes) {
   if (!b || !b->ran) return set_err(MSIM_ESTATE, "no run yet");
+  int rc = msim_batch_sync(b);  // the records are final only after the run (and a capacity escalation, if any) completed
+  if (rc) return rc;
   if (dptr) *dptr = b->d_results;
   if (bytes) *bytes = b->n_seeds * sizeof(SeedResult);
   return MSIM_OK;

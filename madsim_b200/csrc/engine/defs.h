@@ -48,6 +48,25 @@
 #ifndef MSIM_HEAP_ASM_SEL
 #define MSIM_HEAP_ASM_SEL 1
 #endif
+// kernel experiments: -DMSIM_X_<FLAG>=0/1 overrides a program's own code-placement choice (engine.h X_*); -1 = the program's
+#ifndef MSIM_X_SPAWN
+#define MSIM_X_SPAWN -1
+#endif
+#ifndef MSIM_X_FINISH
+#define MSIM_X_FINISH -1
+#endif
+#ifndef MSIM_X_CH
+#define MSIM_X_CH -1
+#endif
+#ifndef MSIM_X_NOW
+#define MSIM_X_NOW -1
+#endif
+#ifndef MSIM_X_BIND
+#define MSIM_X_BIND -1
+#endif
+#ifndef MSIM_X_H16
+#define MSIM_X_H16 -1
+#endif
 #ifndef MSIM_COLD_LIGHT  // 0: every out-of-line call moves the whole register-cached state (kernel experiments)
 #define MSIM_COLD_LIGHT 1
 #endif

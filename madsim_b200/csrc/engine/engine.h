@@ -99,7 +99,7 @@ struct caps_heap16<C, std::void_t<decltype(C::HEAP16)>> { static constexpr bool 
 /// Compile-time layout of one seed's state block for capacities `C` (element offsets per section).
 template <class C>
 struct Layout {
-  static constexpr bool H16 = caps_heap16<C>::value;
+  static constexpr bool H16 = MSIM_X_H16 < 0 ? caps_heap16<C>::value : (MSIM_X_H16 != 0);
   static_assert(C::NT <= 128, "task bitmap is 2 x u64");
   static_assert(C::NT < 255 && C::NMSG < 255 && C::NSOCK < 255, "u8 indices");
   // ---- u64 section ----
@@ -216,6 +216,11 @@ struct caps_cold_now_smem { static constexpr bool value = false; };
 template <class C>
 struct caps_cold_now_smem<C, std::void_t<decltype(C::COLD_NOW_SMEM)>> { static constexpr bool value = C::COLD_NOW_SMEM; };
 
+template <class C, class = void>
+struct caps_bind_inline { static constexpr bool value = false; };
+template <class C>
+struct caps_bind_inline<C, std::void_t<decltype(C::BIND_INLINE)>> { static constexpr bool value = C::BIND_INLINE; };
+
 /// CAPACITY ESCALATION.  Every table of a seed's state block is bounded (Caps); a seed that overflows one ends with
 /// MSIM_ST_FAIL_CAPACITY instead of a wrong result.  BigWL<WL> is the same program over tables 2-4x the size (inside
 /// the index widths the engine packs: task / message slots in 8 bits, the task bitmap, 64 connections); the
@@ -294,6 +299,13 @@ struct Engine {
   MSIM_HD u32& wl_w(int f, int n) const { return w(L::W_WL, f * C::NNODE + n); }
   MSIM_HD u32& wl_s(int i) const { return w(L::W_WLS, i); }
 
+  // The per-program code-placement choices (Caps), or what a kernel-experiment build puts in their place (-DMSIM_X_<FLAG>=0/1)
+  static constexpr bool X_SPAWN = MSIM_X_SPAWN < 0 ? (bool)C::COLD_SPAWN : (MSIM_X_SPAWN != 0);
+  static constexpr bool X_FINISH = MSIM_X_FINISH < 0 ? (bool)C::COLD_FINISH : (MSIM_X_FINISH != 0);
+  static constexpr bool X_CH = MSIM_X_CH < 0 ? (bool)C::COLD_CH : (MSIM_X_CH != 0);
+  static constexpr bool X_NOW = MSIM_X_NOW < 0 ? caps_cold_now_smem<C>::value : (MSIM_X_NOW != 0);
+  static constexpr bool X_BIND = MSIM_X_BIND < 0 ? caps_bind_inline<C>::value : (MSIM_X_BIND != 0);
+
   // ---------------- rarely executed runtime paths ----------------
   /// kill / restart / create_node / bind / panic handling ... run OUT OF LINE: one copy per kernel keeps
   /// them off the hot loop's instruction-cache footprint.  The hot loop's registers are spilled to the
@@ -331,15 +343,15 @@ struct Engine {
   MSIM_HD auto cold_g(F f) {
     constexpr int G = MSIM_COLD_LIGHT ? G_ : (int)G_ALL;
     store_g<G>();
-    if (caps_cold_now_smem<C>::value) q(L::Q_NOW) = now;  // the clock goes through the state block too instead of staying live in registers across the call
+    if (X_NOW) q(L::Q_NOW) = now;  // the clock goes through the state block too instead of staying live in registers across the call
     if constexpr (std::is_void<decltype(cold_run<G>(sb, P, now, f))>::value) {
       cold_run<G>(sb, P, now, f);
       load_g<G>();
-      if (caps_cold_now_smem<C>::value) now = q(L::Q_NOW);
+      if (X_NOW) now = q(L::Q_NOW);
     } else {
       auto r_ = cold_run<G>(sb, P, now, f);
       load_g<G>();
-      if (caps_cold_now_smem<C>::value) now = q(L::Q_NOW);
+      if (X_NOW) now = q(L::Q_NOW);
       return r_;
     }
   }
@@ -723,7 +735,7 @@ struct Engine {
   /// SM's instruction cache (profiles/r2_etcd, r2_tonic_unary: 63-67 % hit rate) run the once-per-request pieces —
   /// spawn, the end of a task, the link test of a channel send, connect1 — out of line (Caps::COLD_*).
   MSIM_HD int spawn(u32 kind, u32 node, u8 extra_flags) {
-    if (C::COLD_SPAWN) return cold_g<G_QUEUES>([kind, node, extra_flags](Engine& e_) { return e_.spawn_inl(kind, node, extra_flags); });
+    if (X_SPAWN) return cold_g<G_QUEUES>([kind, node, extra_flags](Engine& e_) { return e_.spawn_inl(kind, node, extra_flags); });
     return spawn_inl(kind, node, extra_flags);
   }
   MSIM_HD int spawn_inl(u32 kind, u32 node, u8 extra_flags) {
@@ -999,7 +1011,10 @@ MSIM_NOUNROLL
     w(L::W_SK_PORTGEN, k) = port | ((sk_gen(k) + 1) << 16);
     return k;
   }
+  /// out of line for the programs that bind once per node; inline (Caps::BIND_INLINE) where every client call binds an
+  /// ephemeral endpoint: TONIC +6 %, ELECTION +3 %, but ETCD -7 % (profiles/r2w_bind_modes.txt)
   MSIM_HD int sock_bind(int node, u32 addr) {
+    if constexpr (X_BIND) return sock_bind_inl(node, addr);
     return cold([node, addr](Engine& e_) { return e_.sock_bind_inl(node, addr); });
   }
   MSIM_HD void sock_release_storage(int k) {
@@ -1138,7 +1153,7 @@ MSIM_NOUNROLL
   }
   /// channel()'s test_link closure: try_send(node, dst).map(|lat| now + lat)
   MSIM_HD u64 ch_test_link(int d) {
-    if (C::COLD_CH) return cold_g<G_RNG>([d](Engine& e_) { return e_.ch_test_link_inl(d); });
+    if (X_CH) return cold_g<G_RNG>([d](Engine& e_) { return e_.ch_test_link_inl(d); });
     return ch_test_link_inl(d);
   }
   MSIM_HD u64 ch_test_link_inl(int d) {
@@ -1148,7 +1163,7 @@ MSIM_NOUNROLL
   }
   /// NetSim::connect1 after rand_delay.  0 ok / -1 ConnectionRefused
   MSIM_HD int connect1(int t, u32 dst) {
-    if (C::COLD_CH) return cold_g<G_RNG | G_QUEUES>([t, dst](Engine& e_) { return e_.connect1_inl(t, dst); });
+    if (X_CH) return cold_g<G_RNG | G_QUEUES>([t, dst](Engine& e_) { return e_.connect1_inl(t, dst); });
     return connect1_inl(t, dst);
   }
   MSIM_HD int connect1_inl(int t, u32 dst) {
@@ -1882,7 +1897,7 @@ MSIM_NOUNROLL
   MSIM_HD bool run_end(int t, int r) {
     if (MSIM_UNLIKELY(r == POLL_ADVANCE)) return true;
     if (r == POLL_READY) {
-      if (C::COLD_FINISH)
+      if (X_FINISH)
         cold_g<(C::USES_KILL ? G_ALL : G_QUEUES)>([t](Engine& e_) { e_.finish_ready_inl(t); });  // (node_exit is a full cold call)
       else
         finish_ready_inl(t);

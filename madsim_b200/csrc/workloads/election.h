@@ -42,6 +42,7 @@ struct WL_Election {
     static constexpr bool USES_CONN2 = true;    // the observer keeps its ObserveStream while it makes a kv call
     static constexpr bool USES_PMATCH = false;   // does any node use restart_on_panic_matching?
     static constexpr unsigned PMATCH_BASE = 0;  // the panic code bit 0 of a restart_on_panic_matching mask stands for
+    static constexpr bool BIND_INLINE = true;  // every call binds an ephemeral endpoint: Network::bind inline, +3 % (profiles/r2w_bind_modes.txt)
     static constexpr bool COLD_SPAWN = MSIM_COLD_DEFAULT & 1, COLD_FINISH = MSIM_COLD_DEFAULT & 2, COLD_CH = MSIM_COLD_DEFAULT & 4;  // once-per-request runtime pieces out of line
     static constexpr int NCONN = 6, NCQ = 4, NACC = 4;
   };

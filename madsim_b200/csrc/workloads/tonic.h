@@ -41,6 +41,7 @@ struct WL_TonicT {
     static constexpr int BIG_SCALE = SMALL ? 2 : 1;
     static constexpr int NT = BIG ? 80 : SMALL ? 16 : 32, TQ = BIG ? 768 : SMALL ? 32 : 64, NMSG = 2, NSOCK = SMALL ? 16 : 24, NREG = 1, NMBOX = 1, NNODE = 8, NPARK = 1;
     static constexpr int WQ = 0, WW = INTERCEPT ? F_NFIELD : F_ICOUNT, WS = INTERCEPT ? S_END : S_SERVER_CALLS;  // the interceptor counters exist only in that variant
+    static constexpr bool BIND_INLINE = true;  // every call binds an ephemeral endpoint: Network::bind inline, +6 % (profiles/r2w_bind_modes.txt)
     static constexpr bool USES_JOIN = false;
     static constexpr bool USES_KILL = true;
     static constexpr bool USES_CTRLC = false;  // does any task await signal::ctrl_c()?

@@ -51,7 +51,7 @@ struct WL_TonicT {
     static constexpr bool USES_CONN2 = false;    // does any task hold two connection ends at once?
     static constexpr bool USES_PMATCH = false;   // does any node use restart_on_panic_matching?
     static constexpr unsigned PMATCH_BASE = 0;  // the panic code bit 0 of a restart_on_panic_matching mask stands for
-    static constexpr bool COLD_SPAWN = MSIM_COLD_DEFAULT & 1, COLD_FINISH = MSIM_COLD_DEFAULT & 2, COLD_CH = MSIM_COLD_DEFAULT & 4;  // once-per-request runtime pieces out of line
+    static constexpr bool COLD_SPAWN = true, COLD_FINISH = MSIM_COLD_DEFAULT & 2, COLD_CH = MSIM_COLD_DEFAULT & 4;  // spawn out of line: +3 % (profiles/r2x_placement_sweep.txt)
     static constexpr int NCONN = BIG ? 64 : SMALL ? 24 : 32, NCQ = STREAMING ? 4 : 2, NACC = SMALL ? 16 : 32;  // a client-streaming call queues header + 3 items at a slow server
   };
   enum : u32 { K_MAIN = 0, K_SERVE, K_RSP, K_CLIENT, K_RSP_STREAM, K_RSP_CSTREAM, K_RSP_BIDI, K_SENDER };

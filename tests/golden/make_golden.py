@@ -43,6 +43,12 @@ CASES = {
     "tonic_interceptors": (dict(), dict(kind="tonic", interceptors=True), list(range(4))),
     "election": (dict(), dict(kind="election"), list(range(6))),
     "election_timeouts": (dict(), dict(kind="election", timeout_rate=0.125, hold_s=25), list(range(8))),
+    # seeds 5.. of this leaking configuration overflow the default mailbox / message tables about every other time: the device
+    # answers them from the large-capacity variant (capacity escalation)
+    "raft_leaky_300ms_escalated": (dict(), dict(kind="raft", duration_ms=300, rpc_timeout_ms=3, heartbeat_ms=20, election_ms=(40, 80), faults=4),
+                                   list(range(5, 21))),
+    "tonic_server_crash_slow_links_escalated": (dict(packet_loss_rate=0.05, send_latency_ns=(999000000, 2499000000), time_limit_ns=30 * 10**9),
+                                                dict(kind="tonic", clients=4, think_ns=100 * 10**6, server_crash=True, timeouts=True), [626266]),
 }
 
 

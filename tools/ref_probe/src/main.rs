@@ -15,6 +15,10 @@ use madsim::time::{advance, sleep, Instant};
 use madsim_etcd_client::{
     Client, Compare, CompareOp, GetOptions, LeaseGrantOptions, ProclaimOptions, PutOptions, ResignOptions, SimServer, Txn, TxnOp,
 };
+
+fn parse_value(v: &[u8]) -> u32 {
+    std::str::from_utf8(v).unwrap().parse().unwrap()
+}
 use serde::{Deserialize, Serialize};
 use std::net::SocketAddr;
 use std::sync::atomic::{AtomicU32, Ordering};
@@ -450,7 +454,7 @@ async fn etcd_client(c: u32, ops: u64, think: Duration) {
                     Err(_) => need_grant = c == 0, // lease not found: client 0 grants it again
                 }
             } else if let Ok(got) = kv.get(name, None).await {
-                last_seen[key as usize] = got.kvs().first().map_or(0, |kv| kv.value_str().unwrap().parse().unwrap());
+                last_seen[key as usize] = got.kvs().first().map_or(0, |kv| parse_value(kv.value()));
             }
         } else if r < 40 {
             if kv.put(name, value.to_string(), None).await.is_ok() {
@@ -458,22 +462,18 @@ async fn etcd_client(c: u32, ops: u64, think: Duration) {
             }
         } else if r < 75 {
             if let Ok(got) = kv.get(name, None).await {
-                last_seen[key as usize] = got.kvs().first().map_or(0, |kv| kv.value_str().unwrap().parse().unwrap());
+                last_seen[key as usize] = got.kvs().first().map_or(0, |kv| parse_value(kv.value()));
             }
         } else if r < 85 {
             if kv.delete(name, None).await.is_ok() {
                 last_seen[key as usize] = 0;
             }
         } else {
-            // compare-and-swap on the value this client saw last (a key it believes absent: create it if it is)
+            // compare-and-swap on the value this client saw last ("0" for a key it believes absent: the crate's Equal never
+            // matches a missing key, the oracle's model lets it; either way the answer is one message)
             let expect = last_seen[key as usize];
-            let when = if expect == 0 {
-                Compare::version(name.clone(), CompareOp::Equal, 0)
-            } else {
-                Compare::value(name.clone(), CompareOp::Equal, expect.to_string())
-            };
             let txn = Txn::new()
-                .when([when])
+                .when([Compare::value(name.clone(), CompareOp::Equal, expect.to_string())])
                 .and_then([TxnOp::put(name.clone(), value.to_string(), None)])
                 .or_else([TxnOp::get(name, None)]);
             if let Ok(rsp) = kv.txn(txn).await {

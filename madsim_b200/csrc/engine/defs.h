@@ -67,6 +67,9 @@
 #ifndef MSIM_X_H16
 #define MSIM_X_H16 -1
 #endif
+#ifndef MSIM_X_PORTFIRST
+#define MSIM_X_PORTFIRST -1
+#endif
 #ifndef MSIM_COLD_LIGHT  // 0: every out-of-line call moves the whole register-cached state (kernel experiments)
 #define MSIM_COLD_LIGHT 1
 #endif
